@@ -1,0 +1,184 @@
+/*
+ * sigsdp_mmw.h -- C ABI of the B200-native MMW SDP hot path (libsigsdp_mmw.so).
+ *
+ * The reference (zhouyou-gu/sig-sdp-mmw) is pure Python and has no FFI layer; the
+ * drop-in boundary is the duck-typed solver object handed to
+ * sim_src/alg/binary_search_relaxation.py:10,50,53 (class mmw,
+ * sim_src/alg/mmw.py:12-229, and sdp_solver.rounding, sim_src/alg/sdp_solver.py:18-107).
+ * This header is what a ctypes binding inside that class calls instead of
+ * numpy/scipy; every entry point cites the reference lines it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative SIGSDP_E* code on failure;
+ *     sigsdp_last_error() returns a thread-local message for the last failure.
+ *   - `_host` pointers are host memory, `_dev` pointers are device memory on the
+ *     plan's device.  Handles own their device workspace (cudaMalloc).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).
+ *     No entry point synchronises the device unless its comment says so.
+ *   - indices are int32, the dual / loss / averaging state is always fp64; only the
+ *     sketch block (Omega, Taylor terms, Y_h) follows the solver's dtype.
+ *   - no torch types, no C++ types, no exceptions cross this boundary.
+ */
+#ifndef SIGSDP_MMW_H
+#define SIGSDP_MMW_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SIGSDP_OK 0
+#define SIGSDP_EINVAL (-1)   /* bad argument / malformed CSR / asymmetric Q_asso */
+#define SIGSDP_ECUDA (-2)    /* CUDA runtime error (message has the cudaError string) */
+#define SIGSDP_ENOMEM (-3)
+#define SIGSDP_ESTATE (-4)   /* call order violated (e.g. fetch before iterate) */
+
+#define SIGSDP_F64 0
+#define SIGSDP_F32 1
+
+/* launch modes of sigsdp_solver_iterate */
+#define SIGSDP_MODE_FUSED 0     /* one persistent cooperative kernel per call (default) */
+#define SIGSDP_MODE_STEPWISE 1  /* one kernel per phase / Taylor term (profiling, debugging) */
+
+typedef struct sigsdp_plan sigsdp_plan;     /* graph plan: Z-independent (reused across the binary search) */
+typedef struct sigsdp_solver sigsdp_solver; /* MMW state for one (plan, Z, D, eta, dtype) */
+
+const char* sigsdp_last_error(void);
+int sigsdp_version(void);
+/* number of CUDA devices visible, or a negative error */
+int sigsdp_device_count(void);
+
+/* ------------------------------------------------------------------ plan ----
+ * Replaces mmw._process_state (mmw.py:26-41) and the edge-list set-up
+ * (mmw.py:52-57): T = S_gain^T with association pairs and the diagonal zeroed,
+ * S_sum = T 1, sqrt((T o T) 1), gain-UT / asso-UT edge lists in CSR row-major
+ * order, and the symmetric union pattern (diag + gain + asso) every kernel walks.
+ * Inputs are the reference's `state` tuple (env.py:168-196): two n x n CSR
+ * matrices with sorted, duplicate-free int32 indices and h_max (n).  Built on the
+ * host (native C++), uploaded to `device` (device < 0: host-only plan, for inspecting
+ * the edge lists without a GPU; no solver can be created on it).  Synchronous.
+ * `order`: 0 = keep the caller's node numbering inside the kernels,
+ *          1 = renumber nodes internally for locality (clustered BFS); all inputs
+ *              and outputs of this API stay in the caller's numbering.
+ */
+int sigsdp_plan_create(int64_t n,
+                       const int32_t* S_indptr_host, const int32_t* S_indices_host, const double* S_data_host,
+                       const int32_t* Q_indptr_host, const int32_t* Q_indices_host, const double* Q_data_host,
+                       const double* h_max_host, int device, int order, sigsdp_plan** out);
+void sigsdp_plan_destroy(sigsdp_plan* plan);
+
+/* info[0..7] = n, E_gain, E_asso, nnzL (= n + 2 E), nnz(T), device, order, max row length */
+int sigsdp_plan_info(const sigsdp_plan* plan, int64_t info[8]);
+/* Edge lists in the reference's order (mmw.py:56-57): gain-UT (E_gain) then asso-UT
+ * (E_asso); any pointer may be NULL.  t_ij = T[i,j], t_ji = T[j,i] on gain edges. */
+int sigsdp_plan_edges(const sigsdp_plan* plan, int32_t* gain_i_host, int32_t* gain_j_host,
+                      double* t_ij_host, double* t_ji_host, int32_t* asso_i_host, int32_t* asso_j_host);
+/* S_sum (n) and sqrt of the row sums of T o T (n), mmw.py:34-39 */
+int sigsdp_plan_vectors(const sigsdp_plan* plan, double* S_sum_host, double* t_rownorm_host);
+/* the internal node numbering: perm[new] = old (identity when order = 0) */
+int sigsdp_plan_perm(const sigsdp_plan* plan, int32_t* perm_host);
+
+/* ---------------------------------------------------------------- solver ----
+ * Replaces the state set-up of mmw._run (mmw.py:59-73): C = E_asso + 2K,
+ * Y = 1/C, e_accu = 0, L_accu = 0, X = I, X_avgd = 0, Y_avgd = 0, and norm_H for
+ * this Z (mmw.py:39).  D = Z * rank_radio (mmw.py:180).
+ */
+int sigsdp_solver_create(const sigsdp_plan* plan, int Z, int D, double eta, int dtype, sigsdp_solver** out);
+void sigsdp_solver_destroy(sigsdp_solver* s);
+int sigsdp_solver_reset(sigsdp_solver* s, void* stream);
+int sigsdp_solver_set_mode(sigsdp_solver* s, int mode);
+/* info[0..9] = n, Z, D, Dp (padded row length), C, iterations done, dtype, grid blocks,
+ * threads per block, lanes per row */
+int sigsdp_solver_info(const sigsdp_solver* s, int64_t info[10]);
+
+/* n_iters MMW iterations, each = mmw.py:77-78 (averaging) + 124-142 (dual) +
+ * 144-170 (loss) + 172-197 (sketch: expm_half_randsk 224-229 with scipy's
+ * expm_multiply restated on device, and the edge-only Gram).
+ *   omega_dev != NULL : device pointer to n_iters blocks of raw standard normals,
+ *                       fp64, row-major n x D in the caller's node numbering, block i
+ *                       at omega_dev + i * n * D (what np.random.randn returned in
+ *                       the reference: parity mode);
+ *   omega_dev == NULL : normals are generated on device (Philox4x32-10 keyed by
+ *                       `seed`, counter = (iteration, row, column)).
+ * Asynchronous on `stream` in fused mode; stepwise mode synchronises the stream
+ * after every kernel (it reads the Taylor controller back).
+ */
+int sigsdp_solver_iterate(sigsdp_solver* s, int n_iters, const double* omega_dev, uint64_t seed, void* stream);
+
+/* Synchronising host fetches (caller's node numbering, fp64):
+ *   Y        (C)   dual weights [D | F | H]                    mmw.py:139
+ *   e_accu   (C)                                               mmw.py:137
+ *   Y_avgd   (C)   running sum of Y                            mmw.py:78
+ *   X, X_avgd      diag (n), gain edges (E_gain), asso edges (E_asso); X_avgd is the
+ *                  running SUM (the reference divides by nit at mmw.py:203)
+ *   L_accu         diag (n), gain edges, asso edges            mmw.py:167
+ *   Y_h      (n x D) exp(L_accu/2) Omega of the last iteration mmw.py:180
+ * Any pointer may be NULL. */
+int sigsdp_solver_get_dual(sigsdp_solver* s, double* Y_host, double* e_accu_host, double* Y_avgd_host);
+int sigsdp_solver_get_X(sigsdp_solver* s, int averaged, double* diag_host, double* gain_host, double* asso_host);
+int sigsdp_solver_get_L(sigsdp_solver* s, double* diag_host, double* gain_host, double* asso_host);
+int sigsdp_solver_get_sketch(sigsdp_solver* s, double* Yh_host);
+/* Per-iteration Taylor controller history of the last `count` iterations
+ * (scipy _expm_multiply.py:259-303, _fragment_3_1 :503-558): m_star, s, executed
+ * terms (int32 each) and ||A - mu I||_1, mu (fp64 each).  Any pointer may be NULL. */
+int sigsdp_solver_get_history(sigsdp_solver* s, int count, int32_t* m_star_host, int32_t* s_host,
+                              int32_t* nterms_host, double* a1norm_host, double* mu_host);
+/* Device-timed microseconds of the last `count` iterations, count x 3 row-major:
+ * dual (mmw.py:124-142) | loss (:144-170) | sketch + Gram (:172-197) -- what the
+ * reference logs as mmw_dual / mmw_loss / mmw_expm.  Fused mode only (zeros otherwise). */
+int sigsdp_solver_get_phase_times(sigsdp_solver* s, int count, double* us_host);
+/* total Taylor terms (SpMM passes) executed since create/reset */
+int sigsdp_solver_total_terms(sigsdp_solver* s, int64_t* out);
+
+/* Standard normals of the throughput-mode generator (Philox4x32-10 + Box-Muller),
+ * n x D row-major, for testing its moments.  Synchronising. */
+int sigsdp_debug_normals(uint64_t seed, int64_t iter, int n, int D, int dtype, double* out_host);
+
+/* ------------------------------------------------------- eigen building blocks ---
+ * The Lanczos solvers that replace ARPACK (eigsh mmw.py:115, svds mmw.py:215) run in the
+ * host language over these: a symmetric matrix M on the plan's pattern is materialised in
+ * the solver's scratch, then y = M x is applied to device vectors in the INTERNAL node
+ * numbering (sigsdp_plan_perm), nvec columns, column-major, leading dimension n.
+ *   xavg_matrix : M = scale * X_avgd (running sum)                       mmw.py:203
+ *   gap_prepare : the running means at the start of the next iteration,
+ *                 X~ = (X_avgd + X)/N, Y~ = (Y_avgd + Y)/N, N = iterations done + 1;
+ *                 *e_max_host = max_c e_c(X~) (mmw.py:80-96) and M = L(Y~) (mmw.py:98-113).
+ *                 Synchronising.
+ *   get_matrix  : M's values in the pattern's CSR order (sigsdp_plan_pattern), for tests. */
+int sigsdp_solver_xavg_matrix(sigsdp_solver* s, double scale, void* stream);
+int sigsdp_solver_gap_prepare(sigsdp_solver* s, double* e_max_host, void* stream);
+int sigsdp_solver_symv(sigsdp_solver* s, const double* x_dev, double* y_dev, int nvec, void* stream);
+int sigsdp_solver_get_matrix(sigsdp_solver* s, double* vals_host);
+/* the symmetric union pattern in the internal numbering: rowptr (n+1), col (nnzL) */
+int sigsdp_plan_pattern(const sigsdp_plan* plan, int32_t* rowptr_host, int32_t* col_host);
+
+/* ---------------------------------------------------------------- rounding ---
+ * sdp_solver.rounding_one_attempt (sdp_solver.py:27-107) split at its data
+ * dependence:
+ *  (1) sigsdp_round_project (device): inprod = randv gX^T (:56), the per-user slot
+ *      preference order argsort(-inprod, axis=0) (:57) and the visit key ||gX_k|| (:52);
+ *      gX_dev (n x r, row-major fp64), randv_dev (Z x r, rows already normalised :49),
+ *      pref_dev (n x Z int32, user-major), norm_dev (n).
+ *  (2) sigsdp_round_greedy (host, native, O(nnz Z)): the sequential feasibility pass
+ *      (:70-101) on sparse rows instead of toarray(); `rank` is the visit order
+ *      argsort(-norm).  z_vec[k] = slot or -1 when unassigned; returns the number of
+ *      unassigned users in *remainder (the caller draws their random slots, :104-105).
+ *  (3) sigsdp_round_conflicts (device): rounding.py:56-66 in sparse form: per-user
+ *      same-slot interference I_k, #users with I_k > h_max_k, #association pairs
+ *      sharing a slot.  counts[0] = #violations, counts[1] = #asso conflicts.
+ */
+int sigsdp_round_project(const sigsdp_plan* plan, const double* gX_dev, int r, const double* randv_dev, int Z,
+                         int32_t* pref_dev, double* norm_dev, void* stream);
+int sigsdp_round_greedy(int64_t n, int Z,
+                        const int32_t* S_indptr_host, const int32_t* S_indices_host, const double* S_data_host,
+                        const int32_t* Q_indptr_host, const int32_t* Q_indices_host, const double* Q_data_host,
+                        const double* h_max_host, const int32_t* rank_host, const int32_t* pref_host,
+                        int32_t* z_vec_host, int64_t* remainder);
+int sigsdp_round_conflicts(const sigsdp_plan* plan, const int32_t* z_dev, double* I_dev_or_null,
+                           int64_t counts_host[2], void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIGSDP_MMW_H */

@@ -1,0 +1,241 @@
+"""ctypes binding of libsigsdp_mmw.so (include/sigsdp_mmw.h).  There is no CPU
+fallback: if the library is missing or a call fails, this raises."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsigsdp_mmw.so")
+
+F64, F32 = 0, 1
+MODE_FUSED, MODE_STEPWISE = 0, 1
+
+_lib = None
+
+
+class SigSdpError(RuntimeError):
+    pass
+
+
+def _p(arr, ctype):
+    return arr.ctypes.data_as(C.POINTER(ctype)) if arr is not None else None
+
+
+def load():
+    """Load the shared library (build it first with ``python -m sig_sdp_mmw_b200.build``
+    or ``__graft_entry__.build()``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SigSdpError("%s not found: build it with `python -m sig_sdp_mmw_b200.build` "
+                          "(there is no CPU fallback)" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    i32p, i64p, f64p, vp = C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_double), C.c_void_p
+    lib.sigsdp_last_error.restype = C.c_char_p
+    lib.sigsdp_version.restype = C.c_int
+    lib.sigsdp_device_count.restype = C.c_int
+    sigs = {
+        "sigsdp_plan_create": [C.c_int64, i32p, i32p, f64p, i32p, i32p, f64p, f64p, C.c_int, C.c_int, C.POINTER(vp)],
+        "sigsdp_plan_info": [vp, i64p],
+        "sigsdp_plan_edges": [vp, i32p, i32p, f64p, f64p, i32p, i32p],
+        "sigsdp_plan_vectors": [vp, f64p, f64p],
+        "sigsdp_plan_perm": [vp, i32p],
+        "sigsdp_solver_create": [vp, C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(vp)],
+        "sigsdp_solver_reset": [vp, vp],
+        "sigsdp_solver_set_mode": [vp, C.c_int],
+        "sigsdp_solver_info": [vp, i64p],
+        "sigsdp_solver_iterate": [vp, C.c_int, vp, C.c_uint64, vp],
+        "sigsdp_solver_get_dual": [vp, f64p, f64p, f64p],
+        "sigsdp_solver_get_X": [vp, C.c_int, f64p, f64p, f64p],
+        "sigsdp_solver_get_L": [vp, f64p, f64p, f64p],
+        "sigsdp_solver_get_sketch": [vp, f64p],
+        "sigsdp_solver_get_history": [vp, C.c_int, i32p, i32p, i32p, f64p, f64p],
+        "sigsdp_solver_total_terms": [vp, i64p],
+        "sigsdp_solver_get_phase_times": [vp, C.c_int, f64p],
+        "sigsdp_solver_xavg_matrix": [vp, C.c_double, vp],
+        "sigsdp_solver_gap_prepare": [vp, f64p, vp],
+        "sigsdp_solver_symv": [vp, vp, vp, C.c_int, vp],
+        "sigsdp_solver_get_matrix": [vp, f64p],
+        "sigsdp_plan_pattern": [vp, i32p, i32p],
+        "sigsdp_debug_normals": [C.c_uint64, C.c_int64, C.c_int, C.c_int, C.c_int, f64p],
+        "sigsdp_round_project": [vp, vp, C.c_int, vp, C.c_int, vp, vp, vp],
+        "sigsdp_round_greedy": [C.c_int64, C.c_int, i32p, i32p, f64p, i32p, i32p, f64p, f64p, i32p, i32p, i32p, i64p],
+        "sigsdp_round_conflicts": [vp, vp, vp, i64p, vp],
+    }
+    for name, args in sigs.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = C.c_int
+    lib.sigsdp_plan_destroy.argtypes = [vp]
+    lib.sigsdp_plan_destroy.restype = None
+    lib.sigsdp_solver_destroy.argtypes = [vp]
+    lib.sigsdp_solver_destroy.restype = None
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise SigSdpError("libsigsdp_mmw error %d: %s" % (rc, load().sigsdp_last_error().decode()))
+
+
+def csr_arrays(M):
+    """(indptr int32, indices int32, data float64) of a scipy matrix as canonical CSR
+    (sorted, duplicates summed) without touching the caller's object."""
+    import scipy.sparse as sp
+    M = sp.csr_matrix(M, copy=False)
+    if not M.has_canonical_format:
+        M = M.copy()
+        M.sum_duplicates()
+    return (np.ascontiguousarray(M.indptr, dtype=np.int32), np.ascontiguousarray(M.indices, dtype=np.int32),
+            np.ascontiguousarray(M.data, dtype=np.float64))
+
+
+class Plan:
+    """Graph plan (Z-independent), see sigsdp_plan_create."""
+
+    def __init__(self, state, device=0, order=0):
+        lib = load()
+        S, Q, h = state
+        n = S.shape[0]
+        if S.shape != (n, n) or Q.shape != (n, n) or np.asarray(h).shape != (n,):
+            raise ValueError("state must be (S_gain n x n, Q_asso n x n, h_max (n,))")
+        self._S = csr_arrays(S)
+        self._Q = csr_arrays(Q)
+        self._h = np.ascontiguousarray(np.asarray(h, dtype=np.float64))
+        self.handle = C.c_void_p()
+        check(lib.sigsdp_plan_create(n, _p(self._S[0], C.c_int32), _p(self._S[1], C.c_int32), _p(self._S[2], C.c_double),
+                                     _p(self._Q[0], C.c_int32), _p(self._Q[1], C.c_int32), _p(self._Q[2], C.c_double),
+                                     _p(self._h, C.c_double), device, order, C.byref(self.handle)))
+        info = (C.c_int64 * 8)()
+        check(lib.sigsdp_plan_info(self.handle, info))
+        self.n, self.E_g, self.E_a, self.nnz, self.nnzT, self.device, self.order, self.max_row = [int(x) for x in info]
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                load().sigsdp_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def edges(self):
+        gi = np.empty(self.E_g, np.int32); gj = np.empty(self.E_g, np.int32)
+        tij = np.empty(self.E_g); tji = np.empty(self.E_g)
+        ai = np.empty(self.E_a, np.int32); aj = np.empty(self.E_a, np.int32)
+        check(load().sigsdp_plan_edges(self.handle, _p(gi, C.c_int32), _p(gj, C.c_int32), _p(tij, C.c_double),
+                                       _p(tji, C.c_double), _p(ai, C.c_int32), _p(aj, C.c_int32)))
+        return gi, gj, tij, tji, ai, aj
+
+    def vectors(self):
+        a = np.empty(self.n); b = np.empty(self.n)
+        check(load().sigsdp_plan_vectors(self.handle, _p(a, C.c_double), _p(b, C.c_double)))
+        return a, b
+
+    def perm(self):
+        p = np.empty(self.n, np.int32)
+        check(load().sigsdp_plan_perm(self.handle, _p(p, C.c_int32)))
+        return p
+
+    def pattern(self):
+        rp = np.empty(self.n + 1, np.int32); col = np.empty(self.nnz, np.int32)
+        check(load().sigsdp_plan_pattern(self.handle, _p(rp, C.c_int32), _p(col, C.c_int32)))
+        return rp, col
+
+
+class Solver:
+    """MMW state for one (plan, Z, D, eta, dtype), see sigsdp_solver_create."""
+
+    def __init__(self, plan, Z, D, eta, dtype=F64, mode=MODE_FUSED):
+        lib = load()
+        self.plan = plan
+        self.handle = C.c_void_p()
+        check(lib.sigsdp_solver_create(plan.handle, int(Z), int(D), float(eta), int(dtype), C.byref(self.handle)))
+        if mode != MODE_FUSED:
+            check(lib.sigsdp_solver_set_mode(self.handle, mode))
+        self.Z, self.D = int(Z), int(D)
+        i = self.info()
+        self.Dp, self.C, self.grid, self.threads, self.lanes = i["Dp"], i["C"], i["grid"], i["threads"], i["lanes"]
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                load().sigsdp_solver_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def info(self):
+        a = (C.c_int64 * 10)()
+        check(load().sigsdp_solver_info(self.handle, a))
+        keys = ["n", "Z", "D", "Dp", "C", "iters", "dtype", "grid", "threads", "lanes"]
+        return dict(zip(keys, [int(x) for x in a]))
+
+    def reset(self, stream=None):
+        check(load().sigsdp_solver_reset(self.handle, stream))
+
+    def iterate(self, n_iters, omega_dev_ptr=None, seed=0, stream=None):
+        check(load().sigsdp_solver_iterate(self.handle, int(n_iters), omega_dev_ptr, int(seed), stream))
+
+    def dual(self):
+        Y = np.empty(self.C); e = np.empty(self.C); Yb = np.empty(self.C)
+        check(load().sigsdp_solver_get_dual(self.handle, _p(Y, C.c_double), _p(e, C.c_double), _p(Yb, C.c_double)))
+        return Y, e, Yb
+
+    def X(self, averaged=False):
+        p = self.plan
+        d = np.empty(p.n); g = np.empty(p.E_g); a = np.empty(p.E_a)
+        check(load().sigsdp_solver_get_X(self.handle, int(averaged), _p(d, C.c_double), _p(g, C.c_double), _p(a, C.c_double)))
+        return d, g, a
+
+    def L(self):
+        p = self.plan
+        d = np.empty(p.n); g = np.empty(p.E_g); a = np.empty(p.E_a)
+        check(load().sigsdp_solver_get_L(self.handle, _p(d, C.c_double), _p(g, C.c_double), _p(a, C.c_double)))
+        return d, g, a
+
+    def sketch(self):
+        Yh = np.empty((self.plan.n, self.D))
+        check(load().sigsdp_solver_get_sketch(self.handle, _p(Yh, C.c_double)))
+        return Yh
+
+    def history(self, count):
+        m = np.empty(count, np.int32); s = np.empty(count, np.int32); nt = np.empty(count, np.int32)
+        a1 = np.empty(count); mu = np.empty(count)
+        check(load().sigsdp_solver_get_history(self.handle, count, _p(m, C.c_int32), _p(s, C.c_int32), _p(nt, C.c_int32),
+                                               _p(a1, C.c_double), _p(mu, C.c_double)))
+        return dict(m_star=m, s=s, nterms=nt, a1norm=a1, mu=mu)
+
+    def phase_times(self, count):
+        t = np.empty((count, 3))
+        check(load().sigsdp_solver_get_phase_times(self.handle, count, _p(t, C.c_double)))
+        return t
+
+    def xavg_matrix(self, scale, stream=None):
+        check(load().sigsdp_solver_xavg_matrix(self.handle, float(scale), stream))
+
+    def gap_prepare(self, stream=None):
+        v = C.c_double()
+        check(load().sigsdp_solver_gap_prepare(self.handle, C.byref(v), stream))
+        return float(v.value)
+
+    def symv(self, x_ptr, y_ptr, nvec=1, stream=None):
+        check(load().sigsdp_solver_symv(self.handle, x_ptr, y_ptr, int(nvec), stream))
+
+    def matrix_values(self):
+        v = np.empty(self.plan.nnz)
+        check(load().sigsdp_solver_get_matrix(self.handle, _p(v, C.c_double)))
+        return v
+
+    def total_terms(self):
+        v = C.c_int64()
+        check(load().sigsdp_solver_total_terms(self.handle, C.byref(v)))
+        return int(v.value)
+
+
+def debug_normals(seed, it, n, D, dtype=F64):
+    out = np.empty((n, D))
+    check(load().sigsdp_debug_normals(int(seed), int(it), n, D, dtype, _p(out, C.c_double)))
+    return out

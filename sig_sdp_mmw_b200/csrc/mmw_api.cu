@@ -1,0 +1,1068 @@
+// C ABI of libsigsdp_mmw.so: handles, device workspace, kernel launches, host fetches.
+// See include/sigsdp_mmw.h for the contract and the reference lines each entry replaces.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/sigsdp_mmw.h"
+#include "mmw_device.cuh"
+#include "plan_host.h"
+
+using namespace sigsdp;
+
+// ---------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(SIGSDP_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));         \
+    } while (0)
+
+struct DevArena {
+    std::vector<void*> ptrs;
+    template <typename U>
+    cudaError_t alloc(U** p, size_t count) {
+        void* q = nullptr;
+        cudaError_t e = cudaMalloc(&q, (count ? count : 1) * sizeof(U));
+        if (e == cudaSuccess) ptrs.push_back(q);
+        *p = (U*)q;
+        return e;
+    }
+    template <typename U>
+    cudaError_t upload(U** p, const std::vector<U>& v) {
+        cudaError_t e = alloc(p, v.size());
+        if (e != cudaSuccess) return e;
+        if (!v.empty()) e = cudaMemcpy(*p, v.data(), v.size() * sizeof(U), cudaMemcpyHostToDevice);
+        return e;
+    }
+    void release() {
+        for (void* p : ptrs) cudaFree(p);
+        ptrs.clear();
+    }
+};
+
+struct sigsdp_plan {
+    HostPlan h;
+    PlanDev d;
+    int device = 0;
+    int num_sms = 0;
+    DevArena mem;
+    // CSR of S^T (diag and explicit zeros dropped), asso-UT edges and h_max in the
+    // caller's numbering, for the conflict counter
+    int* d_STp = nullptr;
+    int* d_STi = nullptr;
+    double* d_STx = nullptr;
+    int* d_ai = nullptr;
+    int* d_aj = nullptr;
+    double* d_hmax_caller = nullptr;
+};
+
+struct sigsdp_solver {
+    const sigsdp_plan* plan = nullptr;
+    int Z = 0, D = 0, Dp = 0, C = 0, dtype = 0, G = 0, mode = SIGSDP_MODE_FUSED;
+    int grid = 0;
+    double eta = 0.0;
+    DevArena mem;
+    Prob<double> p64;
+    Prob<float> p32;
+    void* B0 = nullptr;
+    void* B1 = nullptr;
+    void* F = nullptr;
+    long long iters_done = 0;
+    bool owned_by_batch = false;
+    // scratch of the eigen-solver building blocks (allocated on first use)
+    double* Mval = nullptr;      // nnz: a symmetric matrix on the plan's pattern
+    double* rtmp = nullptr;      // n
+    double* gscal = nullptr;     // 8 scalars
+    unsigned long long* gkey = nullptr;
+};
+
+// ---------------------------------------------------------------------------
+// kernels
+template <typename T, int G>
+__global__ void __launch_bounds__(NT, 2) k_fused(Prob<T> P, int n_iters) {
+    GridTeam team;
+    run_iterations<T, G>(P, team, n_iters);
+}
+template <typename T, int G>
+__global__ void __launch_bounds__(NT, 2) k_dual(Prob<T> P) {
+    __shared__ double sh[NWARP + 2];
+    phase_dual<T, G>(P, StepTeam(), sh);
+}
+template <typename T, int G>
+__global__ void __launch_bounds__(NT, 2) k_exp(Prob<T> P) {
+    __shared__ double sh[NWARP + 2];
+    phase_exp<T, G>(P, StepTeam(), sh);
+}
+template <typename T, int G>
+__global__ void __launch_bounds__(NT, 2) k_loss(Prob<T> P, int it_local) {
+    __shared__ double sh[NWARP + 2];
+    phase_loss<T, G>(P, StepTeam(), it_local, sh);
+}
+template <typename T, int G>
+__global__ void __launch_bounds__(NT, 2) k_term(Prob<T> P, const T* bin, T* bout, double coeff, double mu, int slot) {
+    __shared__ double sh[NWARP + 2];
+    phase_term<T, G>(P, StepTeam(), bin, bout, coeff, mu, slot, sh);
+}
+template <typename T, int G>
+__global__ void __launch_bounds__(NT, 2) k_copy(Prob<T> P, T* dst) {
+    phase_copy<T, G>(P, StepTeam(), dst);
+}
+template <typename T, int G>
+__global__ void __launch_bounds__(NT, 2) k_gram(Prob<T> P) {
+    __shared__ double sh[NWARP + 2];
+    phase_gram<T, G>(P, StepTeam(), sh);
+}
+// stepwise controller: single-thread kernels that publish decisions for the host
+__global__ void k_begin(Ctrl* ctrl) {
+    TaylorState ts;
+    taylor_begin(ctrl, ts);
+    ctrl->m_star = ts.m_star;
+    ctrl->s = ts.s;
+    ctrl->c1 = ts.c1;
+    ctrl->a1 = ts.a1;
+    ctrl->done = 0;
+}
+__global__ void k_decide(Ctrl* ctrl, int slot, double c1, double tol) {
+    const double c2 = dkey_pos_inv(ld_u64(&ctrl->nrm_b[slot]));
+    const double fn = dkey_pos_inv(ld_u64(&ctrl->nrm_f[slot]));
+    ctrl->done = (c1 + c2 <= tol * fn) ? 1 : 0;
+    ctrl->c1 = c2;
+    ctrl->a1 = fn;
+}
+template <typename T>
+__global__ void k_record(Prob<T> P, int it_local, int m_star, long long s, double a1, double mu, int nterms) {
+    TaylorState ts;
+    ts.m_star = m_star;
+    ts.s = s;
+    ts.a1 = a1;
+    ts.mu = mu;
+    ts.c1 = 0.0;
+    record_history(P, P.ctrl->iter + it_local, ts, nterms);
+    P.ctrl->total_terms += nterms;
+}
+__global__ void k_advance(Ctrl* ctrl, int n_iters) { ctrl->iter += n_iters; }
+
+template <typename T>
+__global__ void k_fill(T* p, size_t n, T v) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+// standard normals of the throughput-mode generator, for testing its moments
+template <typename T>
+__global__ void k_debug_normals(unsigned long long seed, long long iter, int n, int D, double* out) {
+    constexpr int VEC = Vec<T>::N;
+    const int nv = (D + VEC - 1) / VEC;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)n * nv; i += (size_t)gridDim.x * blockDim.x) {
+        const int row = (int)(i / nv), cv = (int)(i % nv);
+        T raw[VEC];
+        philox_normals(seed, iter, row, cv, raw);
+        for (int v = 0; v < VEC; ++v)
+            if (cv * VEC + v < D) out[(size_t)row * D + cv * VEC + v] = (double)raw[v];
+    }
+}
+
+
+// ---------------------------------------------------------------------------
+// rounding kernels (sdp_solver.py:48-57, rounding.py:56-66)
+__global__ void k_round_inprod(const double* gX, int n, int r, const double* randv, int Z, double* inprod, double* norm) {
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const double* x = gX + (size_t)k * r;
+        double ss = 0.0;
+        for (int d = 0; d < r; ++d) ss += x[d] * x[d];
+        norm[k] = sqrt(ss);
+        for (int z = 0; z < Z; ++z) {
+            const double* v = randv + (size_t)z * r;
+            double acc = 0.0;
+            for (int d = 0; d < r; ++d) acc += v[d] * x[d];
+            inprod[(size_t)k * Z + z] = acc;
+        }
+    }
+}
+// pref[k][rank of slot z in descending <randv_z, g_k>] = z   (argsort(-inprod, axis=0))
+__global__ void k_round_pref(const double* inprod, int n, int Z, int* pref) {
+    const size_t tot = (size_t)n * Z;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (size_t)gridDim.x * blockDim.x) {
+        const int k = (int)(i / Z), z = (int)(i % Z);
+        const double* v = inprod + (size_t)k * Z;
+        const double mine = v[z];
+        int rank = 0;
+        for (int y = 0; y < Z; ++y) rank += (v[y] > mine) || (v[y] == mine && y < z);
+        pref[(size_t)k * Z + rank] = z;
+    }
+}
+__global__ void k_round_conflicts(int n, const int* STp, const int* STi, const double* STx, const double* h_max,
+                                  const int* z, int E_a, const int* ai, const int* aj, double* I_out,
+                                  unsigned long long* counts) {
+    unsigned long long vio = 0, asso = 0;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const int zk = z[k];
+        double acc = 0.0;
+        for (int p = STp[k]; p < STp[k + 1]; ++p)
+            if (z[STi[p]] == zk) acc += STx[p];
+        if (I_out) I_out[k] = acc;
+        vio += acc > h_max[k];
+    }
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E_a; e += gridDim.x * blockDim.x) asso += z[ai[e]] == z[aj[e]];
+    for (int o = 16; o > 0; o >>= 1) {
+        vio += __shfl_xor_sync(0xffffffffu, vio, o);
+        asso += __shfl_xor_sync(0xffffffffu, asso, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (vio) atomicAdd(&counts[0], vio);
+        if (asso) atomicAdd(&counts[1], asso);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// building blocks of the eigen-solvers that replace eigsh / svds (mmw.py:115,215) and of
+// the gap log (mmw.py:79-117).  Not on the per-iteration path; one thread per row.
+struct SolverView {  // dtype-independent part of Prob
+    PlanDev g;
+    int Z, C;
+    const double *nH, *hcoef, *Y, *Ybar, *Xd, *Xe, *Xbar_d, *Xbar_e;
+};
+__global__ void k_mat_xavg(SolverView v, double scale, double* Mval) {
+    const PlanDev& g = v.g;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < g.n; k += gridDim.x * blockDim.x)
+        for (int p = g.rowptr[k]; p < g.rowptr[k + 1]; ++p) {
+            const int e = g.eid[p];
+            Mval[p] = scale * (e < 0 ? v.Xbar_d[k] : v.Xbar_e[e]);
+        }
+}
+__global__ void k_symv(PlanDev g, const double* Mval, const double* x, double* y, int nvec) {
+    constexpr int G = 8;
+    const int lane = threadIdx.x & (G - 1);
+    const unsigned mask = 0xffu << ((threadIdx.x & 31) & ~(G - 1));
+    const int ngroups = gridDim.x * blockDim.x / G;
+    for (int v = 0; v < nvec; ++v) {
+        const double* xv = x + (size_t)v * g.n;
+        double* yv = y + (size_t)v * g.n;
+        for (int k = (blockIdx.x * blockDim.x + threadIdx.x) / G; k < g.n; k += ngroups) {
+            double acc = 0.0;
+            for (int p = g.rowptr[k] + lane; p < g.rowptr[k + 1]; p += G) acc += Mval[p] * xv[g.col[p]];
+            for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(mask, acc, o);
+            if (lane == 0) yv[k] = acc;
+        }
+    }
+}
+// running means at the start of iteration i (N = i + 1): X~ = (X_avgd + X)/N, Y~ likewise
+__global__ void k_gap_rowsum(SolverView v, double N, double* rtmp) {
+    const PlanDev& g = v.g;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < g.n; k += gridDim.x * blockDim.x) {
+        double acc = 0.0;
+        for (int p = g.rowptr[k]; p < g.rowptr[k + 1]; ++p) {
+            const int e = g.eid[p];
+            if (e >= 0) acc += (v.Xbar_e[e] + v.Xe[e]) / N;
+        }
+        rtmp[k] = acc;
+    }
+}
+__global__ void k_gap_emax(SolverView v, double N, const double* rtmp, unsigned long long* key) {
+    const PlanDev& g = v.g;
+    const int K = g.n, Z = v.Z;
+    const double invD = 1.0 / (1.0 - 1.0 / K), zr = (double)(Z - 1) / Z, cF = 1.0 / ((double)K * (Z - 1)) + 0.5;
+    double m = -INFINITY;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < K; k += gridDim.x * blockDim.x) {
+        double acc = 0.0;
+        for (int p = g.rowptr[k]; p < g.rowptr[k + 1]; ++p) {
+            const double tf = g.tfwd[p];
+            if (tf != 0.0) acc += tf * rtmp[g.col[p]];
+        }
+        const double eH = (acc * zr - (g.h_max[k] - g.S_sum[k] / Z)) / v.nH[k];
+        const double eD = ((v.Xbar_d[k] + v.Xd[k]) / N - 1.0) * invD;
+        m = fmax(m, fmax(eH, eD));
+    }
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < g.E_a; e += gridDim.x * blockDim.x)
+        m = fmax(m, ((v.Xbar_e[g.E_g + e] + v.Xe[g.E_g + e]) / N + 1.0 / (Z - 1)) / cF);
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0 && m > -INFINITY) atomicMax(key, dkey_any(m));
+}
+// single block: sums of Y~ in a fixed order
+__global__ void k_gap_sums(SolverView v, double N, double* out) {
+    __shared__ double sh[32 + 1];
+    const int K = v.g.n, Ea = v.g.E_a;
+    double sD = 0.0, sF = 0.0, sHq = 0.0;
+    for (int c = threadIdx.x; c < v.C; c += blockDim.x) {
+        const double y = (v.Ybar[c] + v.Y[c]) / N;
+        if (c < K) sD += y;
+        else if (c < K + Ea) sF += y;
+        else sHq += v.hcoef[c - K - Ea] * (y / v.nH[c - K - Ea]);
+    }
+    double vals[3] = {sD, sF, sHq};
+    for (int i = 0; i < 3; ++i) {
+        double t = warp_sum(vals[i]);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = t;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            t = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.0;
+            t = warp_sum(t);
+            if (threadIdx.x == 0) out[i] = t;
+        }
+    }
+}
+__global__ void k_gap_L(SolverView v, double N, const double* sums, double* Mval) {
+    const PlanDev& g = v.g;
+    const int K = g.n, Z = v.Z, Ea = g.E_a;
+    const double invD = 1.0 / (1.0 - 1.0 / K), cF = 1.0 / ((double)K * (Z - 1)) + 0.5, gcoef = (double)(Z - 1) / (2.0 * Z);
+    const double sD = sums[0], sF = sums[1], sHq = sums[2];
+    const double cLF = (sF / ((double)K * (Z - 1))) / cF;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < K; k += gridDim.x * blockDim.x) {
+        const double wk = ((v.Ybar[K + Ea + k] + v.Y[K + Ea + k]) / N) / v.nH[k];
+        for (int p = g.rowptr[k]; p < g.rowptr[k + 1]; ++p) {
+            const int e = g.eid[p];
+            double l;
+            if (e < 0) {
+                l = ((v.Ybar[k] + v.Y[k]) / N - sD / K) * invD + cLF - sHq;
+            } else if (e < g.E_g) {
+                const int c = g.col[p];
+                const double wc = ((v.Ybar[K + Ea + c] + v.Y[K + Ea + c]) / N) / v.nH[c];
+                l = gcoef * (g.tfwd[p] * wc + g.tbwd[p] * wk);
+            } else {
+                l = (((v.Ybar[K + e - g.E_g] + v.Y[K + e - g.E_g]) / N) * 0.5) / cF;
+            }
+            Mval[p] = l;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// dispatch helpers
+template <typename T> static Prob<T>& prob_of(sigsdp_solver* s);
+template <> Prob<double>& prob_of<double>(sigsdp_solver* s) { return s->p64; }
+template <> Prob<float>& prob_of<float>(sigsdp_solver* s) { return s->p32; }
+
+#define FOR_G(Gv, BODY)                                   \
+    switch (Gv) {                                         \
+        case 4: { constexpr int G = 4; BODY; } break;     \
+        case 8: { constexpr int G = 8; BODY; } break;     \
+        case 16: { constexpr int G = 16; BODY; } break;   \
+        default: { constexpr int G = 32; BODY; } break;   \
+    }
+
+template <typename T, int G>
+static int occupancy_fused(int* occ) {
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_fused<T, G>, NT, 0));
+    return SIGSDP_OK;
+}
+
+template <typename T, int G>
+static int launch_fused(sigsdp_solver* s, int n_iters, cudaStream_t st) {
+    Prob<T> P = prob_of<T>(s);
+    void* args[] = {(void*)&P, (void*)&n_iters};
+    CK(cudaLaunchCooperativeKernel((void*)k_fused<T, G>, dim3(s->grid), dim3(NT), args, 0, st));
+    return SIGSDP_OK;
+}
+
+template <typename T, int G>
+static int run_stepwise(sigsdp_solver* s, int n_iters, cudaStream_t st) {
+    Prob<T> P = prob_of<T>(s);
+    const dim3 grid(s->grid), blk(NT);
+    Ctrl hc;
+    for (int it = 0; it < n_iters; ++it) {
+        k_dual<T, G><<<grid, blk, 0, st>>>(P);
+        k_exp<T, G><<<grid, blk, 0, st>>>(P);
+        k_loss<T, G><<<grid, blk, 0, st>>>(P, it);
+        k_begin<<<1, 1, 0, st>>>(P.ctrl);
+        CK(cudaMemcpyAsync(&hc, P.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        const int m_star = hc.m_star;
+        const long long ss = hc.s;
+        const double a1 = hc.a1, mu = hc.mu;
+        double c1 = hc.c1, fn_last = hc.c1;
+        T* bin = P.B0;
+        T* bout = P.B1;
+        int tcount = 0;
+        for (long long si = 0; si < ss; ++si) {
+            if (si > 0) {
+                k_copy<T, G><<<grid, blk, 0, st>>>(P, bin);
+                c1 = fn_last;
+            }
+            for (int j = 0; j < m_star; ++j) {
+                const int slot = tcount % 3;
+                k_term<T, G><<<grid, blk, 0, st>>>(P, bin, bout, 1.0 / ((double)ss * (double)(j + 1)), mu, slot);
+                k_decide<<<1, 1, 0, st>>>(P.ctrl, slot, c1, P.tol);
+                CK(cudaMemcpyAsync(&hc, P.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                T* tmp = bin;
+                bin = bout;
+                bout = tmp;
+                ++tcount;
+                fn_last = hc.a1;
+                c1 = hc.c1;
+                if (hc.done) break;
+            }
+        }
+        k_record<T><<<1, 1, 0, st>>>(P, it, m_star, ss, a1, mu, tcount);
+        k_gram<T, G><<<grid, blk, 0, st>>>(P);
+        CK(cudaGetLastError());
+    }
+    k_advance<<<1, 1, 0, st>>>(P.ctrl, n_iters);
+    CK(cudaStreamSynchronize(st));
+    return SIGSDP_OK;
+}
+
+// ---------------------------------------------------------------------------
+extern "C" {
+
+const char* sigsdp_last_error(void) { return g_err.c_str(); }
+int sigsdp_version(void) { return 100; }
+
+int sigsdp_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return fail(SIGSDP_ECUDA, cudaGetErrorString(e));
+    return n;
+}
+
+int sigsdp_plan_create(int64_t n, const int32_t* Sp, const int32_t* Si, const double* Sx, const int32_t* Qp,
+                       const int32_t* Qi, const double* Qx, const double* h_max, int device, int order,
+                       sigsdp_plan** out) {
+    if (!out) return fail(SIGSDP_EINVAL, "out is null");
+    *out = nullptr;
+    sigsdp_plan* pl = new sigsdp_plan();
+    std::string err;
+    int rc = build_host_plan(n, Sp, Si, Sx, Qp, Qi, Qx, h_max, order, pl->h, err);
+    if (rc != SIGSDP_OK) {
+        delete pl;
+        return fail(rc, err);
+    }
+    pl->device = device;
+    auto bail = [&](cudaError_t e, const char* what) {
+        std::string m = std::string(what) + ": " + cudaGetErrorString(e);
+        pl->mem.release();
+        delete pl;
+        return fail(SIGSDP_ECUDA, m);
+    };
+    cudaError_t e;
+    if (device < 0) {  // host-only plan: edge lists and vectors can be read back, no solver
+        *out = pl;
+        return SIGSDP_OK;
+    }
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(e, "cudaSetDevice");
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail(e, "cudaGetDeviceProperties");
+    pl->num_sms = prop.multiProcessorCount;
+    HostPlan& h = pl->h;
+    PlanDev& d = pl->d;
+    d.n = (int)h.n;
+    d.nnz = (int)h.nnz;
+    d.E_g = (int)h.E_g;
+    d.E_a = (int)h.E_a;
+    int *rowptr, *col, *eid, *perm = nullptr;
+    double *tfwd, *tbwd, *S_sum, *tnorm, *hm;
+    if ((e = pl->mem.upload(&rowptr, h.rowptr)) != cudaSuccess) return bail(e, "upload rowptr");
+    if ((e = pl->mem.upload(&col, h.col)) != cudaSuccess) return bail(e, "upload col");
+    if ((e = pl->mem.upload(&eid, h.eid)) != cudaSuccess) return bail(e, "upload eid");
+    if ((e = pl->mem.upload(&tfwd, h.tfwd)) != cudaSuccess) return bail(e, "upload tfwd");
+    if ((e = pl->mem.upload(&tbwd, h.tbwd)) != cudaSuccess) return bail(e, "upload tbwd");
+    if ((e = pl->mem.upload(&S_sum, h.S_sum)) != cudaSuccess) return bail(e, "upload S_sum");
+    if ((e = pl->mem.upload(&tnorm, h.tnorm)) != cudaSuccess) return bail(e, "upload tnorm");
+    if ((e = pl->mem.upload(&hm, h.h_max)) != cudaSuccess) return bail(e, "upload h_max");
+    if (h.order != 0 && (e = pl->mem.upload(&perm, h.perm)) != cudaSuccess) return bail(e, "upload perm");
+    d.rowptr = rowptr;
+    d.col = col;
+    d.eid = eid;
+    d.tfwd = tfwd;
+    d.tbwd = tbwd;
+    d.S_sum = S_sum;
+    d.tnorm = tnorm;
+    d.h_max = hm;
+    d.perm = perm;
+    // S^T without its diagonal / explicit zeros, caller numbering (rounding.py:56-60)
+    {
+        std::vector<int32_t> sp(n + 1, 0), si;
+        std::vector<double> sx;
+        for (int64_t r = 0; r < n; ++r)
+            for (int32_t q = Sp[r]; q < Sp[r + 1]; ++q)
+                if (Si[q] != r && Sx[q] != 0.0) sp[Si[q] + 1]++;
+        for (int64_t r = 0; r < n; ++r) sp[r + 1] += sp[r];
+        si.resize(sp[n]);
+        sx.resize(sp[n]);
+        std::vector<int32_t> fill(sp.begin(), sp.end() - 1);
+        for (int64_t r = 0; r < n; ++r)
+            for (int32_t q = Sp[r]; q < Sp[r + 1]; ++q)
+                if (Si[q] != r && Sx[q] != 0.0) {
+                    si[fill[Si[q]]] = (int32_t)r;
+                    sx[fill[Si[q]]] = Sx[q];
+                    fill[Si[q]]++;
+                }
+        std::vector<double> hc(h_max, h_max + n);
+        if ((e = pl->mem.upload(&pl->d_STp, sp)) != cudaSuccess) return bail(e, "upload S^T");
+        if ((e = pl->mem.upload(&pl->d_STi, si)) != cudaSuccess) return bail(e, "upload S^T");
+        if ((e = pl->mem.upload(&pl->d_STx, sx)) != cudaSuccess) return bail(e, "upload S^T");
+        if ((e = pl->mem.upload(&pl->d_ai, h.ai)) != cudaSuccess) return bail(e, "upload asso");
+        if ((e = pl->mem.upload(&pl->d_aj, h.aj)) != cudaSuccess) return bail(e, "upload asso");
+        if ((e = pl->mem.upload(&pl->d_hmax_caller, hc)) != cudaSuccess) return bail(e, "upload h_max");
+    }
+    *out = pl;
+    return SIGSDP_OK;
+}
+
+void sigsdp_plan_destroy(sigsdp_plan* plan) {
+    if (!plan) return;
+    if (plan->device >= 0) {
+        cudaSetDevice(plan->device);
+        plan->mem.release();
+    }
+    delete plan;
+}
+
+int sigsdp_plan_info(const sigsdp_plan* plan, int64_t info[8]) {
+    if (!plan || !info) return fail(SIGSDP_EINVAL, "null argument");
+    const HostPlan& h = plan->h;
+    info[0] = h.n;
+    info[1] = h.E_g;
+    info[2] = h.E_a;
+    info[3] = h.nnz;
+    info[4] = h.nnzT;
+    info[5] = plan->device;
+    info[6] = h.order;
+    info[7] = h.max_row;
+    return SIGSDP_OK;
+}
+
+int sigsdp_plan_edges(const sigsdp_plan* plan, int32_t* gi, int32_t* gj, double* tij, double* tji, int32_t* ai,
+                      int32_t* aj) {
+    if (!plan) return fail(SIGSDP_EINVAL, "null plan");
+    const HostPlan& h = plan->h;
+    if (gi) std::memcpy(gi, h.gi.data(), h.gi.size() * sizeof(int32_t));
+    if (gj) std::memcpy(gj, h.gj.data(), h.gj.size() * sizeof(int32_t));
+    if (tij) std::memcpy(tij, h.tij.data(), h.tij.size() * sizeof(double));
+    if (tji) std::memcpy(tji, h.tji.data(), h.tji.size() * sizeof(double));
+    if (ai) std::memcpy(ai, h.ai.data(), h.ai.size() * sizeof(int32_t));
+    if (aj) std::memcpy(aj, h.aj.data(), h.aj.size() * sizeof(int32_t));
+    return SIGSDP_OK;
+}
+
+int sigsdp_plan_vectors(const sigsdp_plan* plan, double* S_sum, double* tnorm) {
+    if (!plan) return fail(SIGSDP_EINVAL, "null plan");
+    const HostPlan& h = plan->h;
+    for (int64_t k = 0; k < h.n; ++k) {
+        if (S_sum) S_sum[h.perm[k]] = h.S_sum[k];
+        if (tnorm) tnorm[h.perm[k]] = h.tnorm[k];
+    }
+    return SIGSDP_OK;
+}
+
+int sigsdp_plan_perm(const sigsdp_plan* plan, int32_t* perm) {
+    if (!plan || !perm) return fail(SIGSDP_EINVAL, "null argument");
+    std::memcpy(perm, plan->h.perm.data(), plan->h.perm.size() * sizeof(int32_t));
+    return SIGSDP_OK;
+}
+
+// ---------------------------------------------------------------------------
+extern "C++" {
+template <typename T>
+static int solver_alloc(sigsdp_solver* s) {
+    const sigsdp_plan* pl = s->plan;
+    const HostPlan& h = pl->h;
+    const int64_t n = h.n, E = h.E_g + h.E_a;
+    Prob<T>& P = prob_of<T>(s);
+    P.g = pl->d;
+    P.Z = s->Z;
+    P.D = s->D;
+    P.Dp = s->Dp;
+    P.C = s->C;
+    P.eta = s->eta;
+    P.tol = sizeof(T) == 8 ? ldexp(1.0, -53) : ldexp(1.0, -24);
+    // norm_H (mmw.py:39) and the h coefficient of LH (mmw.py:164), internal numbering
+    std::vector<double> nH(n), hcoef(n);
+    const double K = (double)n, Z = (double)s->Z;
+    for (int64_t k = 0; k < n; ++k) {
+        nH[k] = h.tnorm[k] * (Z - 1) / (2 * Z) + std::fabs(1 / K * h.h_max[k] - 1 / K / Z * h.S_sum[k]);
+        hcoef[k] = 1. / K * h.h_max[k] - 1 / (K * Z) * h.S_sum[k];
+    }
+    double *d_nH, *d_hcoef;
+    CK(s->mem.upload(&d_nH, nH));
+    CK(s->mem.upload(&d_hcoef, hcoef));
+    P.nH = d_nH;
+    P.hcoef = d_hcoef;
+    CK(s->mem.alloc(&P.Lval, h.nnz));
+    CK(s->mem.alloc(&P.e_acc, s->C));
+    CK(s->mem.alloc(&P.u, s->C));
+    CK(s->mem.alloc(&P.Y, s->C));
+    CK(s->mem.alloc(&P.Ybar, s->C));
+    CK(s->mem.alloc(&P.q, n));
+    CK(s->mem.alloc(&P.Xd, n));
+    CK(s->mem.alloc(&P.Xe, E));
+    CK(s->mem.alloc(&P.Xbar_d, n));
+    CK(s->mem.alloc(&P.Xbar_e, E));
+    CK(s->mem.alloc(&P.r, n));
+    CK(s->mem.alloc(&P.dsq, n));
+    CK(s->mem.alloc(&P.B0, (size_t)n * s->Dp));
+    CK(s->mem.alloc(&P.B1, (size_t)n * s->Dp));
+    CK(s->mem.alloc(&P.F, (size_t)n * s->Dp));
+    s->B0 = P.B0;
+    s->B1 = P.B1;
+    s->F = P.F;
+    const int maxblk = pl->num_sms * 8 + 8;
+    CK(s->mem.alloc(&P.psum, (size_t)maxblk * PSTRIDE));
+    CK(s->mem.alloc(&P.ptr, maxblk));
+    CK(s->mem.alloc(&P.ctrl, 1));
+    CK(s->mem.alloc(&P.hist_m, HIST));
+    CK(s->mem.alloc(&P.hist_s, HIST));
+    CK(s->mem.alloc(&P.hist_nt, HIST));
+    CK(s->mem.alloc(&P.hist_a1, HIST));
+    CK(s->mem.alloc(&P.hist_mu, HIST));
+    CK(s->mem.alloc(&P.hist_t, (size_t)HIST * 3));
+    P.omega = nullptr;
+    P.seed = 0;
+    // launch geometry: persistent grid, one tile of NT/G rows per block iteration
+    int occ = 0, rc = SIGSDP_OK;
+    FOR_G(s->G, rc = (occupancy_fused<T, G>(&occ)));
+    if (rc != SIGSDP_OK) return rc;
+    if (occ < 1) return fail(SIGSDP_ECUDA, "fused kernel does not fit on an SM");
+    const int R = NT / s->G;
+    int64_t tiles = (n + R - 1) / R;
+    int64_t blocks = (int64_t)pl->num_sms * occ;
+    if (blocks > tiles) blocks = tiles;
+    if (blocks > maxblk) blocks = maxblk;
+    if (blocks < 1) blocks = 1;
+    s->grid = (int)blocks;
+    return SIGSDP_OK;
+}
+}  // extern "C++"
+
+extern "C++" {
+template <typename T>
+static int solver_reset_impl(sigsdp_solver* s, cudaStream_t st) {
+    Prob<T>& P = prob_of<T>(s);
+    const HostPlan& h = s->plan->h;
+    const int64_t n = h.n, E = h.E_g + h.E_a;
+    CK(cudaMemsetAsync(P.Lval, 0, h.nnz * sizeof(double), st));
+    CK(cudaMemsetAsync(P.e_acc, 0, s->C * sizeof(double), st));
+    CK(cudaMemsetAsync(P.u, 0, s->C * sizeof(double), st));
+    CK(cudaMemsetAsync(P.Ybar, 0, s->C * sizeof(double), st));
+    CK(cudaMemsetAsync(P.q, 0, n * sizeof(double), st));
+    CK(cudaMemsetAsync(P.Xe, 0, (E ? E : 1) * sizeof(double), st));
+    CK(cudaMemsetAsync(P.Xbar_d, 0, n * sizeof(double), st));
+    CK(cudaMemsetAsync(P.Xbar_e, 0, (E ? E : 1) * sizeof(double), st));
+    CK(cudaMemsetAsync(P.r, 0, n * sizeof(double), st));
+    CK(cudaMemsetAsync(P.dsq, 0, n * sizeof(double), st));
+    CK(cudaMemsetAsync(P.B0, 0, (size_t)n * s->Dp * sizeof(T), st));
+    CK(cudaMemsetAsync(P.B1, 0, (size_t)n * s->Dp * sizeof(T), st));
+    CK(cudaMemsetAsync(P.F, 0, (size_t)n * s->Dp * sizeof(T), st));
+    CK(cudaMemsetAsync(P.ctrl, 0, sizeof(Ctrl), st));
+    CK(cudaMemsetAsync(P.hist_m, 0, HIST * sizeof(int), st));
+    CK(cudaMemsetAsync(P.hist_s, 0, HIST * sizeof(int), st));
+    CK(cudaMemsetAsync(P.hist_nt, 0, HIST * sizeof(int), st));
+    CK(cudaMemsetAsync(P.hist_a1, 0, HIST * sizeof(double), st));
+    CK(cudaMemsetAsync(P.hist_mu, 0, HIST * sizeof(double), st));
+    CK(cudaMemsetAsync(P.hist_t, 0, (size_t)HIST * 3 * sizeof(double), st));
+    k_fill<double><<<64, 256, 0, st>>>(P.Y, (size_t)s->C, 1.0 / (double)s->C);  // Y = 1/C (mmw.py:62)
+    k_fill<double><<<64, 256, 0, st>>>(P.Xd, (size_t)n, 1.0);                   // X = I   (mmw.py:67)
+    CK(cudaGetLastError());
+    s->iters_done = 0;
+    return SIGSDP_OK;
+}
+}  // extern "C++"
+
+int sigsdp_solver_create(const sigsdp_plan* plan, int Z, int D, double eta, int dtype, sigsdp_solver** out) {
+    if (!out) return fail(SIGSDP_EINVAL, "out is null");
+    *out = nullptr;
+    if (!plan) return fail(SIGSDP_EINVAL, "null plan");
+    if (plan->device < 0) return fail(SIGSDP_EINVAL, "host-only plan (device < 0) cannot run a solver");
+    if (Z < 2) return fail(SIGSDP_EINVAL, "Z must be >= 2");
+    if (D < 1 || D > 4096) return fail(SIGSDP_EINVAL, "D must be in [1, 4096]");
+    if (dtype != SIGSDP_F64 && dtype != SIGSDP_F32) return fail(SIGSDP_EINVAL, "dtype must be SIGSDP_F64 or SIGSDP_F32");
+    if (!(eta > 0.0)) return fail(SIGSDP_EINVAL, "eta must be positive");
+    CK(cudaSetDevice(plan->device));
+    sigsdp_solver* s = new sigsdp_solver();
+    s->plan = plan;
+    s->Z = Z;
+    s->D = D;
+    s->eta = eta;
+    s->dtype = dtype;
+    const int VEC = dtype == SIGSDP_F64 ? 2 : 4;
+    s->Dp = (D + VEC - 1) / VEC * VEC;
+    const int lanes = s->Dp / VEC;
+    s->G = lanes <= 4 ? 4 : lanes <= 8 ? 8 : lanes <= 16 ? 16 : 32;
+    s->C = (int)(plan->h.E_a + 2 * plan->h.n);
+    int rc = dtype == SIGSDP_F64 ? solver_alloc<double>(s) : solver_alloc<float>(s);
+    if (rc == SIGSDP_OK) rc = dtype == SIGSDP_F64 ? solver_reset_impl<double>(s, 0) : solver_reset_impl<float>(s, 0);
+    if (rc == SIGSDP_OK && cudaDeviceSynchronize() != cudaSuccess) rc = fail(SIGSDP_ECUDA, "solver initialisation failed");
+    if (rc != SIGSDP_OK) {
+        std::string keep = g_err;
+        s->mem.release();
+        delete s;
+        g_err = keep;
+        return rc;
+    }
+    *out = s;
+    return SIGSDP_OK;
+}
+
+void sigsdp_solver_destroy(sigsdp_solver* s) {
+    if (!s || s->owned_by_batch) return;
+    cudaSetDevice(s->plan->device);
+    s->mem.release();
+    delete s;
+}
+
+int sigsdp_solver_reset(sigsdp_solver* s, void* stream) {
+    if (!s) return fail(SIGSDP_EINVAL, "null solver");
+    CK(cudaSetDevice(s->plan->device));
+    return s->dtype == SIGSDP_F64 ? solver_reset_impl<double>(s, (cudaStream_t)stream)
+                                  : solver_reset_impl<float>(s, (cudaStream_t)stream);
+}
+
+int sigsdp_solver_set_mode(sigsdp_solver* s, int mode) {
+    if (!s) return fail(SIGSDP_EINVAL, "null solver");
+    if (mode != SIGSDP_MODE_FUSED && mode != SIGSDP_MODE_STEPWISE) return fail(SIGSDP_EINVAL, "unknown mode");
+    s->mode = mode;
+    return SIGSDP_OK;
+}
+
+int sigsdp_solver_info(const sigsdp_solver* s, int64_t info[10]) {
+    if (!s || !info) return fail(SIGSDP_EINVAL, "null argument");
+    info[0] = s->plan->h.n;
+    info[1] = s->Z;
+    info[2] = s->D;
+    info[3] = s->Dp;
+    info[4] = s->C;
+    info[5] = s->iters_done;
+    info[6] = s->dtype;
+    info[7] = s->grid;
+    info[8] = NT;
+    info[9] = s->G;
+    return SIGSDP_OK;
+}
+
+extern "C++" {
+template <typename T>
+static int iterate_impl(sigsdp_solver* s, int n_iters, const double* omega_dev, uint64_t seed, cudaStream_t st) {
+    Prob<T>& P = prob_of<T>(s);
+    P.omega = omega_dev;
+    P.seed = seed;
+    int rc = SIGSDP_OK;
+    if (s->mode == SIGSDP_MODE_FUSED) {
+        FOR_G(s->G, rc = (launch_fused<T, G>(s, n_iters, st)));
+    } else {
+        FOR_G(s->G, rc = (run_stepwise<T, G>(s, n_iters, st)));
+    }
+    if (rc == SIGSDP_OK) s->iters_done += n_iters;
+    return rc;
+}
+}  // extern "C++"
+
+int sigsdp_solver_iterate(sigsdp_solver* s, int n_iters, const double* omega_dev, uint64_t seed, void* stream) {
+    if (!s) return fail(SIGSDP_EINVAL, "null solver");
+    if (n_iters < 0) return fail(SIGSDP_EINVAL, "n_iters < 0");
+    if (n_iters == 0) return SIGSDP_OK;
+    CK(cudaSetDevice(s->plan->device));
+    return s->dtype == SIGSDP_F64 ? iterate_impl<double>(s, n_iters, omega_dev, seed, (cudaStream_t)stream)
+                                  : iterate_impl<float>(s, n_iters, omega_dev, seed, (cudaStream_t)stream);
+}
+
+// ---- fetches ---------------------------------------------------------------
+static int fetch(std::vector<double>& dst, const double* src, size_t count) {
+    dst.resize(count);
+    if (count) CK(cudaMemcpy(dst.data(), src, count * sizeof(double), cudaMemcpyDeviceToHost));
+    return SIGSDP_OK;
+}
+
+// [D | F | H] vector from internal to caller numbering
+static void unpermute_dual(const HostPlan& h, const std::vector<double>& in, double* out) {
+    const int64_t n = h.n, Ea = h.E_a;
+    for (int64_t k = 0; k < n; ++k) {
+        out[h.perm[k]] = in[k];
+        out[n + Ea + h.perm[k]] = in[n + Ea + k];
+    }
+    for (int64_t e = 0; e < Ea; ++e) out[n + e] = in[n + e];
+}
+
+#define COMMON(s) (s->dtype == SIGSDP_F64 ? (void*)&s->p64 : (void*)&s->p32)
+
+int sigsdp_solver_get_dual(sigsdp_solver* s, double* Y, double* e_accu, double* Y_avgd) {
+    if (!s) return fail(SIGSDP_EINVAL, "null solver");
+    CK(cudaSetDevice(s->plan->device));
+    CK(cudaDeviceSynchronize());
+    const HostPlan& h = s->plan->h;
+    const double* dY = s->dtype == SIGSDP_F64 ? s->p64.Y : s->p32.Y;
+    const double* dE = s->dtype == SIGSDP_F64 ? s->p64.e_acc : s->p32.e_acc;
+    const double* dB = s->dtype == SIGSDP_F64 ? s->p64.Ybar : s->p32.Ybar;
+    std::vector<double> tmp;
+    int rc;
+    if (Y) {
+        if ((rc = fetch(tmp, dY, s->C)) != SIGSDP_OK) return rc;
+        unpermute_dual(h, tmp, Y);
+    }
+    if (e_accu) {
+        if ((rc = fetch(tmp, dE, s->C)) != SIGSDP_OK) return rc;
+        unpermute_dual(h, tmp, e_accu);
+    }
+    if (Y_avgd) {
+        if ((rc = fetch(tmp, dB, s->C)) != SIGSDP_OK) return rc;
+        unpermute_dual(h, tmp, Y_avgd);
+    }
+    return SIGSDP_OK;
+}
+
+int sigsdp_solver_get_X(sigsdp_solver* s, int averaged, double* diag, double* gain, double* asso) {
+    if (!s) return fail(SIGSDP_EINVAL, "null solver");
+    CK(cudaSetDevice(s->plan->device));
+    CK(cudaDeviceSynchronize());
+    const HostPlan& h = s->plan->h;
+    const double* dd = s->dtype == SIGSDP_F64 ? (averaged ? s->p64.Xbar_d : s->p64.Xd) : (averaged ? s->p32.Xbar_d : s->p32.Xd);
+    const double* de = s->dtype == SIGSDP_F64 ? (averaged ? s->p64.Xbar_e : s->p64.Xe) : (averaged ? s->p32.Xbar_e : s->p32.Xe);
+    std::vector<double> tmp;
+    int rc;
+    if (diag) {
+        if ((rc = fetch(tmp, dd, h.n)) != SIGSDP_OK) return rc;
+        for (int64_t k = 0; k < h.n; ++k) diag[h.perm[k]] = tmp[k];
+    }
+    if (gain && h.E_g) CK(cudaMemcpy(gain, de, h.E_g * sizeof(double), cudaMemcpyDeviceToHost));
+    if (asso && h.E_a) CK(cudaMemcpy(asso, de + h.E_g, h.E_a * sizeof(double), cudaMemcpyDeviceToHost));
+    return SIGSDP_OK;
+}
+
+int sigsdp_solver_get_L(sigsdp_solver* s, double* diag, double* gain, double* asso) {
+    if (!s) return fail(SIGSDP_EINVAL, "null solver");
+    CK(cudaSetDevice(s->plan->device));
+    CK(cudaDeviceSynchronize());
+    const HostPlan& h = s->plan->h;
+    const double* dL = s->dtype == SIGSDP_F64 ? s->p64.Lval : s->p32.Lval;
+    std::vector<double> L;
+    int rc = fetch(L, dL, h.nnz);
+    if (rc != SIGSDP_OK) return rc;
+    for (int64_t k = 0; k < h.n; ++k)
+        for (int32_t p = h.rowptr[k]; p < h.rowptr[k + 1]; ++p) {
+            const int32_t e = h.eid[p];
+            if (e < 0) {
+                if (diag) diag[h.perm[k]] = L[p];
+            } else if (k < h.col[p]) {
+                if (e < h.E_g) {
+                    if (gain) gain[e] = L[p];
+                } else if (asso) {
+                    asso[e - h.E_g] = L[p];
+                }
+            }
+        }
+    return SIGSDP_OK;
+}
+
+int sigsdp_solver_get_sketch(sigsdp_solver* s, double* Yh) {
+    if (!s || !Yh) return fail(SIGSDP_EINVAL, "null argument");
+    if (s->iters_done == 0) return fail(SIGSDP_ESTATE, "no iteration has run yet");
+    CK(cudaSetDevice(s->plan->device));
+    CK(cudaDeviceSynchronize());
+    const HostPlan& h = s->plan->h;
+    Ctrl hc;
+    CK(cudaMemcpy(&hc, s->dtype == SIGSDP_F64 ? s->p64.ctrl : s->p32.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost));
+    const double scale = std::exp(hc.mu);  // deferred e^{mu/s} factors (scipy _expm_multiply.py:277,301)
+    const size_t tot = (size_t)h.n * s->Dp;
+    if (s->dtype == SIGSDP_F64) {
+        std::vector<double> F(tot);
+        CK(cudaMemcpy(F.data(), s->F, tot * sizeof(double), cudaMemcpyDeviceToHost));
+        for (int64_t k = 0; k < h.n; ++k)
+            for (int c = 0; c < s->D; ++c) Yh[(size_t)h.perm[k] * s->D + c] = scale * F[(size_t)k * s->Dp + c];
+    } else {
+        std::vector<float> F(tot);
+        CK(cudaMemcpy(F.data(), s->F, tot * sizeof(float), cudaMemcpyDeviceToHost));
+        for (int64_t k = 0; k < h.n; ++k)
+            for (int c = 0; c < s->D; ++c) Yh[(size_t)h.perm[k] * s->D + c] = scale * (double)F[(size_t)k * s->Dp + c];
+    }
+    return SIGSDP_OK;
+}
+
+int sigsdp_solver_get_history(sigsdp_solver* s, int count, int32_t* m_star, int32_t* ss, int32_t* nterms,
+                              double* a1norm, double* mu) {
+    if (!s) return fail(SIGSDP_EINVAL, "null solver");
+    if (count < 0 || count > HIST || count > s->iters_done) return fail(SIGSDP_EINVAL, "count out of range");
+    CK(cudaSetDevice(s->plan->device));
+    CK(cudaDeviceSynchronize());
+    std::vector<int> hm(HIST), hs(HIST), hn(HIST);
+    std::vector<double> ha(HIST), hu(HIST);
+    const bool d = s->dtype == SIGSDP_F64;
+    CK(cudaMemcpy(hm.data(), d ? s->p64.hist_m : s->p32.hist_m, HIST * sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(hs.data(), d ? s->p64.hist_s : s->p32.hist_s, HIST * sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(hn.data(), d ? s->p64.hist_nt : s->p32.hist_nt, HIST * sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(ha.data(), d ? s->p64.hist_a1 : s->p32.hist_a1, HIST * sizeof(double), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(hu.data(), d ? s->p64.hist_mu : s->p32.hist_mu, HIST * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < count; ++i) {
+        const long long it = s->iters_done - count + i;
+        const int hidx = (int)(it % HIST);
+        if (m_star) m_star[i] = hm[hidx];
+        if (ss) ss[i] = hs[hidx];
+        if (nterms) nterms[i] = hn[hidx];
+        if (a1norm) a1norm[i] = ha[hidx];
+        if (mu) mu[i] = hu[hidx];
+    }
+    return SIGSDP_OK;
+}
+
+int sigsdp_solver_get_phase_times(sigsdp_solver* s, int count, double* us_host) {
+    if (!s || !us_host) return fail(SIGSDP_EINVAL, "null argument");
+    if (count < 0 || count > HIST || count > s->iters_done) return fail(SIGSDP_EINVAL, "count out of range");
+    CK(cudaSetDevice(s->plan->device));
+    CK(cudaDeviceSynchronize());
+    std::vector<double> ht((size_t)HIST * 3);
+    CK(cudaMemcpy(ht.data(), s->dtype == SIGSDP_F64 ? s->p64.hist_t : s->p32.hist_t, ht.size() * sizeof(double),
+                  cudaMemcpyDeviceToHost));
+    for (int i = 0; i < count; ++i) {
+        const long long it = s->iters_done - count + i;
+        for (int j = 0; j < 3; ++j) us_host[(size_t)i * 3 + j] = ht[(size_t)(it % HIST) * 3 + j];
+    }
+    return SIGSDP_OK;
+}
+
+int sigsdp_solver_total_terms(sigsdp_solver* s, int64_t* out) {
+    if (!s || !out) return fail(SIGSDP_EINVAL, "null argument");
+    CK(cudaSetDevice(s->plan->device));
+    CK(cudaDeviceSynchronize());
+    Ctrl hc;
+    CK(cudaMemcpy(&hc, s->dtype == SIGSDP_F64 ? s->p64.ctrl : s->p32.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost));
+    *out = hc.total_terms;
+    return SIGSDP_OK;
+}
+
+int sigsdp_debug_normals(uint64_t seed, int64_t iter, int n, int D, int dtype, double* out_host) {
+    if (!out_host || n <= 0 || D <= 0) return fail(SIGSDP_EINVAL, "bad argument");
+    double* d = nullptr;
+    CK(cudaMalloc(&d, (size_t)n * D * sizeof(double)));
+    if (dtype == SIGSDP_F64)
+        k_debug_normals<double><<<128, 256>>>(seed, iter, n, D, d);
+    else
+        k_debug_normals<float><<<128, 256>>>(seed, iter, n, D, d);
+    cudaError_t e = cudaMemcpy(out_host, d, (size_t)n * D * sizeof(double), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(SIGSDP_ECUDA, cudaGetErrorString(e));
+    return SIGSDP_OK;
+}
+
+
+static SolverView view_of(const sigsdp_solver* s) {
+    SolverView v;
+    if (s->dtype == SIGSDP_F64) {
+        const Prob<double>& P = s->p64;
+        v = SolverView{P.g, P.Z, P.C, P.nH, P.hcoef, P.Y, P.Ybar, P.Xd, P.Xe, P.Xbar_d, P.Xbar_e};
+    } else {
+        const Prob<float>& P = s->p32;
+        v = SolverView{P.g, P.Z, P.C, P.nH, P.hcoef, P.Y, P.Ybar, P.Xd, P.Xe, P.Xbar_d, P.Xbar_e};
+    }
+    return v;
+}
+static int ensure_scratch(sigsdp_solver* s) {
+    if (s->Mval) return SIGSDP_OK;
+    CK(s->mem.alloc(&s->Mval, s->plan->h.nnz));
+    CK(s->mem.alloc(&s->rtmp, s->plan->h.n));
+    CK(s->mem.alloc(&s->gscal, 8));
+    CK(s->mem.alloc(&s->gkey, 1));
+    return SIGSDP_OK;
+}
+
+int sigsdp_solver_xavg_matrix(sigsdp_solver* s, double scale, void* stream) {
+    if (!s) return fail(SIGSDP_EINVAL, "null solver");
+    CK(cudaSetDevice(s->plan->device));
+    int rc = ensure_scratch(s);
+    if (rc != SIGSDP_OK) return rc;
+    k_mat_xavg<<<s->plan->num_sms * 4, 256, 0, (cudaStream_t)stream>>>(view_of(s), scale, s->Mval);
+    CK(cudaGetLastError());
+    return SIGSDP_OK;
+}
+
+int sigsdp_solver_gap_prepare(sigsdp_solver* s, double* e_max_host, void* stream) {
+    if (!s || !e_max_host) return fail(SIGSDP_EINVAL, "null argument");
+    CK(cudaSetDevice(s->plan->device));
+    int rc = ensure_scratch(s);
+    if (rc != SIGSDP_OK) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const SolverView v = view_of(s);
+    const double N = (double)(s->iters_done + 1);
+    const int blocks = s->plan->num_sms * 4;
+    CK(cudaMemsetAsync(s->gkey, 0, sizeof(unsigned long long), st));
+    k_gap_rowsum<<<blocks, 256, 0, st>>>(v, N, s->rtmp);
+    k_gap_emax<<<blocks, 256, 0, st>>>(v, N, s->rtmp, s->gkey);
+    k_gap_sums<<<1, 1024, 0, st>>>(v, N, s->gscal);
+    k_gap_L<<<blocks, 256, 0, st>>>(v, N, s->gscal, s->Mval);
+    unsigned long long key = 0;
+    CK(cudaMemcpyAsync(&key, s->gkey, sizeof(key), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    unsigned long long b = (key >> 63) ? (key & 0x7fffffffffffffffull) : ~key;
+    std::memcpy(e_max_host, &b, sizeof(double));
+    return SIGSDP_OK;
+}
+
+int sigsdp_solver_symv(sigsdp_solver* s, const double* x_dev, double* y_dev, int nvec, void* stream) {
+    if (!s || !x_dev || !y_dev || nvec < 1) return fail(SIGSDP_EINVAL, "bad argument");
+    if (!s->Mval) return fail(SIGSDP_ESTATE, "no matrix prepared (call xavg_matrix or gap_prepare first)");
+    CK(cudaSetDevice(s->plan->device));
+    k_symv<<<s->plan->num_sms * 8, 256, 0, (cudaStream_t)stream>>>(s->plan->d, s->Mval, x_dev, y_dev, nvec);
+    CK(cudaGetLastError());
+    return SIGSDP_OK;
+}
+
+int sigsdp_solver_get_matrix(sigsdp_solver* s, double* vals_host) {
+    if (!s || !vals_host) return fail(SIGSDP_EINVAL, "null argument");
+    if (!s->Mval) return fail(SIGSDP_ESTATE, "no matrix prepared");
+    CK(cudaSetDevice(s->plan->device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(vals_host, s->Mval, s->plan->h.nnz * sizeof(double), cudaMemcpyDeviceToHost));
+    return SIGSDP_OK;
+}
+
+int sigsdp_plan_pattern(const sigsdp_plan* plan, int32_t* rowptr_host, int32_t* col_host) {
+    if (!plan) return fail(SIGSDP_EINVAL, "null plan");
+    if (rowptr_host) std::memcpy(rowptr_host, plan->h.rowptr.data(), plan->h.rowptr.size() * sizeof(int32_t));
+    if (col_host) std::memcpy(col_host, plan->h.col.data(), plan->h.col.size() * sizeof(int32_t));
+    return SIGSDP_OK;
+}
+
+int sigsdp_round_project(const sigsdp_plan* plan, const double* gX_dev, int r, const double* randv_dev, int Z,
+                         int32_t* pref_dev, double* norm_dev, void* stream) {
+    if (!plan || !gX_dev || !randv_dev || !pref_dev || !norm_dev) return fail(SIGSDP_EINVAL, "null argument");
+    if (r < 1 || Z < 1) return fail(SIGSDP_EINVAL, "r and Z must be positive");
+    CK(cudaSetDevice(plan->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = (int)plan->h.n;
+    double* inprod = nullptr;
+    CK(cudaMalloc(&inprod, (size_t)n * Z * sizeof(double)));
+    const int blocks = plan->num_sms * 4;
+    k_round_inprod<<<blocks, 256, 0, st>>>(gX_dev, n, r, randv_dev, Z, inprod, norm_dev);
+    k_round_pref<<<blocks, 256, 0, st>>>(inprod, n, Z, pref_dev);
+    cudaError_t e = cudaStreamSynchronize(st);
+    cudaFree(inprod);
+    if (e != cudaSuccess) return fail(SIGSDP_ECUDA, cudaGetErrorString(e));
+    return SIGSDP_OK;
+}
+
+int sigsdp_round_conflicts(const sigsdp_plan* plan, const int32_t* z_dev, double* I_dev_or_null, int64_t counts_host[2],
+                           void* stream) {
+    if (!plan || !z_dev || !counts_host) return fail(SIGSDP_EINVAL, "null argument");
+    CK(cudaSetDevice(plan->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long* d_counts = nullptr;
+    CK(cudaMalloc(&d_counts, 2 * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(d_counts, 0, 2 * sizeof(unsigned long long), st));
+    k_round_conflicts<<<plan->num_sms * 4, 256, 0, st>>>((int)plan->h.n, plan->d_STp, plan->d_STi, plan->d_STx,
+                                                         plan->d_hmax_caller, z_dev, (int)plan->h.E_a, plan->d_ai,
+                                                         plan->d_aj, I_dev_or_null, d_counts);
+    unsigned long long hcounts[2] = {0, 0};
+    cudaError_t e = cudaMemcpyAsync(hcounts, d_counts, sizeof(hcounts), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_counts);
+    if (e != cudaSuccess) return fail(SIGSDP_ECUDA, cudaGetErrorString(e));
+    counts_host[0] = (int64_t)hcounts[0];
+    counts_host[1] = (int64_t)hcounts[1];
+    return SIGSDP_OK;
+}
+
+int sigsdp_round_greedy(int64_t n, int Z, const int32_t* Sp, const int32_t* Si, const double* Sx, const int32_t* Qp,
+                        const int32_t* Qi, const double* Qx, const double* h_max, const int32_t* rank,
+                        const int32_t* pref, int32_t* z_vec, int64_t* remainder) {
+    std::string err;
+    int rc = round_greedy_host(n, Z, Sp, Si, Sx, Qp, Qi, Qx, h_max, rank, pref, z_vec, remainder, err);
+    if (rc != SIGSDP_OK) return fail(rc, err);
+    return SIGSDP_OK;
+}
+
+}  // extern "C"

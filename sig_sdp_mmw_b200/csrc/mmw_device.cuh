@@ -1,0 +1,797 @@
+// Device side of the MMW hot path: every phase of one iteration as a __device__
+// function over a "team" of thread blocks, so the same code runs
+//   * fused    : one persistent cooperative kernel, grid-wide barriers between phases,
+//   * stepwise : one kernel per phase (kernel boundaries are the barriers),
+//   * batch    : one thread block per independent instance (__syncthreads barriers).
+//
+// Arithmetic follows SURVEY.md App. A (reference sim_src/alg/mmw.py:77-197 and scipy's
+// expm_multiply, _expm_multiply.py:214-303); each phase cites its lines.
+#pragma once
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cg = cooperative_groups;
+
+namespace sigsdp {
+
+constexpr int NT = 512;          // threads per block
+constexpr int NWARP = NT / 32;
+constexpr int HIST = 8192;       // Taylor-controller history ring
+constexpr int PSTRIDE = 8;       // doubles per block in the partial-sum scratch
+
+// ---------------------------------------------------------------------------
+struct PlanDev {
+    int n, nnz, E_g, E_a;
+    const int* rowptr;      // n + 1
+    const int* col;         // nnz, ascending inside a row, diagonal included
+    const int* eid;         // nnz: -1 diag, [0,E_g) gain edge, E_g + a asso edge
+    const double* tfwd;     // nnz: T[row,col]
+    const double* tbwd;     // nnz: T[col,row]
+    const double* S_sum;    // n
+    const double* tnorm;    // n  sqrt(sum_c T[k,c]^2)
+    const double* h_max;    // n
+    const int* perm;        // n: internal -> caller numbering (nullptr = identity)
+};
+
+// device-resident controller: reductions that must be order independent use
+// atomicMax on the bit pattern of non-negative doubles
+struct Ctrl {
+    unsigned long long nrm_b[3];   // ||B_new||_inf per term slot
+    unsigned long long nrm_f[3];   // ||F||_inf per term slot
+    unsigned long long a1_key;     // ||A - mu I||_1
+    unsigned long long c1_key;     // ||Omega_hat||_inf
+    unsigned long long emax_key;   // max e_accu (order-preserving key)
+    double trL[2];                 // tr(L_accu), double-buffered by iteration parity
+    double mu;                     // shift of the current sketch (for exporting Y_h)
+    long long total_terms;
+    long long iter;                // iterations done since reset
+    // stepwise-mode controller (host reads these back)
+    int m_star, done, nterms;
+    long long s;
+    double c1, a1;
+};
+
+template <typename T>
+struct Prob {
+    PlanDev g;
+    int Z, D, Dp, C;
+    double eta;
+    double tol;
+    const double* nH;      // n  norm_H for this Z (mmw.py:39)
+    const double* hcoef;   // n  h/K - S_sum/(K Z)
+    double* Lval;          // nnz  L_accu on the union pattern
+    double* e_acc;         // C
+    double* u;             // C    exp(e_acc - max), unnormalised
+    double* Y;             // C
+    double* Ybar;          // C    running sum
+    double* q;             // n    u_H / norm_H
+    double* Xd;            // n
+    double* Xe;            // E
+    double* Xbar_d;        // n    running sums
+    double* Xbar_e;        // E
+    double* r;             // n    row sums of off-diagonal X
+    double* dsq;           // n    ||F_k||^2
+    T* B0;                 // n x Dp ping
+    T* B1;                 // n x Dp pong
+    T* F;                  // n x Dp
+    double* psum;          // [blocks][PSTRIDE] softmax sums
+    double* ptr;           // [blocks] trace partials
+    Ctrl* ctrl;
+    int* hist_m;           // HIST
+    int* hist_s;
+    int* hist_nt;
+    double* hist_a1;
+    double* hist_mu;
+    double* hist_t;        // HIST x 3: device-timed microseconds of dual / loss / sketch+Gram
+    const double* omega;   // raw normals for this call (caller numbering) or nullptr
+    unsigned long long seed;
+};
+
+// ---------------------------------------------------------------------------
+// teams
+struct GridTeam {
+    __device__ int rank() const { return blockIdx.x; }
+    __device__ int size() const { return gridDim.x; }
+    __device__ void sync() const { cg::this_grid().sync(); }
+};
+struct StepTeam {  // stepwise: the kernel boundary is the barrier
+    __device__ int rank() const { return blockIdx.x; }
+    __device__ int size() const { return gridDim.x; }
+    __device__ void sync() const {}
+};
+struct CtaTeam {  // batch: one block owns the instance
+    __device__ int rank() const { return 0; }
+    __device__ int size() const { return 1; }
+    __device__ void sync() const { __syncthreads(); }
+};
+
+// ---------------------------------------------------------------------------
+// small helpers
+__device__ __forceinline__ unsigned long long dkey_pos(double v) {  // v >= 0
+    return (unsigned long long)__double_as_longlong(v);
+}
+__device__ __forceinline__ double dkey_pos_inv(unsigned long long k) { return __longlong_as_double((long long)k); }
+__device__ __forceinline__ unsigned long long dkey_any(double v) {  // total order on all doubles
+    unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double dkey_any_inv(unsigned long long k) {
+    unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)b);
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ unsigned long long ld_u64(const unsigned long long* p) {
+    return *reinterpret_cast<const volatile unsigned long long*>(p);
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+// deterministic block reductions; result valid in every thread
+__device__ __forceinline__ double block_sum(double v, double* sh /* NWARP + 1 */) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double t = threadIdx.x < NWARP ? sh[threadIdx.x] : 0.0;
+        t = warp_sum(t);
+        if (threadIdx.x == 0) sh[NWARP] = t;
+    }
+    __syncthreads();
+    return sh[NWARP];
+}
+__device__ __forceinline__ double block_max(double v, double* sh) {
+    v = warp_max(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double t = threadIdx.x < NWARP ? sh[threadIdx.x] : -INFINITY;
+        t = warp_max(t);
+        if (threadIdx.x == 0) sh[NWARP] = t;
+    }
+    __syncthreads();
+    return sh[NWARP];
+}
+// sum of one double per block written by every block of the team before the last
+// barrier; fixed order, so every block (and every run) gets the same bits
+__device__ __forceinline__ double team_sum(const double* part, int stride, int nblk, double* sh) {
+    double t = 0.0;
+    if (threadIdx.x < 32) {
+        for (int b = threadIdx.x; b < nblk; b += 32) t += part[(size_t)b * stride];
+        t = warp_sum(t);
+        if (threadIdx.x == 0) sh[NWARP] = t;
+    }
+    __syncthreads();
+    t = sh[NWARP];
+    __syncthreads();
+    return t;
+}
+
+template <int G>
+__device__ __forceinline__ double group_sum(cg::thread_block_tile<G>& tile, double v) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v += tile.shfl_xor(v, o);
+    return v;
+}
+
+// vector of VEC sketch columns held by one lane
+template <typename T> struct Vec;
+template <> struct Vec<double> {
+    static constexpr int N = 2;
+    double v[2];
+    __device__ __forceinline__ void load(const double* p) {
+        double2 t = *reinterpret_cast<const double2*>(p);
+        v[0] = t.x; v[1] = t.y;
+    }
+    __device__ __forceinline__ void store(double* p) const { *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]); }
+};
+template <> struct Vec<float> {
+    static constexpr int N = 4;
+    float v[4];
+    __device__ __forceinline__ void load(const float* p) {
+        float4 t = *reinterpret_cast<const float4*>(p);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+    __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+};
+
+// ---------------------------------------------------------------------------
+// Philox4x32-10 + Box-Muller: counter-based normals for throughput mode
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+    const unsigned M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        unsigned hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
+        unsigned hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += W0;
+        k.y += W1;
+    }
+    return c;
+}
+// VEC standard normals for (iteration, row, first column of the vector)
+__device__ __forceinline__ void philox_normals(unsigned long long seed, long long iter, int row, int colv, double* out2) {
+    uint4 x = philox4x32_10(make_uint4((unsigned)row, (unsigned)colv, (unsigned)iter, (unsigned)(iter >> 32)),
+                            make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
+    double u1 = ((double)(((unsigned long long)x.x << 32) | x.y) + 0.5) * 5.421010862427522e-20;  // 2^-64
+    double u2 = ((double)(((unsigned long long)x.z << 32) | x.w) + 0.5) * 5.421010862427522e-20;
+    double rr = sqrt(-2.0 * log(u1));
+    double s, c;
+    sincospi(2.0 * u2, &s, &c);
+    out2[0] = rr * c;
+    out2[1] = rr * s;
+}
+__device__ __forceinline__ void philox_normals(unsigned long long seed, long long iter, int row, int colv, float* out4) {
+    uint4 x = philox4x32_10(make_uint4((unsigned)row, (unsigned)colv, (unsigned)iter, (unsigned)(iter >> 32)),
+                            make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
+    float u1 = ((float)x.x + 0.5f) * 2.3283064e-10f, u2 = ((float)x.y + 0.5f) * 2.3283064e-10f;
+    float u3 = ((float)x.z + 0.5f) * 2.3283064e-10f, u4 = ((float)x.w + 0.5f) * 2.3283064e-10f;
+    u1 = fminf(u1, 0.99999994f);
+    u3 = fminf(u3, 0.99999994f);
+    float r1 = sqrtf(-2.0f * logf(u1)), r2 = sqrtf(-2.0f * logf(u3));
+    float s, c;
+    sincospif(2.0f * u2, &s, &c);
+    out4[0] = r1 * c;
+    out4[1] = r1 * s;
+    sincospif(2.0f * u4, &s, &c);
+    out4[2] = r2 * c;
+    out4[3] = r2 * s;
+}
+
+// ---------------------------------------------------------------------------
+// Taylor degree selection: scipy _fragment_3_1 (_expm_multiply.py:503-558), the branch
+// taken when condition (3.13) holds: (m*, s) = argmin_m m ceil(||A||_1 / theta_m).
+__constant__ double c_theta[35] = {2.29e-16, 2.58e-8, 1.39e-5, 3.40e-4, 2.40e-3, 9.07e-3, 2.38e-2, 5.00e-2, 8.96e-2,
+                                   1.44e-1,  2.14e-1, 3.00e-1, 4.00e-1, 5.14e-1, 6.41e-1, 7.81e-1, 9.31e-1, 1.09,
+                                   1.26,     1.44,    1.62,    1.82,    2.01,    2.22,    2.43,    2.64,    2.86,
+                                   3.08,     3.31,    3.54,    4.7,     6.0,     7.2,     8.5,     9.9};
+__constant__ int c_theta_m[35] = {1,  2,  3,  4,  5,  6,  7,  8,  9,  10, 11, 12, 13, 14, 15, 16, 17, 18,
+                                  19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 35, 40, 45, 50, 55};
+
+__device__ __forceinline__ void taylor_select(double a1, int& m_star, long long& s) {
+    if (!(a1 > 0.0)) {
+        m_star = 0;
+        s = 1;
+        return;
+    }
+    double best = INFINITY;
+    int bm = 1;
+    double bs = 1.0;
+#pragma unroll 1
+    for (int i = 0; i < 35; ++i) {
+        double si = ceil(a1 / c_theta[i]);
+        double cost = (double)c_theta_m[i] * si;
+        if (cost < best) {
+            best = cost;
+            bm = c_theta_m[i];
+            bs = si;
+        }
+    }
+    m_star = bm;
+    s = bs < 9.0e15 ? (long long)bs : (long long)9.0e15;
+}
+
+// ===========================================================================
+// Phase DUAL (mmw.py:124-137): e = [eD | eF | eH], e_accu += eta e, running max.
+//   eD_k = (X_kk - 1)/(1 - 1/K)
+//   eF_e = (X_e + 1/(Z-1)) / (1/(K(Z-1)) + 1/2)            asso-UT edges
+//   eH_k = ((T r)_k (Z-1)/Z - (h_k - S_sum_k/Z)) / norm_H_k,  r = row sums of X_offdiag
+//          (quirk Q1: the reference's `*` is a sparse mat-mul)
+template <typename T, int G, class Team>
+__device__ void phase_dual(const Prob<T>& P, const Team& team, double* sh) {
+    const PlanDev& g = P.g;
+    const int K = g.n, Z = P.Z;
+    cg::thread_block_tile<G> tile = cg::tiled_partition<G>(cg::this_thread_block());
+    const int lane = tile.thread_rank();
+    const int grp = threadIdx.x / G;
+    constexpr int R = NT / G;
+    const double invD = 1.0 / (1.0 - 1.0 / K);
+    const double zr = (double)(Z - 1) / (double)Z;
+    const double cF = 1.0 / ((double)K * (Z - 1)) + 0.5;
+    double emax = -INFINITY;
+    if (team.rank() == 0 && threadIdx.x < 3) {  // all of these are idle between gram and the loss phase
+        P.ctrl->nrm_b[threadIdx.x] = 0ull;
+        P.ctrl->nrm_f[threadIdx.x] = 0ull;
+        if (threadIdx.x == 0) {
+            P.ctrl->a1_key = 0ull;
+            P.ctrl->c1_key = 0ull;
+        }
+    }
+    const int ntiles = (K + R - 1) / R;
+    for (int t = team.rank(); t < ntiles; t += team.size()) {
+        const int k = t * R + grp;
+        if (k < K) {
+            double acc = 0.0;
+            const int p1 = g.rowptr[k + 1];
+            for (int p = g.rowptr[k] + lane; p < p1; p += G) {
+                double tf = g.tfwd[p];
+                if (tf != 0.0) acc += tf * P.r[g.col[p]];
+            }
+            acc = group_sum<G>(tile, acc);
+            if (lane == 0) {
+                double eH = (acc * zr - (g.h_max[k] - g.S_sum[k] / Z)) / P.nH[k];
+                double eD = (P.Xd[k] - 1.0) * invD;
+                double a = P.e_acc[k] + P.eta * eD;
+                double b = P.e_acc[K + g.E_a + k] + P.eta * eH;
+                P.e_acc[k] = a;
+                P.e_acc[K + g.E_a + k] = b;
+                emax = fmax(emax, fmax(a, b));
+            }
+        }
+    }
+    const double zf = 1.0 / (Z - 1);
+    for (int e = team.rank() * NT + threadIdx.x; e < g.E_a; e += team.size() * NT) {
+        double eF = (P.Xe[g.E_g + e] + zf) / cF;
+        double a = P.e_acc[K + e] + P.eta * eF;
+        P.e_acc[K + e] = a;
+        emax = fmax(emax, a);
+    }
+    emax = block_max(emax, sh);
+    if (threadIdx.x == 0 && emax > -INFINITY) atomicMax(&P.ctrl->emax_key, dkey_any(emax));
+}
+
+// ===========================================================================
+// Phase EXP (mmw.py:139, scipy.special.softmax): u = exp(e_accu - max); partial sums
+//   S = sum u,  S_D = sum u_D,  S_F = sum u_F,  S_hq = sum_k hcoef_k u_Hk / norm_H_k
+// and q_k = u_Hk / norm_H_k for the loss phase.
+template <typename T, int G, class Team>
+__device__ void phase_exp(const Prob<T>& P, const Team& team, double* sh) {
+    const PlanDev& g = P.g;
+    const int K = g.n, C = P.C;
+    const double emax = dkey_any_inv(ld_u64(&P.ctrl->emax_key));
+    double sD = 0.0, sF = 0.0, sH = 0.0, sHq = 0.0;
+    for (int c = team.rank() * NT + threadIdx.x; c < C; c += team.size() * NT) {
+        double v = exp(P.e_acc[c] - emax);
+        P.u[c] = v;
+        if (c < K) {
+            sD += v;
+        } else if (c < K + g.E_a) {
+            sF += v;
+        } else {
+            int k = c - K - g.E_a;
+            double qq = v / P.nH[k];
+            P.q[k] = qq;
+            sH += v;
+            sHq += P.hcoef[k] * qq;
+        }
+    }
+    sD = block_sum(sD, sh);
+    sF = block_sum(sF, sh);
+    sH = block_sum(sH, sh);
+    sHq = block_sum(sHq, sh);
+    if (threadIdx.x == 0) {
+        double* o = P.psum + (size_t)team.rank() * PSTRIDE;
+        o[0] = sD;
+        o[1] = sF;
+        o[2] = sH;
+        o[3] = sHq;
+    }
+}
+
+// ===========================================================================
+// Phase LOSS (mmw.py:144-170 and csr_scal_rows_inplace, scipy_util.py:20-24, quirk Q2):
+//   Y = u / S;  Y_avgd += Y_prev (mmw.py:78)
+//   diag  l_k = (YD_k - sum YD / K)/(1 - 1/K) + (sum YF /(K(Z-1)))/cF - sum_k hcoef_k w_k
+//   asso  l_e = (YF_e / 2)/cF
+//   gain  l_e = (Z-1)/(2Z) (T[i,j] w_j + T[j,i] w_i),   w = YH / norm_H
+//   L_accu -= eta l                                                      (mmw.py:167)
+// plus what the sketch needs next: ||L_accu/2 - mu I||_1 with mu = tr(L_accu)/(2K)
+// (scipy _expm_multiply.py:259-266), Omega_hat = rows of randn/sqrt(D) normalised
+// (mmw.py:226-227) into B0 and F, ||Omega_hat||_inf, and ||Omega_hat_k||^2.
+template <typename T, int G, class Team>
+__device__ void phase_loss(const Prob<T>& P, const Team& team, int it_local, double* sh) {
+    using V = Vec<T>;
+    constexpr int VEC = V::N;
+    const PlanDev& g = P.g;
+    const int K = g.n, Z = P.Z, C = P.C, Dp = P.Dp, D = P.D;
+    cg::thread_block_tile<G> tile = cg::tiled_partition<G>(cg::this_thread_block());
+    const int lane = tile.thread_rank();
+    const int grp = threadIdx.x / G;
+    constexpr int R = NT / G;
+    Ctrl* ctrl = P.ctrl;
+
+    const double sD = team_sum(P.psum + 0, PSTRIDE, team.size(), sh);
+    const double sF = team_sum(P.psum + 1, PSTRIDE, team.size(), sh);
+    const double sH = team_sum(P.psum + 2, PSTRIDE, team.size(), sh);
+    const double sHq = team_sum(P.psum + 3, PSTRIDE, team.size(), sh);
+    const double S = sD + sF + sH;
+    const double cF = 1.0 / ((double)K * (Z - 1)) + 0.5;
+    const double invD = 1.0 / (1.0 - 1.0 / K);
+    const double sumYD = sD / S;
+    const double cLF = ((sF / S) / ((double)K * (Z - 1))) / cF;
+    const double cLH = sHq / S;
+    const double gcoef = (double)(Z - 1) / (2.0 * Z);
+    const double eta = P.eta;
+    const long long iter = ctrl->iter + it_local;
+    // tr(L_accu): sum_k l_k = K (cLF - cLH) + (sum YD - sum YD)/(1-1/K) analytically
+    const double trL = ctrl->trL[iter & 1] - eta * ((double)K * (cLF - cLH));
+    const double mu = 0.5 * trL / K;
+    if (team.rank() == 0 && threadIdx.x == 0) {
+        ctrl->trL[(iter + 1) & 1] = trL;
+        ctrl->mu = mu;
+        ctrl->emax_key = 0ull;  // read by everyone before the previous barrier
+    }
+
+    // ---- Y, Y_avgd
+    for (int c = team.rank() * NT + threadIdx.x; c < C; c += team.size() * NT) {
+        P.Ybar[c] += P.Y[c];
+        P.Y[c] = P.u[c] / S;
+    }
+
+    // ---- L_accu and the 1-norm of the shifted half
+    double a1 = 0.0;
+    const int ntiles = (K + R - 1) / R;
+    for (int t = team.rank(); t < ntiles; t += team.size()) {
+        const int k = t * R + grp;
+        if (k < K) {
+            const double wk = P.q[k] / S;
+            double rowabs = 0.0;
+            const int p1 = g.rowptr[k + 1];
+            for (int p = g.rowptr[k] + lane; p < p1; p += G) {
+                const int e = g.eid[p];
+                double l, shift = 0.0;
+                if (e < 0) {
+                    l = (P.u[k] / S - sumYD / K) * invD + cLF - cLH;
+                    shift = mu;
+                } else if (e < g.E_g) {
+                    const double wc = P.q[g.col[p]] / S;
+                    l = gcoef * (g.tfwd[p] * wc + g.tbwd[p] * wk);
+                } else {
+                    l = ((P.u[K + (e - g.E_g)] / S) * 0.5) / cF;
+                }
+                const double v = P.Lval[p] - eta * l;
+                P.Lval[p] = v;
+                rowabs += fabs(0.5 * v - shift);
+            }
+            rowabs = group_sum<G>(tile, rowabs);
+            a1 = fmax(a1, rowabs);
+        }
+    }
+
+    // ---- Omega_hat -> B0, F; ||.||_inf; ||row||^2
+    double c1 = 0.0, trp = 0.0;
+    const double sqrtD = sqrt((double)D);
+    for (int t = team.rank(); t < ntiles; t += team.size()) {
+        const int k = t * R + grp;
+        if (k < K) {
+            const int ko = g.perm ? g.perm[k] : k;
+            double ss = 0.0;
+            for (int c0 = lane * VEC; c0 < Dp; c0 += G * VEC) {
+                T raw[VEC];
+                if (P.omega) {
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v)
+                        raw[v] = (c0 + v < D) ? (T)(P.omega[((size_t)it_local * K + ko) * D + c0 + v] / sqrtD) : (T)0;
+                } else {
+                    philox_normals(P.seed, iter, ko, c0 / VEC, raw);
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) raw[v] = (c0 + v < D) ? (T)((double)raw[v] / sqrtD) : (T)0;
+                }
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) ss += (double)raw[v] * (double)raw[v];
+                V w;
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) w.v[v] = raw[v];
+                w.store(P.B0 + (size_t)k * Dp + c0);  // unnormalised for now
+            }
+            ss = group_sum<G>(tile, ss);
+            const double nrm = sqrt(ss);
+            double rs = 0.0, dd = 0.0;
+            for (int c0 = lane * VEC; c0 < Dp; c0 += G * VEC) {
+                V w;
+                w.load(P.B0 + (size_t)k * Dp + c0);
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) {
+                    w.v[v] = (T)((double)w.v[v] / nrm);
+                    rs += fabs((double)w.v[v]);
+                    dd += (double)w.v[v] * (double)w.v[v];
+                }
+                w.store(P.B0 + (size_t)k * Dp + c0);
+                w.store(P.F + (size_t)k * Dp + c0);
+            }
+            rs = group_sum<G>(tile, rs);
+            dd = group_sum<G>(tile, dd);
+            c1 = fmax(c1, rs);
+            if (lane == 0) {
+                P.dsq[k] = dd;
+                trp += dd;
+            }
+        }
+    }
+    a1 = block_max(a1, sh);
+    c1 = block_max(c1, sh);
+    trp = block_sum(trp, sh);
+    if (threadIdx.x == 0) {
+        atomicMax(&ctrl->a1_key, dkey_pos(a1));
+        atomicMax(&ctrl->c1_key, dkey_pos(c1));
+        P.ptr[team.rank()] = trp;
+    }
+}
+
+// ===========================================================================
+// One Taylor term (scipy _expm_multiply_simple_core, _expm_multiply.py:291-303), fused:
+//   B_new = coeff (A - mu I) B,  F += B_new,  ||B_new||_inf,  ||F||_inf,  ||F_k||^2
+// with A = L_accu / 2 read straight from the fp64 accumulator.  One group of G lanes
+// per row, each lane holds VEC consecutive sketch columns (16-byte loads); column
+// indices and values of G non-zeros are loaded coalesced and broadcast by shuffle.
+template <typename T, int G, class Team>
+__device__ void phase_term(const Prob<T>& P, const Team& team, const T* Bin, T* Bout, double coeff, double mu,
+                           int slot, double* sh) {
+    using V = Vec<T>;
+    constexpr int VEC = V::N;
+    const PlanDev& g = P.g;
+    const int K = g.n, Dp = P.Dp;
+    cg::thread_block_tile<G> tile = cg::tiled_partition<G>(cg::this_thread_block());
+    const int lane = tile.thread_rank();
+    const int grp = threadIdx.x / G;
+    constexpr int R = NT / G;
+    Ctrl* ctrl = P.ctrl;
+    if (team.rank() == 0 && threadIdx.x == 0) {  // slot+1 was last read two barriers ago
+        ctrl->nrm_b[(slot + 1) % 3] = 0ull;
+        ctrl->nrm_f[(slot + 1) % 3] = 0ull;
+    }
+    const T cf = (T)coeff;
+    double bmax = 0.0, fmaxv = 0.0, trp = 0.0;
+    const int ntiles = (K + R - 1) / R;
+    for (int t = team.rank(); t < ntiles; t += team.size()) {
+        const int k = t * R + grp;
+        if (k < K) {
+            const int p0 = g.rowptr[k], p1 = g.rowptr[k + 1];
+            double rsb = 0.0, rsf = 0.0, dd = 0.0;
+            for (int cb = 0; cb < Dp; cb += G * VEC) {
+                // every lane of the group runs every chunk so the shuffles below stay
+                // convergent; lanes past the row end only broadcast
+                const int c0 = cb + lane * VEC;
+                const bool act = c0 < Dp;
+                T acc[VEC];
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) acc[v] = (T)0;
+                for (int pb = p0; pb < p1; pb += G) {
+                    const int p = pb + lane;
+                    int cc = 0;
+                    T vv = (T)0;
+                    if (p < p1) {
+                        cc = g.col[p];
+                        double a = 0.5 * P.Lval[p];
+                        if (cc == k) a -= mu;
+                        vv = (T)a;
+                    }
+                    const int cnt = min(G, p1 - pb);
+#pragma unroll 4
+                    for (int j = 0; j < cnt; ++j) {
+                        const int cj = tile.shfl(cc, j);
+                        const T vj = tile.shfl(vv, j);
+                        if (act) {
+                            V b;
+                            b.load(Bin + (size_t)cj * Dp + c0);
+#pragma unroll
+                            for (int v = 0; v < VEC; ++v) acc[v] = fma(vj, b.v[v], acc[v]);
+                        }
+                    }
+                }
+                if (act) {
+                    V bn, f;
+                    f.load(P.F + (size_t)k * Dp + c0);
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) {
+                        bn.v[v] = cf * acc[v];
+                        f.v[v] += bn.v[v];
+                        rsb += fabs((double)bn.v[v]);
+                        rsf += fabs((double)f.v[v]);
+                        dd += (double)f.v[v] * (double)f.v[v];
+                    }
+                    bn.store(Bout + (size_t)k * Dp + c0);
+                    f.store(P.F + (size_t)k * Dp + c0);
+                }
+            }
+            rsb = group_sum<G>(tile, rsb);
+            rsf = group_sum<G>(tile, rsf);
+            dd = group_sum<G>(tile, dd);
+            bmax = fmax(bmax, rsb);
+            fmaxv = fmax(fmaxv, rsf);
+            if (lane == 0) {
+                P.dsq[k] = dd;
+                trp += dd;
+            }
+        }
+    }
+    bmax = block_max(bmax, sh);
+    fmaxv = block_max(fmaxv, sh);
+    trp = block_sum(trp, sh);
+    if (threadIdx.x == 0) {
+        atomicMax(&ctrl->nrm_b[slot], dkey_pos(bmax));
+        atomicMax(&ctrl->nrm_f[slot], dkey_pos(fmaxv));
+        P.ptr[team.rank()] = trp;
+    }
+}
+
+// B <- F at an s-step boundary (scipy _expm_multiply.py:301-303 without the eta scaling,
+// which is deferred: exp(A) B = e^mu prod_s T_m((A - mu I)/s) B)
+template <typename T, int G, class Team>
+__device__ void phase_copy(const Prob<T>& P, const Team& team, T* Bdst) {
+    const size_t tot = (size_t)P.g.n * P.Dp;
+    for (size_t i = (size_t)team.rank() * NT + threadIdx.x; i < tot; i += (size_t)team.size() * NT) Bdst[i] = P.F[i];
+}
+
+// ===========================================================================
+// Phase GRAM (mmw.py:182-194, 77): X = sketch Gram on the pattern only, normalised by
+// tr = sum_k ||y_k||^2 / K; running sum X_avgd += X_prev; r = row sums of X_offdiag for
+// the next dual step.  Row-parallel over the symmetric pattern: each directed entry is
+// a dot product of two sketch rows; the entry with row < col owns the edge's storage.
+template <typename T, int G, class Team>
+__device__ void phase_gram(const Prob<T>& P, const Team& team, double* sh) {
+    using V = Vec<T>;
+    constexpr int VEC = V::N;
+    const PlanDev& g = P.g;
+    const int K = g.n, Dp = P.Dp;
+    cg::thread_block_tile<G> tile = cg::tiled_partition<G>(cg::this_thread_block());
+    const int lane = tile.thread_rank();
+    const int grp = threadIdx.x / G;
+    constexpr int R = NT / G;
+    const double tr = team_sum(P.ptr, 1, team.size(), sh) / K;
+    const bool one_chunk = Dp <= G * VEC;
+    const int ntiles = (K + R - 1) / R;
+    for (int t = team.rank(); t < ntiles; t += team.size()) {
+        const int k = t * R + grp;
+        if (k < K) {
+            const int p0 = g.rowptr[k], p1 = g.rowptr[k + 1];
+            V fk;
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) fk.v[v] = (T)0;
+            if (one_chunk && lane * VEC < Dp) fk.load(P.F + (size_t)k * Dp + lane * VEC);
+            double rsum = 0.0;
+            for (int pb = p0; pb < p1; pb += G) {
+                const int p = pb + lane;
+                int cc = 0, ee = -1;
+                if (p < p1) {
+                    cc = g.col[p];
+                    ee = g.eid[p];
+                }
+                const int cnt = min(G, p1 - pb);
+                double mine = 0.0;
+                for (int j = 0; j < cnt; ++j) {
+                    const int cj = tile.shfl(cc, j);
+                    T part = (T)0;
+                    if (cj != k) {
+                        if (one_chunk) {
+                            if (lane * VEC < Dp) {
+                                V b;
+                                b.load(P.F + (size_t)cj * Dp + lane * VEC);
+#pragma unroll
+                                for (int v = 0; v < VEC; ++v) part = fma(fk.v[v], b.v[v], part);
+                            }
+                        } else {
+                            for (int c0 = lane * VEC; c0 < Dp; c0 += G * VEC) {
+                                V a, b;
+                                a.load(P.F + (size_t)k * Dp + c0);
+                                b.load(P.F + (size_t)cj * Dp + c0);
+#pragma unroll
+                                for (int v = 0; v < VEC; ++v) part = fma(a.v[v], b.v[v], part);
+                            }
+                        }
+                    }
+                    double dot = group_sum<G>(tile, (double)part);
+                    if (j == lane) mine = dot;
+                }
+                if (p < p1 && ee >= 0) {
+                    const double x = mine / tr;
+                    rsum += x;
+                    if (k < cc) {
+                        P.Xbar_e[ee] += P.Xe[ee];
+                        P.Xe[ee] = x;
+                    }
+                }
+            }
+            rsum = group_sum<G>(tile, rsum);
+            if (lane == 0) {
+                P.r[k] = rsum;
+                P.Xbar_d[k] += P.Xd[k];
+                P.Xd[k] = P.dsq[k] / tr;
+            }
+        }
+    }
+}
+
+// ===========================================================================
+// controller pieces shared by the fused kernel and the stepwise host loop
+struct TaylorState {
+    int m_star;
+    long long s;
+    double c1, a1, mu;
+};
+
+__device__ __forceinline__ void taylor_begin(const Ctrl* ctrl, TaylorState& ts) {
+    ts.a1 = dkey_pos_inv(ld_u64(&ctrl->a1_key));
+    ts.c1 = dkey_pos_inv(ld_u64(&ctrl->c1_key));
+    ts.mu = *reinterpret_cast<const volatile double*>(&ctrl->mu);
+    taylor_select(ts.a1, ts.m_star, ts.s);
+}
+
+template <typename T>
+__device__ __forceinline__ void record_history(const Prob<T>& P, long long iter, const TaylorState& ts, int nterms) {
+    const int h = (int)(iter % HIST);
+    P.hist_m[h] = ts.m_star;
+    P.hist_s[h] = (int)(ts.s < 0x7fffffff ? ts.s : 0x7fffffff);
+    P.hist_nt[h] = nterms;
+    P.hist_a1[h] = ts.a1;
+    P.hist_mu[h] = ts.mu;
+}
+
+// The whole MMW loop for one team: n_iters iterations, no host involvement.
+template <typename T, int G, class Team>
+__device__ void run_iterations(const Prob<T>& P, const Team& team, int n_iters) {
+    __shared__ double sh[NWARP + 2];
+    Ctrl* ctrl = P.ctrl;
+    long long terms = 0;
+    const bool leader = team.rank() == 0 && threadIdx.x == 0;
+    for (int it = 0; it < n_iters; ++it) {
+        unsigned long long t0 = 0, t1 = 0, t2 = 0;
+        if (leader) t0 = globaltimer_ns();
+        phase_dual<T, G>(P, team, sh);
+        team.sync();
+        phase_exp<T, G>(P, team, sh);
+        team.sync();
+        if (leader) t1 = globaltimer_ns();
+        phase_loss<T, G>(P, team, it, sh);
+        team.sync();
+        if (leader) t2 = globaltimer_ns();
+        TaylorState ts;
+        taylor_begin(ctrl, ts);
+        T* bin = P.B0;
+        T* bout = P.B1;
+        int tcount = 0;
+        double c1 = ts.c1, fn_last = ts.c1;
+        for (long long si = 0; si < ts.s; ++si) {
+            if (si > 0) {
+                phase_copy<T, G>(P, team, bin);
+                c1 = fn_last;
+                team.sync();
+            }
+            for (int j = 0; j < ts.m_star; ++j) {
+                const int slot = tcount % 3;
+                phase_term<T, G>(P, team, bin, bout, 1.0 / ((double)ts.s * (double)(j + 1)), ts.mu, slot, sh);
+                team.sync();
+                const double c2 = dkey_pos_inv(ld_u64(&ctrl->nrm_b[slot]));
+                fn_last = dkey_pos_inv(ld_u64(&ctrl->nrm_f[slot]));
+                T* tmp = bin;
+                bin = bout;
+                bout = tmp;
+                ++tcount;
+                if (c1 + c2 <= P.tol * fn_last) break;
+                c1 = c2;
+            }
+        }
+        terms += tcount;
+        phase_gram<T, G>(P, team, sh);
+        team.sync();
+        if (leader) {
+            const long long iter = ctrl->iter + it;
+            record_history(P, iter, ts, tcount);
+            const unsigned long long t3 = globaltimer_ns();
+            double* ht = P.hist_t + (size_t)(iter % HIST) * 3;
+            ht[0] = (double)(t1 - t0) * 1e-3;
+            ht[1] = (double)(t2 - t1) * 1e-3;
+            ht[2] = (double)(t3 - t2) * 1e-3;
+        }
+    }
+    if (team.rank() == 0 && threadIdx.x == 0) {
+        ctrl->iter += n_iters;
+        ctrl->total_terms += terms;
+    }
+}
+
+}  // namespace sigsdp

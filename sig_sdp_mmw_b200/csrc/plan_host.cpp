@@ -1,0 +1,386 @@
+// Host-side graph plan builder and the sequential rounding pass (native C++).
+// Follows mmw.py:26-41 (_process_state), mmw.py:52-57 (edge lists) and
+// sdp_solver.py:70-101 (greedy feasibility pass) of the reference; written against
+// flat CSR arrays instead of scipy objects.
+#include "plan_host.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <numeric>
+#include <queue>
+
+#include "../../include/sigsdp_mmw.h"
+
+namespace sigsdp {
+namespace {
+
+bool check_csr(int64_t n, const int32_t* p, const int32_t* idx, const char* name, std::string& err) {
+    if (p[0] != 0) {
+        err = std::string(name) + ": indptr[0] != 0";
+        return false;
+    }
+    for (int64_t r = 0; r < n; ++r) {
+        if (p[r + 1] < p[r]) {
+            err = std::string(name) + ": indptr not monotone";
+            return false;
+        }
+        for (int32_t q = p[r]; q < p[r + 1]; ++q) {
+            if (idx[q] < 0 || idx[q] >= n) {
+                err = std::string(name) + ": column index out of range";
+                return false;
+            }
+            if (q > p[r] && idx[q] <= idx[q - 1]) {
+                err = std::string(name) + ": indices must be sorted and duplicate-free per row";
+                return false;
+            }
+        }
+    }
+    return true;
+}
+
+// value of the CSR entry (r, c) or 0
+inline double csr_at(const int32_t* p, const int32_t* idx, const double* x, int32_t r, int32_t c) {
+    const int32_t* b = idx + p[r];
+    const int32_t* e = idx + p[r + 1];
+    const int32_t* it = std::lower_bound(b, e, c);
+    if (it == e || *it != c) return 0.0;
+    return x[it - idx];
+}
+
+struct Ent {
+    int32_t col;
+    int32_t kind;  // 0 diag, 1 gain, 2 asso
+    double tf, tb;
+};
+
+// Clustered BFS ordering: grow clusters of ~cluster nodes breadth-first, visiting the
+// graph cluster by cluster so that the rows of one CTA tile are a compact patch of
+// the (geometric) interference graph and share their neighbours.
+void locality_order(const HostPlan& P, int cluster, std::vector<int32_t>& perm) {
+    const int64_t n = P.n;
+    perm.clear();
+    perm.reserve(n);
+    std::vector<uint8_t> seen(n, 0);
+    std::vector<int32_t> frontier;  // nodes adjacent to finished clusters, FIFO
+    size_t fhead = 0;
+    std::vector<int32_t> q;
+    for (int64_t start = 0; start < n; ++start) {
+        if (seen[start]) continue;
+        frontier.push_back((int32_t)start);
+        while (fhead < frontier.size()) {
+            int32_t seed = frontier[fhead++];
+            if (seen[seed]) continue;
+            // BFS from seed limited to `cluster` nodes
+            q.clear();
+            q.push_back(seed);
+            seen[seed] = 1;
+            size_t qh = 0;
+            while (qh < q.size()) {
+                int32_t u = q[qh++];
+                for (int32_t e = P.rowptr[u]; e < P.rowptr[u + 1]; ++e) {
+                    int32_t v = P.col[e];
+                    if (seen[v]) continue;
+                    if ((int)q.size() < cluster) {
+                        seen[v] = 1;
+                        q.push_back(v);
+                    } else {
+                        frontier.push_back(v);
+                    }
+                }
+            }
+            for (int32_t u : q) perm.push_back(u);
+        }
+    }
+}
+
+}  // namespace
+
+int build_host_plan(int64_t n, const int32_t* Sp, const int32_t* Si, const double* Sx,
+                    const int32_t* Qp, const int32_t* Qi, const double* Qx, const double* h_max,
+                    int order, HostPlan& P, std::string& err) {
+    if (n <= 1 || n > (int64_t)1 << 30) {
+        err = "n must be in [2, 2^30]";
+        return SIGSDP_EINVAL;
+    }
+    if (!Sp || !Si || !Sx || !Qp || !Qi || !Qx || !h_max) {
+        err = "null input array";
+        return SIGSDP_EINVAL;
+    }
+    if (!check_csr(n, Sp, Si, "S_gain", err) || !check_csr(n, Qp, Qi, "Q_asso", err)) return SIGSDP_EINVAL;
+    P = HostPlan();
+    P.n = n;
+    P.order = order;
+
+    // Q_asso must be symmetric with an empty diagonal (the reference counts
+    // E_asso = nnz(Q)/2 and indexes triu(Q,1), mmw.py:57-59)
+    for (int64_t i = 0; i < n; ++i)
+        for (int32_t q = Qp[i]; q < Qp[i + 1]; ++q) {
+            if (Qx[q] == 0.0) continue;
+            int32_t j = Qi[q];
+            if (j == i) {
+                err = "Q_asso has a non-zero diagonal entry";
+                return SIGSDP_EINVAL;
+            }
+            if (csr_at(Qp, Qi, Qx, j, (int32_t)i) == 0.0) {
+                err = "Q_asso is not structurally symmetric";
+                return SIGSDP_EINVAL;
+            }
+        }
+
+    // ---- T = S^T with association pairs and the diagonal zeroed (mmw.py:28-33)
+    std::vector<int32_t> Tp(n + 1, 0), Ti;
+    std::vector<double> Tx;
+    {
+        for (int64_t j = 0; j < n; ++j)
+            for (int32_t q = Sp[j]; q < Sp[j + 1]; ++q) {
+                int32_t i = Si[q];
+                if (Sx[q] == 0.0 || i == j) continue;
+                if (csr_at(Qp, Qi, Qx, i, (int32_t)j) != 0.0) continue;
+                Tp[i + 1]++;
+            }
+        for (int64_t i = 0; i < n; ++i) Tp[i + 1] += Tp[i];
+        Ti.resize(Tp[n]);
+        Tx.resize(Tp[n]);
+        std::vector<int32_t> fill(Tp.begin(), Tp.end() - 1);
+        for (int64_t j = 0; j < n; ++j)
+            for (int32_t q = Sp[j]; q < Sp[j + 1]; ++q) {
+                int32_t i = Si[q];
+                if (Sx[q] == 0.0 || i == j) continue;
+                if (csr_at(Qp, Qi, Qx, i, (int32_t)j) != 0.0) continue;
+                Ti[fill[i]] = (int32_t)j;
+                Tx[fill[i]] = Sx[q];
+                fill[i]++;
+            }
+    }
+    P.nnzT = Tp[n];
+    // transpose of T (rows = columns of T), for the symmetric pattern
+    std::vector<int32_t> TTp(n + 1, 0), TTi(Tp[n]);
+    std::vector<double> TTx(Tp[n]);
+    {
+        for (int32_t q = 0; q < Tp[n]; ++q) TTp[Ti[q] + 1]++;
+        for (int64_t i = 0; i < n; ++i) TTp[i + 1] += TTp[i];
+        std::vector<int32_t> fill(TTp.begin(), TTp.end() - 1);
+        for (int64_t i = 0; i < n; ++i)
+            for (int32_t q = Tp[i]; q < Tp[i + 1]; ++q) {
+                int32_t j = Ti[q];
+                TTi[fill[j]] = (int32_t)i;
+                TTx[fill[j]] = Tx[q];
+                fill[j]++;
+            }
+    }
+
+    // ---- S_sum = T 1 and sqrt((T o T) 1) (mmw.py:34-39)
+    std::vector<double> S_sum(n), tnorm(n);
+    for (int64_t i = 0; i < n; ++i) {
+        double s = 0.0, s2 = 0.0;
+        for (int32_t q = Tp[i]; q < Tp[i + 1]; ++q) {
+            s += Tx[q];
+            s2 += Tx[q] * Tx[q];
+        }
+        S_sum[i] = s;
+        tnorm[i] = std::sqrt(s2);
+    }
+
+    // ---- union pattern: diag + gain (T + T^T != 0) + asso, per row, columns ascending
+    std::vector<int32_t> rowptr(n + 1, 0);
+    std::vector<Ent> ents;
+    ents.reserve((size_t)Tp[n] * 2 + n + Qp[n]);
+    std::vector<Ent> row;
+    std::vector<int64_t> g_ut(n + 1, 0), a_ut(n + 1, 0);
+    for (int64_t i = 0; i < n; ++i) {
+        row.clear();
+        row.push_back(Ent{(int32_t)i, 0, 0.0, 0.0});
+        // merge T row i (forward) and T^T row i (backward)
+        int32_t a = Tp[i], ae = Tp[i + 1], b = TTp[i], be = TTp[i + 1];
+        while (a < ae || b < be) {
+            int32_t ca = a < ae ? Ti[a] : INT32_MAX, cb = b < be ? TTi[b] : INT32_MAX;
+            Ent e{0, 1, 0.0, 0.0};
+            if (ca == cb) {
+                e.col = ca; e.tf = Tx[a]; e.tb = TTx[b]; ++a; ++b;
+            } else if (ca < cb) {
+                e.col = ca; e.tf = Tx[a]; ++a;
+            } else {
+                e.col = cb; e.tb = TTx[b]; ++b;
+            }
+            if (e.tf + e.tb == 0.0) continue;  // eliminate_zeros on T + T^T (mmw.py:54)
+            row.push_back(e);
+        }
+        for (int32_t q = Qp[i]; q < Qp[i + 1]; ++q)
+            if (Qx[q] != 0.0) row.push_back(Ent{Qi[q], 2, 0.0, 0.0});
+        std::sort(row.begin(), row.end(), [](const Ent& x, const Ent& y) { return x.col < y.col; });
+        for (size_t k = 1; k < row.size(); ++k)
+            if (row[k].col == row[k - 1].col) {
+                err = "a node pair is both a gain edge and an association edge";
+                return SIGSDP_EINVAL;
+            }
+        for (const Ent& e : row) {
+            if (e.col > i && e.kind == 1) g_ut[i + 1]++;
+            if (e.col > i && e.kind == 2) a_ut[i + 1]++;
+            ents.push_back(e);
+        }
+        rowptr[i + 1] = (int32_t)ents.size();
+        P.max_row = std::max<int>(P.max_row, (int)row.size());
+    }
+    if (ents.size() > (size_t)INT32_MAX) {
+        err = "pattern too large for int32 indices";
+        return SIGSDP_EINVAL;
+    }
+    for (int64_t i = 0; i < n; ++i) {
+        g_ut[i + 1] += g_ut[i];
+        a_ut[i + 1] += a_ut[i];
+    }
+    P.E_g = g_ut[n];
+    P.E_a = a_ut[n];
+    P.nnz = (int64_t)ents.size();
+
+    // ---- edge ids in the reference's order (row-major upper triangle, mmw.py:56-57)
+    std::vector<int32_t> col(P.nnz), eid(P.nnz);
+    std::vector<double> tfwd(P.nnz), tbwd(P.nnz);
+    P.gi.resize(P.E_g); P.gj.resize(P.E_g); P.tij.resize(P.E_g); P.tji.resize(P.E_g);
+    P.ai.resize(P.E_a); P.aj.resize(P.E_a);
+    for (int64_t i = 0; i < n; ++i) {
+        int64_t g = g_ut[i], a = a_ut[i];
+        for (int32_t q = rowptr[i]; q < rowptr[i + 1]; ++q) {
+            const Ent& e = ents[q];
+            col[q] = e.col;
+            tfwd[q] = e.tf;
+            tbwd[q] = e.tb;
+            eid[q] = -1;
+            if (e.col > i) {
+                if (e.kind == 1) {
+                    P.gi[g] = (int32_t)i; P.gj[g] = e.col; P.tij[g] = e.tf; P.tji[g] = e.tb;
+                    eid[q] = (int32_t)g++;
+                } else {
+                    P.ai[a] = (int32_t)i; P.aj[a] = e.col;
+                    eid[q] = (int32_t)(P.E_g + a++);
+                }
+            }
+        }
+    }
+    for (int64_t i = 0; i < n; ++i)
+        for (int32_t q = rowptr[i]; q < rowptr[i + 1]; ++q) {
+            int32_t j = col[q];
+            if (j >= i) continue;
+            const int32_t* b = col.data() + rowptr[j];
+            const int32_t* e = col.data() + rowptr[j + 1];
+            const int32_t* it = std::lower_bound(b, e, (int32_t)i);
+            if (it == e || *it != i) {
+                err = "internal: asymmetric union pattern";
+                return SIGSDP_EINVAL;
+            }
+            eid[q] = eid[it - col.data()];
+        }
+
+    P.rowptr.swap(rowptr);
+    P.col.swap(col);
+    P.eid.swap(eid);
+    P.tfwd.swap(tfwd);
+    P.tbwd.swap(tbwd);
+    P.S_sum.swap(S_sum);
+    P.tnorm.swap(tnorm);
+    P.h_max.assign(h_max, h_max + n);
+    P.perm.resize(n);
+    P.iperm.resize(n);
+    std::iota(P.perm.begin(), P.perm.end(), 0);
+    std::iota(P.iperm.begin(), P.iperm.end(), 0);
+
+    if (order != 0) {
+        // renumber nodes for locality; edge ids and edge lists keep the caller's order
+        std::vector<int32_t> perm;
+        locality_order(P, order > 1 ? order : 64, perm);
+        std::vector<int32_t> iperm(n);
+        for (int64_t k = 0; k < n; ++k) iperm[perm[k]] = (int32_t)k;
+        std::vector<int32_t> rp(n + 1, 0), c2(P.nnz), e2(P.nnz);
+        std::vector<double> f2(P.nnz), b2(P.nnz);
+        std::vector<int32_t> ord;
+        int32_t w = 0;
+        for (int64_t k = 0; k < n; ++k) {
+            int32_t o = perm[k];
+            int32_t b = P.rowptr[o], e = P.rowptr[o + 1];
+            ord.resize(e - b);
+            std::iota(ord.begin(), ord.end(), b);
+            std::sort(ord.begin(), ord.end(), [&](int32_t x, int32_t y) { return iperm[P.col[x]] < iperm[P.col[y]]; });
+            for (int32_t q : ord) {
+                c2[w] = iperm[P.col[q]];
+                e2[w] = P.eid[q];
+                f2[w] = P.tfwd[q];
+                b2[w] = P.tbwd[q];
+                ++w;
+            }
+            rp[k + 1] = w;
+        }
+        auto permute = [&](std::vector<double>& v) {
+            std::vector<double> t(n);
+            for (int64_t k = 0; k < n; ++k) t[k] = v[perm[k]];
+            v.swap(t);
+        };
+        permute(P.S_sum);
+        permute(P.tnorm);
+        permute(P.h_max);
+        P.rowptr.swap(rp);
+        P.col.swap(c2);
+        P.eid.swap(e2);
+        P.tfwd.swap(f2);
+        P.tbwd.swap(b2);
+        P.perm.swap(perm);
+        P.iperm.swap(iperm);
+    }
+    return SIGSDP_OK;
+}
+
+int round_greedy_host(int64_t n, int Z, const int32_t* Sp, const int32_t* Si, const double* Sx,
+                      const int32_t* Qp, const int32_t* Qi, const double* Qx, const double* h_max,
+                      const int32_t* rank, const int32_t* pref, int32_t* z_vec, int64_t* remainder,
+                      std::string& err) {
+    if (n <= 0 || Z <= 0 || !Sp || !Si || !Sx || !Qp || !Qi || !Qx || !h_max || !rank || !pref || !z_vec || !remainder) {
+        err = "bad argument";
+        return SIGSDP_EINVAL;
+    }
+    // gain_sum[z][c]: interference already committed into slot z at user c; asso_sum alike
+    std::vector<double> gain_sum((size_t)Z * n, 0.0), asso_sum((size_t)Z * n, 0.0);
+    std::vector<int32_t> slot(n, -1);
+    int64_t rem = 0;
+    for (int64_t kk = 0; kk < n; ++kk) {
+        int32_t k = rank[kk];
+        if (k < 0 || k >= n) {
+            err = "rank entry out of range";
+            return SIGSDP_EINVAL;
+        }
+        int32_t chosen = -1;
+        for (int zz = 0; zz < Z && chosen < 0; ++zz) {
+            int32_t z = pref[(size_t)k * Z + zz];
+            if (z < 0 || z >= Z) {
+                err = "pref entry out of range";
+                return SIGSDP_EINVAL;
+            }
+            double* gs = gain_sum.data() + (size_t)z * n;
+            double* as = asso_sum.data() + (size_t)z * n;
+            bool vio = gs[k] > h_max[k];  // S[k,k] is zeroed (sdp_solver.py:33)
+            for (int32_t q = Sp[k]; q < Sp[k + 1] && !vio; ++q) {
+                int32_t c = Si[q];
+                if (c == k || Sx[q] == 0.0 || slot[c] != z) continue;
+                vio = gs[c] + Sx[q] > h_max[c];
+            }
+            if (vio) continue;
+            vio = as[k] >= 1.0;
+            for (int32_t q = Qp[k]; q < Qp[k + 1] && !vio; ++q) {
+                int32_t c = Qi[q];
+                if (slot[c] != z) continue;
+                vio = as[c] + Qx[q] >= 1.0;
+            }
+            if (vio) continue;
+            for (int32_t q = Sp[k]; q < Sp[k + 1]; ++q)
+                if (Si[q] != k) gs[Si[q]] += Sx[q];
+            for (int32_t q = Qp[k]; q < Qp[k + 1]; ++q) as[Qi[q]] += Qx[q];
+            chosen = z;
+        }
+        slot[k] = chosen;
+        if (chosen < 0) ++rem;
+    }
+    for (int64_t k = 0; k < n; ++k) z_vec[k] = slot[k];
+    *remainder = rem;
+    return SIGSDP_OK;
+}
+
+}  // namespace sigsdp

@@ -1,0 +1,156 @@
+"""class mmw: the reference's solver object (sim_src/alg/mmw.py:12-229) with the work done
+by hand-written sm_100a kernels behind the C ABI of include/sigsdp_mmw.h.
+
+Same constructor, attributes, methods, return values and LOGGED_NP_DATA keys as the
+reference, so `binary_search_relaxation.feasibility_check_alg = mmw(...)` and the
+sim_script drivers run unchanged.  Extra keyword arguments select what the reference
+has no notion of (all default to the reference's behaviour):
+
+  dtype   : "float64" (default) or "float32" sketch block
+  omega   : "numpy"  -- draw np.random.randn(K, D) per iteration on numpy's global stream
+                       exactly where the reference does (mmw.py:226), so a seeded run
+                       reproduces the reference's Omega and everything downstream;
+            "device" -- counter-based Philox normals generated inside the kernel
+                       (throughput mode; statistically equivalent, different stream)
+  device  : CUDA device index
+  order   : 0 keep the caller's node numbering inside the kernels, 1 renumber for locality
+
+There is no CPU fallback: a missing library or CUDA device raises."""
+import math
+
+import numpy as np
+
+from . import _lib
+from .lanczos import thick_restart_lanczos
+from .sdp_solver import sdp_solver
+from .stats import STATS_OBJECT
+
+# host staging budget for the numpy Omega stream (bytes per kernel launch)
+_OMEGA_CHUNK_BYTES = 1 << 30
+
+
+class mmw(STATS_OBJECT, sdp_solver):
+    def __init__(self, nit=100, rank_radio=2, alpha=1., eta=0.1, log_gap=False,
+                 dtype="float64", omega="numpy", device=0, order=0, seed=0):
+        sdp_solver.__init__(self, nit=nit, rank_radio=rank_radio, alpha=alpha)
+        self.eta = eta
+        self.LOG_GAP = log_gap
+        self.dtype = dtype
+        self.omega = omega
+        self.device = device
+        self.plan_order = order
+        self.seed = seed
+        self.mode = _lib.MODE_FUSED
+        self.last_solver = None
+
+    def run_with_state(self, bs_iteration, Z, state):
+        tic = self._get_tic()
+        ret = self._run(Z, state)
+        tim = self._get_tim(tic)
+        K = state[0].shape[0]
+        self._add_np_log("mmw_all_it", bs_iteration, np.array([Z, K, tim]))
+        return ret
+
+    # ------------------------------------------------------------------ internals
+    def _dtype_code(self):
+        if self.dtype in ("float64", "f64", np.float64):
+            return _lib.F64
+        if self.dtype in ("float32", "f32", np.float32):
+            return _lib.F32
+        raise ValueError("dtype must be 'float64' or 'float32'")
+
+    def _matmat(self, solver, torch, dev):
+        n = solver.plan.n
+
+        def mm(X):
+            X = X.contiguous()
+            Y = torch.empty_like(X)
+            solver.symv(X.data_ptr(), Y.data_ptr(), X.shape[0], torch.cuda.current_stream().cuda_stream)
+            return Y
+        return mm
+
+    def _gap_row(self, solver, torch, dev):
+        """mmw.py:79-117 for the state at the start of the next iteration."""
+        e_max = solver.gap_prepare(torch.cuda.current_stream().cuda_stream)
+        n = solver.plan.n
+        g = torch.Generator(device="cpu").manual_seed(12345)
+        v0 = torch.randn(n, dtype=torch.float64, generator=g).to(dev)
+        lam, _, _ = thick_restart_lanczos(self._matmat(solver, torch, dev), n, 1, "SA", v0, ncv=40, tol=1e-10)
+        lam_min = float(lam[0]) * n
+        return np.array([e_max, lam_min, e_max - lam_min])
+
+    def _run(self, Z, state):
+        import torch
+        if not torch.cuda.is_available():
+            raise _lib.SigSdpError("no CUDA device: sig_sdp_mmw_b200 has no CPU fallback")
+        sp_tic = self._get_tic()
+        K = state[0].shape[0]
+        D = Z * self.rank_radio                                   # mmw.py:180
+        plan = self._plan_for(state)
+        solver = _lib.Solver(plan, Z, D, self.eta, self._dtype_code(), self.mode)
+        self.last_solver = solver
+        dev = torch.device("cuda", plan.device)
+        self._add_np_log("mmw_state_process", 0, np.array([Z, K, self._get_tim(sp_tic)]))
+
+        nit = int(self.nit)
+        self.N_STEP = 0
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream().cuda_stream
+            step = 1 if self.LOG_GAP else nit
+            if self.omega == "numpy" and not self.LOG_GAP:
+                step = max(1, min(nit, _OMEGA_CHUNK_BYTES // max(1, K * D * 8)))
+            done = 0
+            wall_tic = self._get_tic()
+            while done < nit:
+                cnt = min(step, nit - done)
+                if self.LOG_GAP:
+                    self._add_np_log("gap", done, self._gap_row(solver, torch, dev))
+                if self.omega == "numpy":
+                    # the reference's stream: one randn(K, D) per iteration (mmw.py:226)
+                    om = np.empty((cnt, K, D))
+                    for i in range(cnt):
+                        om[i] = np.random.randn(K, D)
+                    om_d = torch.from_numpy(om).to(dev)
+                    solver.iterate(cnt, om_d.data_ptr(), 0, stream)
+                    torch.cuda.current_stream().synchronize()      # om_d must outlive the kernel
+                    del om_d
+                elif self.omega == "device":
+                    solver.iterate(cnt, None, self.seed, stream)
+                else:
+                    raise ValueError("omega must be 'numpy' or 'device'")
+                done += cnt
+                self.N_STEP = done
+            torch.cuda.current_stream().synchronize()
+            wall_us = self._get_tim(wall_tic)
+
+            # per-iteration phase logs, device-timed (mmw.py:142,170,197,200)
+            cnt = min(nit, 8192)
+            pt = solver.phase_times(cnt) if self.mode == _lib.MODE_FUSED else np.zeros((cnt, 3))
+            if not pt.any():
+                pt = np.full((cnt, 3), wall_us / max(nit, 1) / 3.0)
+            for i in range(cnt):
+                it = nit - cnt + i
+                self._add_np_log("mmw_dual", it, np.array([Z, K, pt[i, 0]]))
+                self._add_np_log("mmw_loss", it, np.array([Z, K, pt[i, 1]]))
+                self._add_np_log("mmw_expm", it, np.array([Z, K, pt[i, 2]]))
+                self._add_np_log("mmw_per_it", it, np.array([Z, K, pt[i].sum()]))
+
+            # final factor (mmw.py:202-216): top-r |lambda| eigenpairs of X_avgd / nit
+            tic_xavg = self._get_tic()
+            rank = int(min(K - 1, (Z - 1) * self.rank_radio))
+            solver.xavg_matrix(1.0 / nit, stream)
+            if self.omega == "numpy":
+                v0 = torch.from_numpy(np.random.standard_normal(K)).to(dev)   # svds' ARPACK start vector
+            else:
+                g = torch.Generator(device="cpu").manual_seed(int(self.seed) + 1)
+                v0 = torch.randn(K, dtype=torch.float64, generator=g).to(dev)
+            perm = torch.from_numpy(plan.perm().astype(np.int64)).to(dev)
+            lam, V, info = thick_restart_lanczos(self._matmat(solver, torch, dev), K, rank, "LM", v0[perm])
+            self.last_eig_info = info
+            X_half_int = V * torch.sqrt(lam.abs())[None, :]
+            X_half = torch.empty_like(X_half_int)
+            X_half[perm] = X_half_int                              # internal -> caller numbering
+            X_half = X_half.cpu().numpy()
+            self.last_singular_values = lam.abs().cpu().numpy()
+            self._add_np_log("mmw_xavg", 0, np.array([Z, K, self._get_tim(tic_xavg)]))
+        return True, X_half

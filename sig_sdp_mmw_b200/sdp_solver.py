@@ -1,0 +1,127 @@
+"""Solver base class and randomized rounding with the reference's surface
+(sim_src/alg/sdp_solver.py:9-107).  The arithmetic runs in libsigsdp_mmw.so:
+
+  * sigsdp_round_project  (device): randv gX^T, per-user slot preference order, ||gX_k||
+  * sigsdp_round_greedy   (native host pass): the sequential feasibility assignment
+  * sigsdp_round_conflicts(device): same-slot interference / violation / asso-conflict counts
+
+The random draws (np.random.randn for the directions, np.random.randint for the
+leftovers) stay on numpy's global stream exactly where the reference draws them
+(sdp_solver.py:48,105), so a seeded run reproduces the reference's colouring."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+class sdp_solver:
+    def __init__(self, nit=100, rank_radio=2, alpha=1.):
+        self.nit = nit
+        self.rank_radio = rank_radio
+        self.alpha = alpha  # unused, as in the reference (sdp_solver.py:13)
+
+    # set by subclasses / callers
+    device = 0
+    plan_order = 0
+
+    def run_with_state(self, bs_iteration, Z, state):
+        pass
+
+    # ---- plan cache: the graph plan is Z-independent and reused across the binary search
+    def _plan_for(self, state):
+        S, Q, h = state
+        key = (id(S), id(Q), S.shape, S.nnz, Q.nnz, float(S.data.sum()) if S.nnz else 0.0,
+               float(np.asarray(h).sum()), self.device, self.plan_order)
+        cache = self.__dict__.setdefault("_plan_cache", {})
+        if cache.get("key") != key:
+            cache["plan"] = _lib.Plan(state, device=self.device, order=self.plan_order)
+            cache["key"] = key
+        return cache["plan"]
+
+    def rounding(self, Z, gX, state, nattempt=10):
+        z_vec = None
+        remainder = None
+        for n in range(nattempt):
+            z_vec, Z, remainder = self.rounding_one_attempt(Z, gX, state)
+            if remainder == 0:
+                return z_vec, Z, remainder
+        return z_vec, Z, remainder
+
+    def rounding_one_attempt(self, Z, gX, state):
+        import torch
+        lib = _lib.load()
+        plan = self._plan_for(state)
+        K = state[0].shape[0]
+        gX = np.ascontiguousarray(np.asarray(gX, dtype=np.float64))
+        D = gX.shape[1]
+        randv = np.random.randn(Z, D)                                  # sdp_solver.py:48
+        randv = randv / np.linalg.norm(randv, axis=1, keepdims=True)   # :49
+        dev = torch.device("cuda", plan.device)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream().cuda_stream
+            gX_d = torch.from_numpy(gX).to(dev)
+            rv_d = torch.from_numpy(np.ascontiguousarray(randv)).to(dev)
+            pref_d = torch.empty((K, Z), dtype=torch.int32, device=dev)
+            norm_d = torch.empty(K, dtype=torch.float64, device=dev)
+            _lib.check(lib.sigsdp_round_project(plan.handle, gX_d.data_ptr(), D, rv_d.data_ptr(), Z,
+                                                pref_d.data_ptr(), norm_d.data_ptr(), stream))
+            # visit order argsort(-||gX_k||) (:52); stable so equal norms keep index order
+            rank = torch.argsort(-norm_d, stable=True).to(torch.int32).cpu().numpy()
+            pref = pref_d.cpu().numpy()
+        z_int = np.empty(K, np.int32)
+        rem = C.c_int64()
+        S, Q, h = plan._S, plan._Q, plan._h
+        _lib.check(lib.sigsdp_round_greedy(K, Z, _lib._p(S[0], C.c_int32), _lib._p(S[1], C.c_int32), _lib._p(S[2], C.c_double),
+                                           _lib._p(Q[0], C.c_int32), _lib._p(Q[1], C.c_int32), _lib._p(Q[2], C.c_double),
+                                           _lib._p(h, C.c_double), _lib._p(rank, C.c_int32),
+                                           _lib._p(np.ascontiguousarray(pref), C.c_int32), _lib._p(z_int, C.c_int32),
+                                           C.byref(rem)))
+        z_vec = z_int.astype(np.float64)
+        not_assigned = z_int < 0
+        z_vec[not_assigned] = 0.0
+        remainder = int(rem.value)
+        if remainder:
+            z_vec[not_assigned] = np.random.randint(Z, size=remainder)  # :104-105
+        return z_vec, Z, remainder
+
+    def conflict_counts(self, z_vec, state, return_interference=False):
+        """rounding.py:56-66 on device: (#users whose same-slot interference exceeds h_max,
+        #association pairs sharing a slot[, I])."""
+        import torch
+        plan = self._plan_for(state)
+        dev = torch.device("cuda", plan.device)
+        with torch.cuda.device(dev):
+            z_d = torch.from_numpy(np.ascontiguousarray(np.asarray(z_vec).astype(np.int32))).to(dev)
+            I_d = torch.empty(plan.n, dtype=torch.float64, device=dev) if return_interference else None
+            counts = (C.c_int64 * 2)()
+            _lib.check(_lib.load().sigsdp_round_conflicts(plan.handle, z_d.data_ptr(),
+                                                          I_d.data_ptr() if I_d is not None else None, counts,
+                                                          torch.cuda.current_stream().cuda_stream))
+        if return_interference:
+            return int(counts[0]), int(counts[1]), I_d.cpu().numpy()
+        return int(counts[0]), int(counts[1])
+
+    def argmax_colours(self, Z, gX, randv_raw=None):
+        """rounding.py:46-54 on the solver's factor: colour_k = argmax_z <randv_z, g_k>, the
+        first preference of rounding_one_attempt."""
+        import torch
+        lib = _lib.load()
+        gX = np.ascontiguousarray(np.asarray(gX, dtype=np.float64))
+        K, D = gX.shape
+        if randv_raw is None:
+            randv_raw = np.random.randn(Z, D)
+        randv = randv_raw / np.linalg.norm(randv_raw, axis=1, keepdims=True)
+        plan = self.__dict__.get("_plan_cache", {}).get("plan")
+        if plan is None or plan.n != K:
+            raise RuntimeError("argmax_colours needs a plan: call run_with_state/rounding on the state first")
+        dev = torch.device("cuda", plan.device)
+        with torch.cuda.device(dev):
+            gX_d = torch.from_numpy(gX).to(dev)
+            rv_d = torch.from_numpy(np.ascontiguousarray(randv)).to(dev)
+            pref_d = torch.empty((K, Z), dtype=torch.int32, device=dev)
+            norm_d = torch.empty(K, dtype=torch.float64, device=dev)
+            _lib.check(lib.sigsdp_round_project(plan.handle, gX_d.data_ptr(), D, rv_d.data_ptr(), Z,
+                                                pref_d.data_ptr(), norm_d.data_ptr(),
+                                                torch.cuda.current_stream().cuda_stream))
+            return pref_d[:, 0].cpu().numpy().astype(np.int64)

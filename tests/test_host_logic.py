@@ -1,0 +1,165 @@
+"""CPU tests (no GPU): the C-ABI library loads and exports every symbol the header
+declares; the native host logic (graph plan, sequential rounding pass) matches the
+oracle; the sparse topology generator reproduces the reference's fixtures."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from oracle import mmw_oracle as orc
+from sig_sdp_mmw_b200 import _lib
+from sig_sdp_mmw_b200.topology import sparse_env
+from tests.golden_util import CASES, ROOT, load_case
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "sigsdp_mmw.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = sorted(set(re.findall(r"\b(sigsdp_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 25
+    lib = C.CDLL(_lib.LIB_PATH)
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    assert _lib.load().sigsdp_version() >= 100
+
+
+def test_binding_covers_header():
+    hdr = open(os.path.join(ROOT, "include", "sigsdp_mmw.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b(sigsdp_[a-z0-9_]+)\s*\(", hdr))
+    src = open(os.path.join(ROOT, "sig_sdp_mmw_b200", "_lib.py")).read()
+    assert not [n for n in names if n not in src]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_plan_matches_oracle(name):
+    g = load_case(name)
+    p = orc.build_problem(g["Z"], g["state"])
+    pl = _lib.Plan(g["state"], device=-1)
+    gi, gj, tij, tji, ai, aj = pl.edges()
+    assert (pl.n, pl.E_g, pl.E_a) == (p.K, p.E_g, p.E_a)
+    assert pl.nnz == p.K + 2 * (p.E_g + p.E_a)
+    np.testing.assert_array_equal(gi, p.gi)
+    np.testing.assert_array_equal(gj, p.gj)
+    np.testing.assert_array_equal(ai, p.ai)
+    np.testing.assert_array_equal(aj, p.aj)
+    np.testing.assert_array_equal(tij, p.tij)
+    np.testing.assert_array_equal(tji, p.tji)
+    S_sum, tn = pl.vectors()
+    np.testing.assert_allclose(S_sum, p.S_sum, rtol=1e-14)
+    np.testing.assert_allclose(tn, np.sqrt(np.asarray(p.T.multiply(p.T).sum(axis=1)).ravel()), rtol=1e-14)
+    assert pl.nnzT == p.T.nnz
+    # pattern is the symmetric union, diagonal included, columns ascending
+    rp, col = pl.pattern()
+    U = sp.csr_matrix((np.ones(pl.nnz), col, rp), shape=(pl.n, pl.n))
+    assert (U != U.T).nnz == 0
+    assert (U.diagonal() == 1).all()
+    assert all(np.all(np.diff(col[rp[k]:rp[k + 1]]) > 0) for k in range(pl.n))
+
+
+@pytest.mark.parametrize("order", [1, 16])
+def test_plan_locality_order_is_a_relabelling(order):
+    g = load_case("n300_z10")
+    p0 = _lib.Plan(g["state"], device=-1, order=0)
+    p1 = _lib.Plan(g["state"], device=-1, order=order)
+    perm = p1.perm()
+    assert sorted(perm.tolist()) == list(range(p0.n))
+    for a, b in zip(p0.edges(), p1.edges()):      # edge lists stay in the caller's numbering
+        np.testing.assert_array_equal(a, b)
+    for a, b in zip(p0.vectors(), p1.vectors()):
+        np.testing.assert_array_equal(a, b)
+    rp0, c0 = p0.pattern()
+    rp1, c1 = p1.pattern()
+    U0 = sp.csr_matrix((np.ones(p0.nnz), c0, rp0), shape=(p0.n, p0.n))
+    U1 = sp.csr_matrix((np.ones(p1.nnz), c1, rp1), shape=(p0.n, p0.n))
+    P = sp.csr_matrix((np.ones(p0.n), (np.arange(p0.n), perm)), shape=(p0.n, p0.n))   # new <- old
+    assert abs(P @ U0 @ P.T - U1).nnz == 0
+
+
+def test_plan_rejects_bad_input():
+    g = load_case("n75_z8")
+    S, Q, h = g["state"]
+    Qbad = Q.tolil()
+    i, j = sp.triu(Q, 1).nonzero()
+    Qbad[i[0], j[0]] = 0
+    with pytest.raises(_lib.SigSdpError, match="symmetric"):
+        _lib.Plan((S, Qbad.tocsr(), h), device=-1)
+    Qd = Q.tolil()
+    Qd[3, 3] = 1
+    with pytest.raises(_lib.SigSdpError, match="diagonal"):
+        _lib.Plan((S, Qd.tocsr(), h), device=-1)
+    with pytest.raises(ValueError):
+        _lib.Plan((S, Q, h[:-1]), device=-1)
+    pl = _lib.Plan(g["state"], device=-1)
+    with pytest.raises(_lib.SigSdpError, match="host-only"):
+        _lib.Solver(pl, 4, 8, 0.1)
+
+
+def _greedy(g, randv_raw):
+    S, Q, h = g["state"]
+    Z, gX = g["Z"], g["X_half"]
+    K = S.shape[0]
+    randv = randv_raw / np.linalg.norm(randv_raw, axis=1, keepdims=True)
+    rank = np.argsort(-np.linalg.norm(gX, axis=1)).astype(np.int32)
+    pref = np.ascontiguousarray(np.argsort(-(randv @ gX.T), axis=0).T.astype(np.int32))
+    Sa, Qa = _lib.csr_arrays(S), _lib.csr_arrays(Q)
+    z = np.empty(K, np.int32)
+    rem = C.c_int64()
+    _lib.check(_lib.load().sigsdp_round_greedy(
+        K, Z, _lib._p(Sa[0], C.c_int32), _lib._p(Sa[1], C.c_int32), _lib._p(Sa[2], C.c_double),
+        _lib._p(Qa[0], C.c_int32), _lib._p(Qa[1], C.c_int32), _lib._p(Qa[2], C.c_double),
+        _lib._p(np.ascontiguousarray(h), C.c_double), _lib._p(rank, C.c_int32), _lib._p(pref, C.c_int32),
+        _lib._p(z, C.c_int32), C.byref(rem)))
+    return z, int(rem.value)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_native_greedy_pass_matches_reference_rounding(name):
+    """sigsdp_round_greedy fed the same preference order reproduces the reference's
+    rounding_one_attempt result stored in the fixture (np.random.seed(2000))."""
+    g = load_case(name)
+    rs = np.random.RandomState(2000)
+    randv_raw = rs.randn(g["Z"], g["X_half"].shape[1])
+    z, rem = _greedy(g, randv_raw)
+    assert rem == int(g["round1_rem"])
+    ok = z >= 0
+    np.testing.assert_array_equal(z[ok].astype(float), g["round1_z"][ok])
+    if rem:
+        fill = rs.randint(g["Z"], size=rem)
+        np.testing.assert_array_equal(fill.astype(float), g["round1_z"][~ok])
+
+
+def test_native_greedy_pass_infeasible_Z():
+    g = load_case("n500_z4_cfg1")     # Z=4 is below the association bound: leftovers expected
+    z, rem = _greedy(g, np.random.RandomState(1).randn(g["Z"], g["X_half"].shape[1]))
+    assert rem > 0 and (z < 0).sum() == rem
+
+
+@pytest.mark.parametrize("name,kw", [
+    ("n75_z8", dict(cell_size=5, sta_density_per_1m2=75e-4, seed=0)),
+    ("n75_z6_rr3", dict(cell_size=5, sta_density_per_1m2=75e-4, seed=3)),
+    ("n300_z10", dict(cell_size=10, sta_density_per_1m2=75e-4, seed=1)),
+    ("n500_z13", dict(cell_size=10, sta_density_per_1m2=125e-4, seed=0)),
+])
+def test_sparse_topology_reproduces_reference_state(name, kw):
+    g = load_case(name)
+    S, Q, h = g["state"]
+    S2, Q2, h2 = sparse_env(**kw).generate_S_Q_hmax()
+    assert S2.shape == S.shape and S2.nnz == S.nnz
+    np.testing.assert_array_equal(S2.indptr, S.indptr)
+    np.testing.assert_array_equal(S2.indices, S.indices)
+    np.testing.assert_allclose(S2.data, S.data, rtol=1e-12)
+    assert abs(Q2 - Q).nnz == 0
+    np.testing.assert_allclose(h2, h, rtol=1e-12)
+
+
+def test_sparse_topology_large_is_bounded_degree():
+    e = sparse_env(cell_size=60, sta_density_per_1m2=6.25e-3, seed=0)
+    S, Q, h = e.generate_S_Q_hmax()
+    assert S.shape[0] == 9000
+    deg = np.diff((S + S.T).tocsr().indptr)
+    assert deg.max() < 200 and 10 < deg.mean() < 60
+    assert (h > 0).all()
