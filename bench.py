@@ -175,7 +175,8 @@ def run_ours(args):
     t0 = time.perf_counter()
     plan = _lib.Plan(state, device=local, order=args.order)
     plan_s = time.perf_counter() - t0
-    sol = _lib.Solver(plan, Z, D, ETA, dt_code, _lib.MODE_FUSED if args.mode == "fused" else _lib.MODE_STEPWISE)
+    sol = _lib.Solver(plan, Z, D, ETA, dt_code, _lib.MODE_FUSED if args.mode == "fused" else _lib.MODE_STEPWISE,
+                      args.tiling)
     stream = torch.cuda.current_stream().cuda_stream
 
     # ---- device-resident timing: W warm-up iterations, reset, K timed iterations
@@ -196,6 +197,7 @@ def run_ours(args):
     phase = sol.phase_times(min(args.steps, 8192)).sum(axis=0)
     if args.skip_e2e:
         if rank == 0:
+            sampler.stop()
             print(json.dumps({"profiling_run": True, "mode": args.mode, "workload": args.workload, "steps": args.steps,
                               "ms": ms, "taylor_terms": terms, "phase_us": phase.tolist()}))
         return
@@ -241,7 +243,7 @@ def run_ours(args):
                        "timed": "K iterations from the initial state in one fused-kernel launch",
                        "l2": "working set %.0f MB > 126 MB L2 (no flush)" % ws if ws > 126 else
                              "working set %.0f MB fits L2: traffic is L2-resident after the first pass" % ws,
-                       "grid": sol.grid, "threads": sol.threads, "lanes_per_row": sol.lanes,
+                       "grid": sol.grid, "threads": sol.threads, "lanes_per_row": sol.lanes, "tile_rows": sol.tile_rows, "smem_bytes": sol.smem,
                        "phase_us": {"dual": phase[0], "loss": phase[1], "sketch_gram": phase[2]},
                        "plan_build_s": plan_s},
             "gpu_launches": 1,
@@ -271,7 +273,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg4_100k", choices=sorted(WORKLOADS))
-    ap.add_argument("--order", type=int, default=0, help="node renumbering inside the kernels (0 = caller's order)")
+    ap.add_argument("--order", type=int, default=1, help="node renumbering inside the kernels (0 = caller's order)")
+    ap.add_argument("--tiling", type=int, default=-1, help="rows per staged tile (-1 auto, 0 = direct-gather kernels)")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--ref-budget", type=float, default=60.0)
     ap.add_argument("--no-cpu", action="store_true")

@@ -85,12 +85,19 @@ int sigsdp_plan_perm(const sigsdp_plan* plan, int32_t* perm_host);
  * this Z (mmw.py:39).  D = Z * rank_radio (mmw.py:180).
  */
 int sigsdp_solver_create(const sigsdp_plan* plan, int Z, int D, double eta, int dtype, sigsdp_solver** out);
+/* Same, choosing the kernels' row tiling: -1 automatic (the largest tile of consecutive
+ * rows whose distinct neighbour rows of the sketch block fit in shared memory; the Taylor
+ * SpMM and the Gram then stage that slice with TMA bulk copies), 0 = direct-gather
+ * kernels, > 0 = that many rows per tile. */
+int sigsdp_solver_create_tiled(const sigsdp_plan* plan, int Z, int D, double eta, int dtype, int tiling,
+                               sigsdp_solver** out);
 void sigsdp_solver_destroy(sigsdp_solver* s);
 int sigsdp_solver_reset(sigsdp_solver* s, void* stream);
 int sigsdp_solver_set_mode(sigsdp_solver* s, int mode);
-/* info[0..9] = n, Z, D, Dp (padded row length), C, iterations done, dtype, grid blocks,
- * threads per block, lanes per row */
-int sigsdp_solver_info(const sigsdp_solver* s, int64_t info[10]);
+/* info[0..11] = n, Z, D, Dp (padded row length), C, iterations done, dtype, grid blocks,
+ * threads per block, lanes per row, rows per tile (0 = gather kernels), dynamic shared
+ * memory bytes per block */
+int sigsdp_solver_info(const sigsdp_solver* s, int64_t info[12]);
 
 /* n_iters MMW iterations, each = mmw.py:77-78 (averaging) + 124-142 (dual) +
  * 144-170 (loss) + 172-197 (sketch: expm_half_randsk 224-229 with scipy's

@@ -1,15 +1,21 @@
 #!/bin/bash
-# ncu pass (one GPU): launch list of the stepwise pipeline, full captures of the hot kernels.
+# ncu pass (one GPU): full captures of the hot kernels in stepwise mode + the fused kernel.
 set -u
 mkdir -p gpurun_out
-WL=${WL:-cfg4_100k}; ORD=${ORD:-32}; TAG=${TAG:-r1}
-STEP="python bench.py --workload $WL --order $ORD --mode stepwise --steps 12 --warmup 3 --skip-e2e"
-FUSE="python bench.py --workload $WL --order $ORD --mode fused --steps 20 --warmup 3 --skip-e2e"
-$STEP > gpurun_out/plain_step_$TAG.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_step_$TAG.csv $STEP > gpurun_out/ncu_step_$TAG.log 2>&1
-$STEP > /dev/null 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:'k_term|k_gram|k_loss|k_dual|k_exp' -s 60 -c 12 -o gpurun_out/prof_step_$TAG -f $STEP > gpurun_out/ncu_full_step_$TAG.log 2>&1
-$FUSE > gpurun_out/plain_fused_$TAG.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:k_fused -s 1 -c 1 -o gpurun_out/prof_fused_$TAG -f $FUSE > gpurun_out/ncu_full_fused_$TAG.log 2>&1
-cat gpurun_out/plain_step_$TAG.log gpurun_out/plain_fused_$TAG.log | tail -4
-ls -la gpurun_out | tail -12
+WL=${WL:-cfg4_100k}; ORD=${ORD:-1}; TAG=${TAG:-r1}; TIL=${TIL:--1}
+LOG=gpurun_out/profile_$TAG.log
+STEP="python bench.py --workload $WL --order $ORD --tiling $TIL --mode stepwise --steps 4 --warmup 3 --skip-e2e"
+FUSE="python bench.py --workload $WL --order $ORD --tiling $TIL --mode fused --steps 12 --warmup 3 --skip-e2e"
+echo "$(date +%T) plain step" >> $LOG
+timeout 300 $STEP >> $LOG 2>&1 || { echo "plain stepwise run failed" >> $LOG; exit 1; }
+echo "$(date +%T) ncu full step" >> $LOG
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_term|k_gram|k_loss|k_dual' -s 22 -c 8 -o gpurun_out/prof_step_$TAG -f $STEP >> $LOG 2>&1
+echo "$(date +%T) rc=$? plain fused" >> $LOG
+timeout 300 $FUSE >> $LOG 2>&1 || { echo "plain fused run failed" >> $LOG; exit 1; }
+echo "$(date +%T) ncu launches fused" >> $LOG
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_fused_$TAG.csv $FUSE >> $LOG 2>&1
+echo "$(date +%T) rc=$? ncu full fused" >> $LOG
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_fused -s 1 -c 1 -o gpurun_out/prof_fused_$TAG -f $FUSE >> $LOG 2>&1
+echo "$(date +%T) rc=$? done" >> $LOG
+tail -30 $LOG
+ls -la gpurun_out | tail

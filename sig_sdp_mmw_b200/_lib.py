@@ -43,6 +43,7 @@ def load():
         "sigsdp_plan_vectors": [vp, f64p, f64p],
         "sigsdp_plan_perm": [vp, i32p],
         "sigsdp_solver_create": [vp, C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(vp)],
+        "sigsdp_solver_create_tiled": [vp, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.POINTER(vp)],
         "sigsdp_solver_reset": [vp, vp],
         "sigsdp_solver_set_mode": [vp, C.c_int],
         "sigsdp_solver_info": [vp, i64p],
@@ -148,16 +149,18 @@ class Plan:
 class Solver:
     """MMW state for one (plan, Z, D, eta, dtype), see sigsdp_solver_create."""
 
-    def __init__(self, plan, Z, D, eta, dtype=F64, mode=MODE_FUSED):
+    def __init__(self, plan, Z, D, eta, dtype=F64, mode=MODE_FUSED, tiling=-1):
         lib = load()
         self.plan = plan
         self.handle = C.c_void_p()
-        check(lib.sigsdp_solver_create(plan.handle, int(Z), int(D), float(eta), int(dtype), C.byref(self.handle)))
+        check(lib.sigsdp_solver_create_tiled(plan.handle, int(Z), int(D), float(eta), int(dtype), int(tiling),
+                                             C.byref(self.handle)))
         if mode != MODE_FUSED:
             check(lib.sigsdp_solver_set_mode(self.handle, mode))
         self.Z, self.D = int(Z), int(D)
         i = self.info()
         self.Dp, self.C, self.grid, self.threads, self.lanes = i["Dp"], i["C"], i["grid"], i["threads"], i["lanes"]
+        self.tile_rows, self.smem = i["tile_rows"], i["smem"]
 
     def __del__(self):
         try:
@@ -168,9 +171,9 @@ class Solver:
             pass
 
     def info(self):
-        a = (C.c_int64 * 10)()
+        a = (C.c_int64 * 12)()
         check(load().sigsdp_solver_info(self.handle, a))
-        keys = ["n", "Z", "D", "Dp", "C", "iters", "dtype", "grid", "threads", "lanes"]
+        keys = ["n", "Z", "D", "Dp", "C", "iters", "dtype", "grid", "threads", "lanes", "tile_rows", "smem"]
         return dict(zip(keys, [int(x) for x in a]))
 
     def reset(self, stream=None):

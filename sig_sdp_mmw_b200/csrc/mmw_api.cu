@@ -3,6 +3,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <tuple>
 #include <string>
 #include <vector>
 
@@ -63,12 +65,23 @@ struct sigsdp_plan {
     int* d_ai = nullptr;
     int* d_aj = nullptr;
     double* d_hmax_caller = nullptr;
+    // row tiles per (max_rows, ucap, nnzcap), built on first use (see TileDev)
+    struct TileCache {
+        HostTiles h;
+        TileDev d;
+    };
+    mutable std::map<std::tuple<int, int, int>, TileCache> tiles;
+    mutable DevArena tile_mem;
 };
 
 struct sigsdp_solver {
     const sigsdp_plan* plan = nullptr;
     int Z = 0, D = 0, Dp = 0, C = 0, dtype = 0, G = 0, mode = SIGSDP_MODE_FUSED;
     int grid = 0;
+    size_t smem = 0;   // dynamic shared memory of the staged kernels
+    int RT = 0;        // max rows per tile (0 = direct-gather kernels)
+    int ntiles = 0;
+    int tiling = -1;   // requested: -1 auto, 0 off, >0 rows per tile
     double eta = 0.0;
     DevArena mem;
     Prob<double> p64;
@@ -89,8 +102,9 @@ struct sigsdp_solver {
 // kernels
 template <typename T, int G>
 __global__ void __launch_bounds__(NT, 2) k_fused(Prob<T> P, int n_iters) {
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
     GridTeam team;
-    run_iterations<T, G>(P, team, n_iters);
+    run_iterations<T, G>(P, team, n_iters, dyn_smem);
 }
 template <typename T, int G>
 __global__ void __launch_bounds__(NT, 2) k_dual(Prob<T> P) {
@@ -109,8 +123,15 @@ __global__ void __launch_bounds__(NT, 2) k_loss(Prob<T> P, int it_local) {
 }
 template <typename T, int G>
 __global__ void __launch_bounds__(NT, 2) k_term(Prob<T> P, const T* bin, T* bout, double coeff, double mu, int slot) {
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
     __shared__ double sh[NWARP + 2];
-    phase_term<T, G>(P, StepTeam(), bin, bout, coeff, mu, slot, sh);
+    if (P.tl.enabled) {
+        Stage<T> st;
+        stage_setup(P, dyn_smem, st);
+        phase_term_staged<T, G>(P, StepTeam(), bin, bout, coeff, slot, sh, st);
+    } else {
+        phase_term<T, G>(P, StepTeam(), bin, bout, coeff, mu, slot, sh);
+    }
 }
 template <typename T, int G>
 __global__ void __launch_bounds__(NT, 2) k_copy(Prob<T> P, T* dst) {
@@ -118,8 +139,15 @@ __global__ void __launch_bounds__(NT, 2) k_copy(Prob<T> P, T* dst) {
 }
 template <typename T, int G>
 __global__ void __launch_bounds__(NT, 2) k_gram(Prob<T> P) {
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
     __shared__ double sh[NWARP + 2];
-    phase_gram<T, G>(P, StepTeam(), sh);
+    if (P.tl.enabled) {
+        Stage<T> st;
+        stage_setup(P, dyn_smem, st);
+        phase_gram_staged<T, G>(P, StepTeam(), sh, st);
+    } else {
+        phase_gram<T, G>(P, StepTeam(), sh);
+    }
 }
 // stepwise controller: single-thread kernels that publish decisions for the host
 __global__ void k_begin(Ctrl* ctrl) {
@@ -151,6 +179,9 @@ __global__ void k_record(Prob<T> P, int it_local, int m_star, long long s, doubl
 }
 __global__ void k_advance(Ctrl* ctrl, int n_iters) { ctrl->iter += n_iters; }
 
+__global__ void k_set_diag(double* v, const int* dpos, int n, double x) {
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) v[dpos[k]] = x;
+}
 template <typename T>
 __global__ void k_fill(T* p, size_t n, T v) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
@@ -227,15 +258,12 @@ __global__ void k_round_conflicts(int n, const int* STp, const int* STi, const d
 struct SolverView {  // dtype-independent part of Prob
     PlanDev g;
     int Z, C;
-    const double *nH, *hcoef, *Y, *Ybar, *Xd, *Xe, *Xbar_d, *Xbar_e;
+    const double *nH, *hcoef, *Y, *Ybar, *Xv, *Xbarv;
 };
 __global__ void k_mat_xavg(SolverView v, double scale, double* Mval) {
     const PlanDev& g = v.g;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < g.n; k += gridDim.x * blockDim.x)
-        for (int p = g.rowptr[k]; p < g.rowptr[k + 1]; ++p) {
-            const int e = g.eid[p];
-            Mval[p] = scale * (e < 0 ? v.Xbar_d[k] : v.Xbar_e[e]);
-        }
+        for (int p = g.rowptr[k]; p < g.rowptr[k + 1]; ++p) Mval[p] = scale * v.Xbarv[p];
 }
 __global__ void k_symv(PlanDev g, const double* Mval, const double* x, double* y, int nvec) {
     constexpr int G = 8;
@@ -259,8 +287,7 @@ __global__ void k_gap_rowsum(SolverView v, double N, double* rtmp) {
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < g.n; k += gridDim.x * blockDim.x) {
         double acc = 0.0;
         for (int p = g.rowptr[k]; p < g.rowptr[k + 1]; ++p) {
-            const int e = g.eid[p];
-            if (e >= 0) acc += (v.Xbar_e[e] + v.Xe[e]) / N;
+            if (p != g.dpos[k]) acc += (v.Xbarv[p] + v.Xv[p]) / N;
         }
         rtmp[k] = acc;
     }
@@ -277,11 +304,11 @@ __global__ void k_gap_emax(SolverView v, double N, const double* rtmp, unsigned 
             if (tf != 0.0) acc += tf * rtmp[g.col[p]];
         }
         const double eH = (acc * zr - (g.h_max[k] - g.S_sum[k] / Z)) / v.nH[k];
-        const double eD = ((v.Xbar_d[k] + v.Xd[k]) / N - 1.0) * invD;
+        const double eD = ((v.Xbarv[g.dpos[k]] + v.Xv[g.dpos[k]]) / N - 1.0) * invD;
         m = fmax(m, fmax(eH, eD));
     }
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < g.E_a; e += gridDim.x * blockDim.x)
-        m = fmax(m, ((v.Xbar_e[g.E_g + e] + v.Xe[g.E_g + e]) / N + 1.0 / (Z - 1)) / cF);
+        m = fmax(m, ((v.Xbarv[g.apos[e]] + v.Xv[g.apos[e]]) / N + 1.0 / (Z - 1)) / cF);
     m = warp_max(m);
     if ((threadIdx.x & 31) == 0 && m > -INFINITY) atomicMax(key, dkey_any(m));
 }
@@ -349,8 +376,13 @@ template <> Prob<float>& prob_of<float>(sigsdp_solver* s) { return s->p32; }
     }
 
 template <typename T, int G>
-static int occupancy_fused(int* occ) {
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_fused<T, G>, NT, 0));
+static int occupancy_fused(int* occ, size_t smem) {
+    if (smem > 48 * 1024) {
+        CK(cudaFuncSetAttribute(k_fused<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(k_term<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(k_gram<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_fused<T, G>, NT, smem));
     return SIGSDP_OK;
 }
 
@@ -358,7 +390,7 @@ template <typename T, int G>
 static int launch_fused(sigsdp_solver* s, int n_iters, cudaStream_t st) {
     Prob<T> P = prob_of<T>(s);
     void* args[] = {(void*)&P, (void*)&n_iters};
-    CK(cudaLaunchCooperativeKernel((void*)k_fused<T, G>, dim3(s->grid), dim3(NT), args, 0, st));
+    CK(cudaLaunchCooperativeKernel((void*)k_fused<T, G>, dim3(s->grid), dim3(NT), args, s->smem, st));
     return SIGSDP_OK;
 }
 
@@ -388,7 +420,7 @@ static int run_stepwise(sigsdp_solver* s, int n_iters, cudaStream_t st) {
             }
             for (int j = 0; j < m_star; ++j) {
                 const int slot = tcount % 3;
-                k_term<T, G><<<grid, blk, 0, st>>>(P, bin, bout, 1.0 / ((double)ss * (double)(j + 1)), mu, slot);
+                k_term<T, G><<<grid, blk, s->smem, st>>>(P, bin, bout, 1.0 / ((double)ss * (double)(j + 1)), mu, slot);
                 k_decide<<<1, 1, 0, st>>>(P.ctrl, slot, c1, P.tol);
                 CK(cudaMemcpyAsync(&hc, P.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
                 CK(cudaStreamSynchronize(st));
@@ -402,7 +434,7 @@ static int run_stepwise(sigsdp_solver* s, int n_iters, cudaStream_t st) {
             }
         }
         k_record<T><<<1, 1, 0, st>>>(P, it, m_star, ss, a1, mu, tcount);
-        k_gram<T, G><<<grid, blk, 0, st>>>(P);
+        k_gram<T, G><<<grid, blk, s->smem, st>>>(P);
         CK(cudaGetLastError());
     }
     k_advance<<<1, 1, 0, st>>>(P.ctrl, n_iters);
@@ -457,7 +489,7 @@ int sigsdp_plan_create(int64_t n, const int32_t* Sp, const int32_t* Si, const do
     d.nnz = (int)h.nnz;
     d.E_g = (int)h.E_g;
     d.E_a = (int)h.E_a;
-    int *rowptr, *col, *eid, *perm = nullptr;
+    int *rowptr, *col, *eid, *perm = nullptr, *dpos, *apos;
     double *tfwd, *tbwd, *S_sum, *tnorm, *hm;
     if ((e = pl->mem.upload(&rowptr, h.rowptr)) != cudaSuccess) return bail(e, "upload rowptr");
     if ((e = pl->mem.upload(&col, h.col)) != cudaSuccess) return bail(e, "upload col");
@@ -468,6 +500,10 @@ int sigsdp_plan_create(int64_t n, const int32_t* Sp, const int32_t* Si, const do
     if ((e = pl->mem.upload(&tnorm, h.tnorm)) != cudaSuccess) return bail(e, "upload tnorm");
     if ((e = pl->mem.upload(&hm, h.h_max)) != cudaSuccess) return bail(e, "upload h_max");
     if (h.order != 0 && (e = pl->mem.upload(&perm, h.perm)) != cudaSuccess) return bail(e, "upload perm");
+    if ((e = pl->mem.upload(&dpos, h.dpos)) != cudaSuccess) return bail(e, "upload dpos");
+    if ((e = pl->mem.upload(&apos, h.apos)) != cudaSuccess) return bail(e, "upload apos");
+    d.dpos = dpos;
+    d.apos = apos;
     d.rowptr = rowptr;
     d.col = col;
     d.eid = eid;
@@ -512,6 +548,7 @@ void sigsdp_plan_destroy(sigsdp_plan* plan) {
     if (plan->device >= 0) {
         cudaSetDevice(plan->device);
         plan->mem.release();
+        plan->tile_mem.release();
     }
     delete plan;
 }
@@ -587,15 +624,14 @@ static int solver_alloc(sigsdp_solver* s) {
     P.nH = d_nH;
     P.hcoef = d_hcoef;
     CK(s->mem.alloc(&P.Lval, h.nnz));
+    CK(s->mem.alloc(&P.Aval, h.nnz + 8));   // + padding: bulk copies read 16-byte supersets
     CK(s->mem.alloc(&P.e_acc, s->C));
     CK(s->mem.alloc(&P.u, s->C));
     CK(s->mem.alloc(&P.Y, s->C));
     CK(s->mem.alloc(&P.Ybar, s->C));
     CK(s->mem.alloc(&P.q, n));
-    CK(s->mem.alloc(&P.Xd, n));
-    CK(s->mem.alloc(&P.Xe, E));
-    CK(s->mem.alloc(&P.Xbar_d, n));
-    CK(s->mem.alloc(&P.Xbar_e, E));
+    CK(s->mem.alloc(&P.Xv, h.nnz));
+    CK(s->mem.alloc(&P.Xbarv, h.nnz));
     CK(s->mem.alloc(&P.r, n));
     CK(s->mem.alloc(&P.dsq, n));
     CK(s->mem.alloc(&P.B0, (size_t)n * s->Dp));
@@ -616,13 +652,62 @@ static int solver_alloc(sigsdp_solver* s) {
     CK(s->mem.alloc(&P.hist_t, (size_t)HIST * 3));
     P.omega = nullptr;
     P.seed = 0;
-    // launch geometry: persistent grid, one tile of NT/G rows per block iteration
+    // row tiles for the staged (shared-memory) kernels: tiles of up to `max_rows` consecutive
+    // rows, capped so that a tile's distinct sketch rows, its L_accu slice and its local
+    // column indices fit the per-block shared-memory budget (two blocks per SM)
+    const int R = NT / s->G;
+    P.tl = TileDev{0, 0, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr};
+    s->smem = 0;
+    s->RT = 0;
+    if (s->tiling != 0) {
+        const size_t rowbytes = (size_t)s->Dp * sizeof(T);
+        const size_t budget = 106 * 1024;
+        const int max_rows = s->tiling > 0 ? s->tiling : std::max(R, 64);
+        const int nnzcap = (std::max(2048, std::min(8192, 4 * h.max_row)) + 7) & ~7;
+        const size_t fixed = 16 + (size_t)(nnzcap + 4) * sizeof(T) + (size_t)(nnzcap + 8) * 2 + 48;
+        const int ucap = budget > fixed ? (int)std::min<size_t>((budget - fixed) / rowbytes, 65535) : 0;
+        if (ucap >= h.max_row && h.max_row <= nnzcap) {
+            auto key = std::make_tuple(max_rows, ucap, nnzcap);
+            auto it = pl->tiles.find(key);
+            if (it == pl->tiles.end()) {
+                sigsdp_plan::TileCache tc;
+                build_tiles(h, max_rows, ucap, nnzcap, tc.h);
+                tc.d = TileDev{0, tc.h.ntiles, ucap, nnzcap, nullptr, nullptr, nullptr, nullptr, nullptr};
+                if (tc.h.ok) {
+                    int *trow, *ucnt, *rptr, *runs;
+                    unsigned short* lcol;
+                    std::vector<uint16_t> lpad(tc.h.lcol);
+                    lpad.resize(lpad.size() + 16, 0);   // bulk copies read 16-byte supersets
+                    CK(pl->tile_mem.upload(&trow, tc.h.trow));
+                    CK(pl->tile_mem.upload(&ucnt, tc.h.ucnt));
+                    CK(pl->tile_mem.upload(&rptr, tc.h.rptr));
+                    CK(pl->tile_mem.upload(&runs, tc.h.runs));
+                    CK(pl->tile_mem.upload(&lcol, lpad));
+                    tc.d.enabled = 1;
+                    tc.d.trow = trow;
+                    tc.d.ucnt = ucnt;
+                    tc.d.rptr = rptr;
+                    tc.d.runs = reinterpret_cast<const int4*>(runs);
+                    tc.d.lcol = lcol;
+                }
+                it = pl->tiles.emplace(key, std::move(tc)).first;
+            }
+            if (it->second.d.enabled) {
+                P.tl = it->second.d;
+                const size_t rows_bytes = ((size_t)ucap * rowbytes + 15) & ~(size_t)15;
+                const size_t vals_bytes = ((size_t)(nnzcap + 4) * sizeof(T) + 15) & ~(size_t)15;
+                s->smem = 16 + rows_bytes + vals_bytes + (size_t)(nnzcap + 8) * 2;
+                s->RT = max_rows;
+                s->ntiles = it->second.h.ntiles;
+            }
+        }
+    }
+    // launch geometry: persistent grid, one tile per block iteration
     int occ = 0, rc = SIGSDP_OK;
-    FOR_G(s->G, rc = (occupancy_fused<T, G>(&occ)));
+    FOR_G(s->G, rc = (occupancy_fused<T, G>(&occ, s->smem)));
     if (rc != SIGSDP_OK) return rc;
     if (occ < 1) return fail(SIGSDP_ECUDA, "fused kernel does not fit on an SM");
-    const int R = NT / s->G;
-    int64_t tiles = (n + R - 1) / R;
+    int64_t tiles = s->RT > 0 ? s->ntiles : (n + R - 1) / R;
     int64_t blocks = (int64_t)pl->num_sms * occ;
     if (blocks > tiles) blocks = tiles;
     if (blocks > maxblk) blocks = maxblk;
@@ -639,13 +724,13 @@ static int solver_reset_impl(sigsdp_solver* s, cudaStream_t st) {
     const HostPlan& h = s->plan->h;
     const int64_t n = h.n, E = h.E_g + h.E_a;
     CK(cudaMemsetAsync(P.Lval, 0, h.nnz * sizeof(double), st));
+    CK(cudaMemsetAsync(P.Aval, 0, (h.nnz + 8) * sizeof(T), st));
     CK(cudaMemsetAsync(P.e_acc, 0, s->C * sizeof(double), st));
     CK(cudaMemsetAsync(P.u, 0, s->C * sizeof(double), st));
     CK(cudaMemsetAsync(P.Ybar, 0, s->C * sizeof(double), st));
     CK(cudaMemsetAsync(P.q, 0, n * sizeof(double), st));
-    CK(cudaMemsetAsync(P.Xe, 0, (E ? E : 1) * sizeof(double), st));
-    CK(cudaMemsetAsync(P.Xbar_d, 0, n * sizeof(double), st));
-    CK(cudaMemsetAsync(P.Xbar_e, 0, (E ? E : 1) * sizeof(double), st));
+    CK(cudaMemsetAsync(P.Xv, 0, h.nnz * sizeof(double), st));
+    CK(cudaMemsetAsync(P.Xbarv, 0, h.nnz * sizeof(double), st));
     CK(cudaMemsetAsync(P.r, 0, n * sizeof(double), st));
     CK(cudaMemsetAsync(P.dsq, 0, n * sizeof(double), st));
     CK(cudaMemsetAsync(P.B0, 0, (size_t)n * s->Dp * sizeof(T), st));
@@ -659,7 +744,7 @@ static int solver_reset_impl(sigsdp_solver* s, cudaStream_t st) {
     CK(cudaMemsetAsync(P.hist_mu, 0, HIST * sizeof(double), st));
     CK(cudaMemsetAsync(P.hist_t, 0, (size_t)HIST * 3 * sizeof(double), st));
     k_fill<double><<<64, 256, 0, st>>>(P.Y, (size_t)s->C, 1.0 / (double)s->C);  // Y = 1/C (mmw.py:62)
-    k_fill<double><<<64, 256, 0, st>>>(P.Xd, (size_t)n, 1.0);                   // X = I   (mmw.py:67)
+    k_set_diag<<<64, 256, 0, st>>>(P.Xv, P.g.dpos, (int)n, 1.0);                // X = I   (mmw.py:67)
     CK(cudaGetLastError());
     s->iters_done = 0;
     return SIGSDP_OK;
@@ -667,6 +752,11 @@ static int solver_reset_impl(sigsdp_solver* s, cudaStream_t st) {
 }  // extern "C++"
 
 int sigsdp_solver_create(const sigsdp_plan* plan, int Z, int D, double eta, int dtype, sigsdp_solver** out) {
+    return sigsdp_solver_create_tiled(plan, Z, D, eta, dtype, -1, out);
+}
+
+int sigsdp_solver_create_tiled(const sigsdp_plan* plan, int Z, int D, double eta, int dtype, int tiling,
+                               sigsdp_solver** out) {
     if (!out) return fail(SIGSDP_EINVAL, "out is null");
     *out = nullptr;
     if (!plan) return fail(SIGSDP_EINVAL, "null plan");
@@ -682,6 +772,7 @@ int sigsdp_solver_create(const sigsdp_plan* plan, int Z, int D, double eta, int 
     s->D = D;
     s->eta = eta;
     s->dtype = dtype;
+    s->tiling = tiling;
     const int VEC = dtype == SIGSDP_F64 ? 2 : 4;
     s->Dp = (D + VEC - 1) / VEC * VEC;
     const int lanes = s->Dp / VEC;
@@ -722,7 +813,7 @@ int sigsdp_solver_set_mode(sigsdp_solver* s, int mode) {
     return SIGSDP_OK;
 }
 
-int sigsdp_solver_info(const sigsdp_solver* s, int64_t info[10]) {
+int sigsdp_solver_info(const sigsdp_solver* s, int64_t info[12]) {
     if (!s || !info) return fail(SIGSDP_EINVAL, "null argument");
     info[0] = s->plan->h.n;
     info[1] = s->Z;
@@ -734,6 +825,8 @@ int sigsdp_solver_info(const sigsdp_solver* s, int64_t info[10]) {
     info[7] = s->grid;
     info[8] = NT;
     info[9] = s->G;
+    info[10] = s->RT;
+    info[11] = (int64_t)s->smem;
     return SIGSDP_OK;
 }
 
@@ -812,16 +905,23 @@ int sigsdp_solver_get_X(sigsdp_solver* s, int averaged, double* diag, double* ga
     CK(cudaSetDevice(s->plan->device));
     CK(cudaDeviceSynchronize());
     const HostPlan& h = s->plan->h;
-    const double* dd = s->dtype == SIGSDP_F64 ? (averaged ? s->p64.Xbar_d : s->p64.Xd) : (averaged ? s->p32.Xbar_d : s->p32.Xd);
-    const double* de = s->dtype == SIGSDP_F64 ? (averaged ? s->p64.Xbar_e : s->p64.Xe) : (averaged ? s->p32.Xbar_e : s->p32.Xe);
-    std::vector<double> tmp;
-    int rc;
-    if (diag) {
-        if ((rc = fetch(tmp, dd, h.n)) != SIGSDP_OK) return rc;
-        for (int64_t k = 0; k < h.n; ++k) diag[h.perm[k]] = tmp[k];
-    }
-    if (gain && h.E_g) CK(cudaMemcpy(gain, de, h.E_g * sizeof(double), cudaMemcpyDeviceToHost));
-    if (asso && h.E_a) CK(cudaMemcpy(asso, de + h.E_g, h.E_a * sizeof(double), cudaMemcpyDeviceToHost));
+    const double* dv = s->dtype == SIGSDP_F64 ? (averaged ? s->p64.Xbarv : s->p64.Xv) : (averaged ? s->p32.Xbarv : s->p32.Xv);
+    std::vector<double> X;
+    int rc = fetch(X, dv, h.nnz);
+    if (rc != SIGSDP_OK) return rc;
+    for (int64_t k = 0; k < h.n; ++k)
+        for (int32_t p = h.rowptr[k]; p < h.rowptr[k + 1]; ++p) {
+            const int32_t e = h.eid[p];
+            if (e < 0) {
+                if (diag) diag[h.perm[k]] = X[p];
+            } else if (k < h.col[p]) {
+                if (e < h.E_g) {
+                    if (gain) gain[e] = X[p];
+                } else if (asso) {
+                    asso[e - h.E_g] = X[p];
+                }
+            }
+        }
     return SIGSDP_OK;
 }
 
@@ -944,10 +1044,10 @@ static SolverView view_of(const sigsdp_solver* s) {
     SolverView v;
     if (s->dtype == SIGSDP_F64) {
         const Prob<double>& P = s->p64;
-        v = SolverView{P.g, P.Z, P.C, P.nH, P.hcoef, P.Y, P.Ybar, P.Xd, P.Xe, P.Xbar_d, P.Xbar_e};
+        v = SolverView{P.g, P.Z, P.C, P.nH, P.hcoef, P.Y, P.Ybar, P.Xv, P.Xbarv};
     } else {
         const Prob<float>& P = s->p32;
-        v = SolverView{P.g, P.Z, P.C, P.nH, P.hcoef, P.Y, P.Ybar, P.Xd, P.Xe, P.Xbar_d, P.Xbar_e};
+        v = SolverView{P.g, P.Z, P.C, P.nH, P.hcoef, P.Y, P.Ybar, P.Xv, P.Xbarv};
     }
     return v;
 }

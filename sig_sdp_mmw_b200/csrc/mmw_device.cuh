@@ -32,6 +32,23 @@ struct PlanDev {
     const double* tnorm;    // n  sqrt(sum_c T[k,c]^2)
     const double* h_max;    // n
     const int* perm;        // n: internal -> caller numbering (nullptr = identity)
+    const int* dpos;        // n: position of the diagonal entry of each row
+    const int* apos;        // E_a: position of the (row < col) entry of each asso edge
+};
+
+// Row tiles for the staged kernels: the rows of a tile are consecutive (after the
+// locality renumbering they are a compact patch of the graph), `ucol` lists the distinct
+// columns the tile touches (ascending) and `lcol` maps every non-zero to its index in
+// that list, so a tile's slice of the sketch block can be staged in shared memory once
+// and reused by all of its rows.
+struct TileDev {
+    int enabled;                 // 0 = no tiling (direct-gather kernels)
+    int ntiles, ucap, nnzcap;
+    const int* trow;             // ntiles + 1: first row of each tile
+    const int* ucnt;             // ntiles: distinct columns of the tile
+    const int* rptr;             // ntiles + 1: runs of consecutive distinct columns
+    const int4* runs;            // {first column, first shared-memory slot, length, 0}
+    const unsigned short* lcol;  // nnz (+ padding)
 };
 
 // device-resident controller: reductions that must be order independent use
@@ -61,15 +78,14 @@ struct Prob {
     const double* nH;      // n  norm_H for this Z (mmw.py:39)
     const double* hcoef;   // n  h/K - S_sum/(K Z)
     double* Lval;          // nnz  L_accu on the union pattern
+    T* Aval;               // nnz  L_accu/2 - mu I in the sketch dtype (what the Taylor terms multiply by)
     double* e_acc;         // C
     double* u;             // C    exp(e_acc - max), unnormalised
     double* Y;             // C
     double* Ybar;          // C    running sum
     double* q;             // n    u_H / norm_H
-    double* Xd;            // n
-    double* Xe;            // E
-    double* Xbar_d;        // n    running sums
-    double* Xbar_e;        // E
+    double* Xv;            // nnz  X on the union pattern (every directed entry, diagonal included)
+    double* Xbarv;         // nnz  running sum of X
     double* r;             // n    row sums of off-diagonal X
     double* dsq;           // n    ||F_k||^2
     T* B0;                 // n x Dp ping
@@ -86,6 +102,7 @@ struct Prob {
     double* hist_t;        // HIST x 3: device-timed microseconds of dual / loss / sketch+Gram
     const double* omega;   // raw normals for this call (caller numbering) or nullptr
     unsigned long long seed;
+    TileDev tl;
 };
 
 // ---------------------------------------------------------------------------
@@ -209,6 +226,131 @@ template <> struct Vec<float> {
     __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
 };
 
+
+// ---------------------------------------------------------------------------
+// TMA bulk copies (cp.async.bulk, SASS UBLKCP) tracked by an mbarrier
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// raw shared-memory loads by 32-bit shared address (keeps the address math 32-bit and the
+// loads LDS, whatever the compiler can or cannot infer about the pointers)
+template <typename T> struct SmemLd;
+template <> struct SmemLd<double> {
+    static __device__ __forceinline__ void vec(Vec<double>& v, unsigned a) {
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.v[0]), "=d"(v.v[1]) : "r"(a));
+    }
+    static __device__ __forceinline__ double val(unsigned a) {
+        double x;
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x) : "r"(a));
+        return x;
+    }
+};
+template <> struct SmemLd<float> {
+    static __device__ __forceinline__ void vec(Vec<float>& v, unsigned a) {
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.v[0]), "=f"(v.v[1]), "=f"(v.v[2]), "=f"(v.v[3]) : "r"(a));
+    }
+    static __device__ __forceinline__ float val(unsigned a) {
+        float x;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(a));
+        return x;
+    }
+};
+__device__ __forceinline__ unsigned lds_u16(unsigned a) {
+    unsigned short x;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(x) : "r"(a));
+    return (unsigned)x;
+}
+
+// per-block staging state.  Dynamic shared memory layout (32-bit shared addresses):
+//   [mbarrier 16 B][rows: ucap x Dp x T][vals: (nnzcap + 4) x T][lcol: (nnzcap + 8) u16]
+template <typename T>
+struct Stage {
+    unsigned rows_a, vals_a, lcol_a, bar_a;
+    unsigned parity;
+    unsigned va, la;   // shared address of the staged value / local column of non-zero 0 (biased by the tile's first nnz)
+};
+
+__device__ __forceinline__ void mbar_expect_tx_a(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_a(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait_a(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+
+// Stage one tile with TMA bulk copies: the distinct rows of `src` (n x Dp, global) its
+// non-zeros touch -- one copy per run of consecutive rows -- plus the tile's contiguous
+// slices of `vals_src` (nnz values of the sketch dtype; nullptr to skip) and of the local
+// column indices, each from a 16-byte aligned superset.  Completion is counted in bytes
+// on the mbarrier; the compute that follows reads shared memory only.
+template <typename T>
+__device__ __forceinline__ void stage_tile(const Prob<T>& P, const T* src, const T* vals_src, int t, Stage<T>& st) {
+    const TileDev& tl = P.tl;
+    constexpr int VA = 16 / (int)sizeof(T);   // values per 16 bytes
+    __syncthreads();  // every reader of the previous tile is done with the buffers
+    const int p0 = P.g.rowptr[tl.trow[t]], p1 = P.g.rowptr[tl.trow[t + 1]];
+    const unsigned rowbytes = (unsigned)(P.Dp * sizeof(T));
+    const int pv = p0 & ~(VA - 1), pl = p0 & ~7;
+    const unsigned vbytes = vals_src ? (unsigned)(((p1 - pv + VA - 1) & ~(VA - 1)) * sizeof(T)) : 0u;
+    const unsigned lbytes = (unsigned)(((p1 - pl + 7) & ~7) * 2);
+    st.va = st.vals_a - (unsigned)(pv * (int)sizeof(T));
+    st.la = st.lcol_a - (unsigned)(pl * 2);
+    fence_proxy_async();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx_a(st.bar_a, (unsigned)tl.ucnt[t] * rowbytes + vbytes + lbytes);
+        bulk_g2s_a(st.lcol_a, tl.lcol + pl, lbytes, st.bar_a);
+        if (vals_src) bulk_g2s_a(st.vals_a, vals_src + pv, vbytes, st.bar_a);
+    }
+    // the row copies are spread over the warps (a bulk copy is a per-warp instruction with
+    // uniform operands, so this spreads them over the SM's four schedulers)
+    for (int i = tl.rptr[t] + threadIdx.x; i < tl.rptr[t + 1]; i += NT) {
+        const int4 r = tl.runs[i];
+        bulk_g2s_a(st.rows_a + (unsigned)r.y * rowbytes, src + (size_t)r.x * P.Dp, (unsigned)r.z * rowbytes, st.bar_a);
+    }
+    mbar_wait_a(st.bar_a, st.parity);
+    st.parity ^= 1u;
+}
+
 // ---------------------------------------------------------------------------
 // Philox4x32-10 + Box-Muller: counter-based normals for throughput mode
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
@@ -223,33 +365,30 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
     }
     return c;
 }
-// VEC standard normals for (iteration, row, first column of the vector)
-__device__ __forceinline__ void philox_normals(unsigned long long seed, long long iter, int row, int colv, double* out2) {
+// VEC standard normals for (iteration, row, vector index).  Box-Muller in fp32 for both
+// sketch dtypes: the sketch only needs Gaussian directions, 24-bit normals are plenty.
+__device__ __forceinline__ void philox_normals4(unsigned long long seed, long long iter, int row, int colv, float* out4) {
     uint4 x = philox4x32_10(make_uint4((unsigned)row, (unsigned)colv, (unsigned)iter, (unsigned)(iter >> 32)),
                             make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
-    double u1 = ((double)(((unsigned long long)x.x << 32) | x.y) + 0.5) * 5.421010862427522e-20;  // 2^-64
-    double u2 = ((double)(((unsigned long long)x.z << 32) | x.w) + 0.5) * 5.421010862427522e-20;
-    double rr = sqrt(-2.0 * log(u1));
-    double s, c;
-    sincospi(2.0 * u2, &s, &c);
-    out2[0] = rr * c;
-    out2[1] = rr * s;
-}
-__device__ __forceinline__ void philox_normals(unsigned long long seed, long long iter, int row, int colv, float* out4) {
-    uint4 x = philox4x32_10(make_uint4((unsigned)row, (unsigned)colv, (unsigned)iter, (unsigned)(iter >> 32)),
-                            make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
-    float u1 = ((float)x.x + 0.5f) * 2.3283064e-10f, u2 = ((float)x.y + 0.5f) * 2.3283064e-10f;
-    float u3 = ((float)x.z + 0.5f) * 2.3283064e-10f, u4 = ((float)x.w + 0.5f) * 2.3283064e-10f;
-    u1 = fminf(u1, 0.99999994f);
-    u3 = fminf(u3, 0.99999994f);
-    float r1 = sqrtf(-2.0f * logf(u1)), r2 = sqrtf(-2.0f * logf(u3));
+    float u1 = ((float)(x.x >> 8) + 0.5f) * 5.9604645e-8f, u2 = ((float)(x.y >> 8) + 0.5f) * 5.9604645e-8f;
+    float u3 = ((float)(x.z >> 8) + 0.5f) * 5.9604645e-8f, u4 = ((float)(x.w >> 8) + 0.5f) * 5.9604645e-8f;
+    float r1 = sqrtf(-2.0f * __logf(u1)), r2 = sqrtf(-2.0f * __logf(u3));
     float s, c;
-    sincospif(2.0f * u2, &s, &c);
+    __sincosf(6.2831853f * u2, &s, &c);
     out4[0] = r1 * c;
     out4[1] = r1 * s;
-    sincospif(2.0f * u4, &s, &c);
+    __sincosf(6.2831853f * u4, &s, &c);
     out4[2] = r2 * c;
     out4[3] = r2 * s;
+}
+__device__ __forceinline__ void philox_normals(unsigned long long seed, long long iter, int row, int colv, double* out2) {
+    float t[4];
+    philox_normals4(seed, iter, row, colv >> 1, t);   // two fp64 vectors share one Philox block
+    out2[0] = (double)t[(colv & 1) * 2];
+    out2[1] = (double)t[(colv & 1) * 2 + 1];
+}
+__device__ __forceinline__ void philox_normals(unsigned long long seed, long long iter, int row, int colv, float* out4) {
+    philox_normals4(seed, iter, row, colv, out4);
 }
 
 // ---------------------------------------------------------------------------
@@ -324,7 +463,7 @@ __device__ void phase_dual(const Prob<T>& P, const Team& team, double* sh) {
             acc = group_sum<G>(tile, acc);
             if (lane == 0) {
                 double eH = (acc * zr - (g.h_max[k] - g.S_sum[k] / Z)) / P.nH[k];
-                double eD = (P.Xd[k] - 1.0) * invD;
+                double eD = (P.Xv[g.dpos[k]] - 1.0) * invD;
                 double a = P.e_acc[k] + P.eta * eD;
                 double b = P.e_acc[K + g.E_a + k] + P.eta * eH;
                 P.e_acc[k] = a;
@@ -335,7 +474,7 @@ __device__ void phase_dual(const Prob<T>& P, const Team& team, double* sh) {
     }
     const double zf = 1.0 / (Z - 1);
     for (int e = team.rank() * NT + threadIdx.x; e < g.E_a; e += team.size() * NT) {
-        double eF = (P.Xe[g.E_g + e] + zf) / cF;
+        double eF = (P.Xv[g.apos[e]] + zf) / cF;
         double a = P.e_acc[K + e] + P.eta * eF;
         P.e_acc[K + e] = a;
         emax = fmax(emax, a);
@@ -432,30 +571,34 @@ __device__ void phase_loss(const Prob<T>& P, const Team& team, int it_local, dou
         P.Y[c] = P.u[c] / S;
     }
 
-    // ---- L_accu and the 1-norm of the shifted half
+    // ---- L_accu, the shifted half A = L_accu/2 - mu I in the sketch dtype, and ||A||_1
     double a1 = 0.0;
+    const double invS = 1.0 / S;
+    const double aF = invS * 0.5 / cF;
     const int ntiles = (K + R - 1) / R;
     for (int t = team.rank(); t < ntiles; t += team.size()) {
         const int k = t * R + grp;
         if (k < K) {
-            const double wk = P.q[k] / S;
+            const double wk = P.q[k] * invS;
             double rowabs = 0.0;
             const int p1 = g.rowptr[k + 1];
             for (int p = g.rowptr[k] + lane; p < p1; p += G) {
                 const int e = g.eid[p];
                 double l, shift = 0.0;
                 if (e < 0) {
-                    l = (P.u[k] / S - sumYD / K) * invD + cLF - cLH;
+                    l = (P.u[k] * invS - sumYD / K) * invD + cLF - cLH;
                     shift = mu;
                 } else if (e < g.E_g) {
-                    const double wc = P.q[g.col[p]] / S;
+                    const double wc = P.q[g.col[p]] * invS;
                     l = gcoef * (g.tfwd[p] * wc + g.tbwd[p] * wk);
                 } else {
-                    l = ((P.u[K + (e - g.E_g)] / S) * 0.5) / cF;
+                    l = P.u[K + (e - g.E_g)] * aF;
                 }
                 const double v = P.Lval[p] - eta * l;
                 P.Lval[p] = v;
-                rowabs += fabs(0.5 * v - shift);
+                const double a = 0.5 * v - shift;
+                P.Aval[p] = (T)a;
+                rowabs += fabs(a);
             }
             rowabs = group_sum<G>(tile, rowabs);
             a1 = fmax(a1, rowabs);
@@ -566,9 +709,7 @@ __device__ void phase_term(const Prob<T>& P, const Team& team, const T* Bin, T* 
                     T vv = (T)0;
                     if (p < p1) {
                         cc = g.col[p];
-                        double a = 0.5 * P.Lval[p];
-                        if (cc == k) a -= mu;
-                        vv = (T)a;
+                        vv = P.Aval[p];
                     }
                     const int cnt = min(G, p1 - pb);
 #pragma unroll 4
@@ -687,21 +828,195 @@ __device__ void phase_gram(const Prob<T>& P, const Team& team, double* sh) {
                     double dot = group_sum<G>(tile, (double)part);
                     if (j == lane) mine = dot;
                 }
-                if (p < p1 && ee >= 0) {
-                    const double x = mine / tr;
-                    rsum += x;
-                    if (k < cc) {
-                        P.Xbar_e[ee] += P.Xe[ee];
-                        P.Xe[ee] = x;
-                    }
+                if (p < p1) {
+                    const double x = ee >= 0 ? mine / tr : P.dsq[k] / tr;
+                    if (ee >= 0) rsum += x;
+                    P.Xbarv[p] += P.Xv[p];
+                    P.Xv[p] = x;
                 }
             }
             rsum = group_sum<G>(tile, rsum);
-            if (lane == 0) {
-                P.r[k] = rsum;
-                P.Xbar_d[k] += P.Xd[k];
-                P.Xd[k] = P.dsq[k] / tr;
+            if (lane == 0) P.r[k] = rsum;
+        }
+    }
+}
+
+
+// ===========================================================================
+// Staged Taylor term: same arithmetic as phase_term, but everything a tile needs -- the
+// distinct rows of B its non-zeros touch, its slice of A = L_accu/2 - mu I and its local
+// column indices -- is brought into shared memory by TMA bulk copies first, so the multiply
+// loop never waits on global memory: per non-zero one 2-byte and one value broadcast load,
+// one 16-byte row load and VEC FMAs.  L2 -> SM traffic for B drops by the tile's reuse
+// factor, and the two resident blocks per SM overlap one tile's copies with the other's math.
+template <typename T, int G, class Team>
+__device__ void phase_term_staged(const Prob<T>& P, const Team& team, const T* Bin, T* Bout, double coeff, int slot,
+                                  double* sh, Stage<T>& st) {
+    using V = Vec<T>;
+    using LD = SmemLd<T>;
+    constexpr int VEC = V::N;
+    constexpr int W = (int)sizeof(T);
+    const PlanDev& g = P.g;
+    const TileDev& tl = P.tl;
+    const int Dp = P.Dp;
+    const unsigned rowb = (unsigned)(Dp * W);
+    const int lane = threadIdx.x & (G - 1);
+    const int grp = threadIdx.x / G;
+    constexpr int R = NT / G;
+    Ctrl* ctrl = P.ctrl;
+    if (team.rank() == 0 && threadIdx.x == 0) {
+        ctrl->nrm_b[(slot + 1) % 3] = 0ull;
+        ctrl->nrm_f[(slot + 1) % 3] = 0ull;
+    }
+    const T cf = (T)coeff;
+    double bmax = 0.0, fmaxv = 0.0, trp = 0.0;
+    for (int t = team.rank(); t < tl.ntiles; t += team.size()) {
+        const int r0 = tl.trow[t], r1 = tl.trow[t + 1];
+        stage_tile(P, Bin, (const T*)P.Aval, t, st);
+        for (int kb = r0; kb < r1; kb += R) {   // block-uniform trip count
+            const int k = kb + grp;
+            const bool valid = k < r1;
+            const int p0 = valid ? g.rowptr[k] : 0, len = valid ? g.rowptr[k + 1] - p0 : 0;
+            double rsb = 0.0, rsf = 0.0, dd = 0.0;
+            for (int cb = 0; cb < Dp; cb += G * VEC) {
+                const int c0 = cb + lane * VEC;
+                const bool act = valid && c0 < Dp;
+                V f;
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) f.v[v] = (T)0;
+                if (act) f.load(P.F + (size_t)k * Dp + c0);   // consumed in the epilogue
+                T acc[VEC];
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) acc[v] = (T)0;
+                if (act) {
+                    const unsigned la = st.la + 2u * (unsigned)p0, va = st.va + (unsigned)(W * p0);
+                    const unsigned rb = st.rows_a + (unsigned)(c0 * W);
+                    int j = 0;
+                    for (; j + 4 <= len; j += 4) {
+                        unsigned lc[4];
+                        T a[4];
+                        V b[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            lc[i] = lds_u16(la + 2u * (unsigned)(j + i));
+                            a[i] = LD::val(va + (unsigned)(W * (j + i)));
+                        }
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) LD::vec(b[i], rb + lc[i] * rowb);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+#pragma unroll
+                            for (int v = 0; v < VEC; ++v) acc[v] = fma(a[i], b[i].v[v], acc[v]);
+                    }
+                    for (; j < len; ++j) {
+                        const unsigned lc = lds_u16(la + 2u * (unsigned)j);
+                        const T a = LD::val(va + (unsigned)(W * j));
+                        V b;
+                        LD::vec(b, rb + lc * rowb);
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) acc[v] = fma(a, b.v[v], acc[v]);
+                    }
+                    V bn;
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) {
+                        bn.v[v] = cf * acc[v];
+                        f.v[v] += bn.v[v];
+                        rsb += fabs((double)bn.v[v]);
+                        rsf += fabs((double)f.v[v]);
+                        dd += (double)f.v[v] * (double)f.v[v];
+                    }
+                    bn.store(Bout + (size_t)k * Dp + c0);
+                    f.store(P.F + (size_t)k * Dp + c0);
+                }
             }
+            // all 32 lanes are converged here: xor-shuffles below G stay inside the group
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) {
+                rsb += __shfl_xor_sync(0xffffffffu, rsb, o);
+                rsf += __shfl_xor_sync(0xffffffffu, rsf, o);
+                dd += __shfl_xor_sync(0xffffffffu, dd, o);
+            }
+            bmax = fmax(bmax, rsb);
+            fmaxv = fmax(fmaxv, rsf);
+            if (valid && lane == 0) {
+                P.dsq[k] = dd;
+                trp += dd;
+            }
+        }
+    }
+    bmax = block_max(bmax, sh);
+    fmaxv = block_max(fmaxv, sh);
+    trp = block_sum(trp, sh);
+    if (threadIdx.x == 0) {
+        atomicMax(&ctrl->nrm_b[slot], dkey_pos(bmax));
+        atomicMax(&ctrl->nrm_f[slot], dkey_pos(fmaxv));
+        P.ptr[team.rank()] = trp;
+    }
+}
+
+// Staged Gram: the tile's rows of F (its own rows included: the diagonal is in the
+// pattern) and its local column indices sit in shared memory; one warp per row, one lane
+// per non-zero, each lane accumulates its own dot product over the sketch columns.  No
+// shuffles; each lane starts at a different 16-byte chunk and wraps around, so the eight
+// lanes of a quarter-warp always hit eight different bank groups whatever rows they read.
+template <typename T, int G, class Team>
+__device__ void phase_gram_staged(const Prob<T>& P, const Team& team, double* sh, Stage<T>& st) {
+    using V = Vec<T>;
+    using LD = SmemLd<T>;
+    constexpr int VEC = V::N;
+    constexpr int W = (int)sizeof(T);
+    const PlanDev& g = P.g;
+    const TileDev& tl = P.tl;
+    const int K = g.n, Dp = P.Dp;
+    const unsigned rowb = (unsigned)(Dp * W);
+    const int nc = Dp / VEC;
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    const double tr = team_sum(P.ptr, 1, team.size(), sh) / K;
+    const double inv_tr = 1.0 / tr;
+    for (int t = team.rank(); t < tl.ntiles; t += team.size()) {
+        const int r0 = tl.trow[t], r1 = tl.trow[t + 1];
+        stage_tile(P, (const T*)P.F, (const T*)nullptr, t, st);
+        for (int kb = r0; kb < r1; kb += NWARP) {   // block-uniform trip count
+            const int k = kb + wrp;
+            double rsum = 0.0;
+            if (k < r1) {
+                const int p0 = g.rowptr[k], p1 = g.rowptr[k + 1], pd = g.dpos[k];
+                const unsigned abase = st.rows_a + lds_u16(st.la + 2u * (unsigned)pd) * rowb;
+                for (int p = p0 + lane; p < p1; p += 32) {
+                    const double xold = P.Xv[p], xbar = P.Xbarv[p];   // in flight during the dot product
+                    double x;
+                    if (p == pd) {
+                        x = P.dsq[k] * inv_tr;
+                    } else {
+                        const unsigned bbase = st.rows_a + lds_u16(st.la + 2u * (unsigned)p) * rowb;
+                        T d0 = (T)0, d1 = (T)0;
+                        int ch = lane % nc;
+                        for (int s2 = 0; s2 < nc; s2 += 2) {
+                            V a, b;
+                            unsigned off = (unsigned)(ch * 16);
+                            LD::vec(a, abase + off);
+                            LD::vec(b, bbase + off);
+#pragma unroll
+                            for (int v = 0; v < VEC; ++v) d0 = fma(a.v[v], b.v[v], d0);
+                            ch = ch + 1 == nc ? 0 : ch + 1;
+                            if (s2 + 1 < nc) {
+                                off = (unsigned)(ch * 16);
+                                LD::vec(a, abase + off);
+                                LD::vec(b, bbase + off);
+#pragma unroll
+                                for (int v = 0; v < VEC; ++v) d1 = fma(a.v[v], b.v[v], d1);
+                                ch = ch + 1 == nc ? 0 : ch + 1;
+                            }
+                        }
+                        x = ((double)d0 + (double)d1) * inv_tr;
+                        rsum += x;
+                    }
+                    P.Xbarv[p] = xbar + xold;
+                    P.Xv[p] = x;
+                }
+            }
+            rsum = warp_sum(rsum);
+            if (k < r1 && lane == 0) P.r[k] = rsum;
         }
     }
 }
@@ -732,9 +1047,31 @@ __device__ __forceinline__ void record_history(const Prob<T>& P, long long iter,
 }
 
 // The whole MMW loop for one team: n_iters iterations, no host involvement.
+template <typename T>
+__device__ __forceinline__ void stage_setup(const Prob<T>& P, unsigned char* dyn, Stage<T>& st) {
+    const TileDev& tl = P.tl;
+    const unsigned base = smem_u32(dyn);
+    const unsigned rows_bytes = ((unsigned)tl.ucap * (unsigned)P.Dp * (unsigned)sizeof(T) + 15u) & ~15u;
+    const unsigned vals_bytes = ((unsigned)(tl.nnzcap + 4) * (unsigned)sizeof(T) + 15u) & ~15u;
+    st.bar_a = base;
+    st.rows_a = base + 16u;
+    st.vals_a = st.rows_a + rows_bytes;
+    st.lcol_a = st.vals_a + vals_bytes;
+    st.parity = 0u;
+    st.va = st.vals_a;
+    st.la = st.lcol_a;
+    if (tl.enabled) {
+        if (threadIdx.x == 0) mbar_init(reinterpret_cast<unsigned long long*>(dyn), 1);
+        __syncthreads();
+    }
+}
+
 template <typename T, int G, class Team>
-__device__ void run_iterations(const Prob<T>& P, const Team& team, int n_iters) {
+__device__ void run_iterations(const Prob<T>& P, const Team& team, int n_iters, unsigned char* dyn) {
     __shared__ double sh[NWARP + 2];
+    Stage<T> st;
+    stage_setup(P, dyn, st);
+    const bool staged = P.tl.enabled != 0;
     Ctrl* ctrl = P.ctrl;
     long long terms = 0;
     const bool leader = team.rank() == 0 && threadIdx.x == 0;
@@ -763,7 +1100,11 @@ __device__ void run_iterations(const Prob<T>& P, const Team& team, int n_iters) 
             }
             for (int j = 0; j < ts.m_star; ++j) {
                 const int slot = tcount % 3;
-                phase_term<T, G>(P, team, bin, bout, 1.0 / ((double)ts.s * (double)(j + 1)), ts.mu, slot, sh);
+                const double coeff = 1.0 / ((double)ts.s * (double)(j + 1));
+                if (staged)
+                    phase_term_staged<T, G>(P, team, bin, bout, coeff, slot, sh, st);
+                else
+                    phase_term<T, G>(P, team, bin, bout, coeff, ts.mu, slot, sh);
                 team.sync();
                 const double c2 = dkey_pos_inv(ld_u64(&ctrl->nrm_b[slot]));
                 fn_last = dkey_pos_inv(ld_u64(&ctrl->nrm_f[slot]));
@@ -776,7 +1117,10 @@ __device__ void run_iterations(const Prob<T>& P, const Team& team, int n_iters) 
             }
         }
         terms += tcount;
-        phase_gram<T, G>(P, team, sh);
+        if (staged)
+            phase_gram_staged<T, G>(P, team, sh, st);
+        else
+            phase_gram<T, G>(P, team, sh);
         team.sync();
         if (leader) {
             const long long iter = ctrl->iter + it;

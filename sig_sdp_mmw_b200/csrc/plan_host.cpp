@@ -326,7 +326,73 @@ int build_host_plan(int64_t n, const int32_t* Sp, const int32_t* Si, const doubl
         P.perm.swap(perm);
         P.iperm.swap(iperm);
     }
+    P.dpos.assign(n, -1);
+    P.apos.assign(P.E_a, -1);
+    for (int64_t k = 0; k < n; ++k)
+        for (int32_t q = P.rowptr[k]; q < P.rowptr[k + 1]; ++q) {
+            if (P.eid[q] < 0) P.dpos[k] = q;
+            else if (P.eid[q] >= P.E_g && k < P.col[q]) P.apos[P.eid[q] - P.E_g] = q;
+        }
     return SIGSDP_OK;
+}
+
+void build_tiles(const HostPlan& P, int max_rows, int ucap, int nnzcap, HostTiles& T) {
+    const int64_t n = P.n;
+    T = HostTiles();
+    T.max_rows = max_rows;
+    T.ucap = std::min(ucap, 65535);
+    T.nnzcap = nnzcap;
+    T.lcol.resize(P.nnz);
+    T.trow.push_back(0);
+    T.rptr.push_back(0);
+    std::vector<int32_t> stamp(n, -1), local(n, 0), cols, fresh;
+    int64_t r0 = 0;
+    int t = 0;
+    while (r0 < n) {
+        cols.clear();
+        int64_t r1 = r0;
+        while (r1 < n && r1 - r0 < max_rows) {
+            // distinct columns row r1 would add
+            fresh.clear();
+            for (int32_t q = P.rowptr[r1]; q < P.rowptr[r1 + 1]; ++q) {
+                const int32_t c = P.col[q];
+                if (stamp[c] != t) {
+                    stamp[c] = t;
+                    fresh.push_back(c);
+                }
+            }
+            const bool fits = (int)(cols.size() + fresh.size()) <= T.ucap &&
+                              P.rowptr[r1 + 1] - P.rowptr[r0] <= nnzcap;
+            if (!fits) {
+                for (int32_t c : fresh) stamp[c] = -1;
+                break;
+            }
+            cols.insert(cols.end(), fresh.begin(), fresh.end());
+            ++r1;
+        }
+        if (r1 == r0) return;  // a single row exceeds the caps: T.ok stays false
+        std::sort(cols.begin(), cols.end());
+        for (size_t i = 0; i < cols.size(); ++i) local[cols[i]] = (int32_t)i;
+        for (int32_t q = P.rowptr[r0]; q < P.rowptr[r1]; ++q) T.lcol[q] = (uint16_t)local[P.col[q]];
+        for (size_t i = 0; i < cols.size();) {
+            size_t j = i + 1;
+            while (j < cols.size() && cols[j] == cols[j - 1] + 1) ++j;
+            T.runs.push_back(cols[i]);
+            T.runs.push_back((int32_t)i);
+            T.runs.push_back((int32_t)(j - i));
+            T.runs.push_back(0);
+            i = j;
+        }
+        T.rptr.push_back((int32_t)(T.runs.size() / 4));
+        T.ucnt.push_back((int32_t)cols.size());
+        T.trow.push_back((int32_t)r1);
+        T.umax = std::max<int>(T.umax, (int)cols.size());
+        T.nnzmax = std::max<int>(T.nnzmax, P.rowptr[r1] - P.rowptr[r0]);
+        r0 = r1;
+        ++t;
+    }
+    T.ntiles = t;
+    T.ok = true;
 }
 
 int round_greedy_host(int64_t n, int Z, const int32_t* Sp, const int32_t* Si, const double* Sx,

@@ -24,7 +24,25 @@ struct HostPlan {
     // perm[new] = old, iperm[old] = new
     std::vector<int32_t> perm, iperm;
     int order = 0;
+    // position of each row's diagonal entry; position of the (row < col, internal
+    // numbering) entry of each asso edge
+    std::vector<int32_t> dpos, apos;
 };
+
+// Row tiles: consecutive rows grouped greedily so that a tile has at most `max_rows` rows,
+// `ucap` distinct columns and `nnzcap` non-zeros (see TileDev in mmw_device.cuh).
+// ok = false when a single row exceeds the caps (the caller falls back to gather kernels).
+struct HostTiles {
+    int max_rows = 0, ucap = 0, nnzcap = 0;
+    int ntiles = 0, umax = 0, nnzmax = 0;
+    bool ok = false;
+    std::vector<int32_t> trow;   // ntiles + 1: first row of each tile
+    std::vector<int32_t> ucnt;   // ntiles: distinct columns
+    std::vector<int32_t> rptr;   // ntiles + 1: runs of consecutive distinct columns
+    std::vector<int32_t> runs;   // 4 ints per run: first column, first slot, length, 0
+    std::vector<uint16_t> lcol;  // nnz
+};
+void build_tiles(const HostPlan& P, int max_rows, int ucap, int nnzcap, HostTiles& out);
 
 // returns 0 or a negative SIGSDP_E* code; err gets the message
 int build_host_plan(int64_t n, const int32_t* Sp, const int32_t* Si, const double* Sx,

@@ -13,7 +13,8 @@ has no notion of (all default to the reference's behaviour):
             "device" -- counter-based Philox normals generated inside the kernel
                        (throughput mode; statistically equivalent, different stream)
   device  : CUDA device index
-  order   : 0 keep the caller's node numbering inside the kernels, 1 renumber for locality
+  order   : 1 (default) renumber nodes inside the kernels for locality (transparent: all
+            inputs and outputs stay in the caller's numbering), 0 keep the caller's order
 
 There is no CPU fallback: a missing library or CUDA device raises."""
 import math
@@ -31,7 +32,7 @@ _OMEGA_CHUNK_BYTES = 1 << 30
 
 class mmw(STATS_OBJECT, sdp_solver):
     def __init__(self, nit=100, rank_radio=2, alpha=1., eta=0.1, log_gap=False,
-                 dtype="float64", omega="numpy", device=0, order=0, seed=0):
+                 dtype="float64", omega="numpy", device=0, order=1, seed=0):
         sdp_solver.__init__(self, nit=nit, rank_radio=rank_radio, alpha=alpha)
         self.eta = eta
         self.LOG_GAP = log_gap

@@ -26,14 +26,14 @@ def _require_gpu():
     assert _lib.load().sigsdp_device_count() >= 1
 
 
-def _run_device(g, nit, dtype=_lib.F64, mode=_lib.MODE_FUSED, order=0, chunk=None):
+def _run_device(g, nit, dtype=_lib.F64, mode=_lib.MODE_FUSED, order=0, chunk=None, tiling=-1):
     _require_gpu()
     S = g["state"][0]
     K = S.shape[0]
     D = g["Z"] * g["rank_radio"]
     om = np.stack(omega_stream(g["seed"], K, D, nit))
     plan = _lib.Plan(g["state"], device=0, order=order)
-    sol = _lib.Solver(plan, g["Z"], D, g["eta"], dtype, mode)
+    sol = _lib.Solver(plan, g["Z"], D, g["eta"], dtype, mode, tiling)
     om_d = torch.from_numpy(om).cuda()
     chunk = chunk or nit
     done = 0
@@ -122,6 +122,24 @@ def test_stepwise_mode_equals_fused(name):
         np.testing.assert_allclose(x, y, rtol=1e-12, atol=1e-15)
     np.testing.assert_allclose(a.sketch(), b.sketch(), rtol=1e-12, atol=1e-15)
     np.testing.assert_array_equal(a.history(nit)["nterms"], b.history(nit)["nterms"])
+
+
+@pytest.mark.parametrize("name,order,tiling,dtype", [
+    ("n300_z10", 0, 0, _lib.F64),      # direct-gather kernels
+    ("n300_z10", 1, 32, _lib.F64),     # staged, small tiles
+    ("n500_z13", 1, 128, _lib.F64),    # staged, large tiles, D = 26 (ragged lanes)
+    ("n500_z4_cfg1", 0, -1, _lib.F64), # automatic
+    ("n75_z6_rr3", 1, 64, _lib.F64),
+])
+def test_tiling_variants_match_oracle(name, order, tiling, dtype):
+    g = load_case(name)
+    nit = min(g["nit"], 40)
+    _, sol, om = _run_device(g, nit, dtype=dtype, order=order, tiling=tiling)
+    assert sol.tile_rows == (tiling if tiling >= 0 else sol.tile_rows)
+    _, st = _run_oracle(g, nit, om)
+    _assert_state_close(sol, st, RTOL64)
+    _, step, _ = _run_device(g, nit, dtype=dtype, order=order, tiling=tiling, mode=_lib.MODE_STEPWISE)
+    np.testing.assert_allclose(step.sketch(), sol.sketch(), rtol=1e-12, atol=1e-15)
 
 
 def test_chunked_calls_equal_one_call():
