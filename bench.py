@@ -199,7 +199,9 @@ def run_ours(args):
         if rank == 0:
             sampler.stop()
             print(json.dumps({"profiling_run": True, "mode": args.mode, "workload": args.workload, "steps": args.steps,
-                              "ms": ms, "taylor_terms": terms, "phase_us": phase.tolist()}))
+                              "ms": ms, "taylor_terms": terms, "phase_us": phase.tolist(), "grid": sol.grid,
+                              "tile_rows": sol.tile_rows, "smem": sol.smem,
+                              "block0_Mcycles": {k: round(v / 1e6, 3) for k, v in sol.debug_cycles().items()}}))
         return
 
     # ---- end to end through the drop-in object, host buffers in, host factor out

@@ -135,6 +135,10 @@ int sigsdp_solver_get_history(sigsdp_solver* s, int count, int32_t* m_star_host,
  * dual (mmw.py:124-142) | loss (:144-170) | sketch + Gram (:172-197) -- what the
  * reference logs as mmw_dual / mmw_loss / mmw_expm.  Fused mode only (zeros otherwise). */
 int sigsdp_solver_get_phase_times(sigsdp_solver* s, int count, double* us_host);
+/* Block-0 cycle counters of the fused kernel since create/reset (SM clock cycles):
+ * [0] Taylor-term staging wait, [1] Taylor-term compute, [2] Gram staging wait,
+ * [3] Gram compute, [4] grid-barrier wait, [5] dual, [6] exp, [7] loss.  Diagnostics. */
+int sigsdp_solver_debug_cycles(sigsdp_solver* s, int64_t out8[8]);
 /* total Taylor terms (SpMM passes) executed since create/reset */
 int sigsdp_solver_total_terms(sigsdp_solver* s, int64_t* out);
 

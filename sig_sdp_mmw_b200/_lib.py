@@ -54,6 +54,7 @@ def load():
         "sigsdp_solver_get_sketch": [vp, f64p],
         "sigsdp_solver_get_history": [vp, C.c_int, i32p, i32p, i32p, f64p, f64p],
         "sigsdp_solver_total_terms": [vp, i64p],
+        "sigsdp_solver_debug_cycles": [vp, i64p],
         "sigsdp_solver_get_phase_times": [vp, C.c_int, f64p],
         "sigsdp_solver_xavg_matrix": [vp, C.c_double, vp],
         "sigsdp_solver_gap_prepare": [vp, f64p, vp],
@@ -231,6 +232,12 @@ class Solver:
         v = np.empty(self.plan.nnz)
         check(load().sigsdp_solver_get_matrix(self.handle, _p(v, C.c_double)))
         return v
+
+    def debug_cycles(self):
+        a = (C.c_int64 * 8)()
+        check(load().sigsdp_solver_debug_cycles(self.handle, a))
+        keys = ["term_wait", "term_compute", "gram_wait", "gram_compute", "grid_sync", "dual", "exp", "loss"]
+        return dict(zip(keys, [int(x) for x in a]))
 
     def total_terms(self):
         v = C.c_int64()

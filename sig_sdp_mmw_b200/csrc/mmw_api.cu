@@ -1015,6 +1015,16 @@ int sigsdp_solver_get_phase_times(sigsdp_solver* s, int count, double* us_host) 
     return SIGSDP_OK;
 }
 
+int sigsdp_solver_debug_cycles(sigsdp_solver* s, int64_t out8[8]) {
+    if (!s || !out8) return fail(SIGSDP_EINVAL, "null argument");
+    CK(cudaSetDevice(s->plan->device));
+    CK(cudaDeviceSynchronize());
+    Ctrl hc;
+    CK(cudaMemcpy(&hc, s->dtype == SIGSDP_F64 ? s->p64.ctrl : s->p32.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 8; ++i) out8[i] = hc.dbg[i];
+    return SIGSDP_OK;
+}
+
 int sigsdp_solver_total_terms(sigsdp_solver* s, int64_t* out) {
     if (!s || !out) return fail(SIGSDP_EINVAL, "null argument");
     CK(cudaSetDevice(s->plan->device));

@@ -67,6 +67,9 @@ struct Ctrl {
     int m_star, done, nterms;
     long long s;
     double c1, a1;
+    // block-0 cycle counters (clock64): [0] term staging wait, [1] term compute, [2] gram staging
+    // wait, [3] gram compute, [4] grid-barrier wait, [5] dual, [6] exp, [7] loss
+    long long dbg[8];
 };
 
 template <typename T>
@@ -324,7 +327,9 @@ __device__ __forceinline__ void mbar_wait_a(unsigned bar, unsigned parity) {
 // column indices, each from a 16-byte aligned superset.  Completion is counted in bytes
 // on the mbarrier; the compute that follows reads shared memory only.
 template <typename T>
-__device__ __forceinline__ void stage_tile(const Prob<T>& P, const T* src, const T* vals_src, int t, Stage<T>& st) {
+__device__ __forceinline__ void stage_tile(const Prob<T>& P, const T* src, const T* vals_src, int t, Stage<T>& st,
+                                           long long* wait_cycles = nullptr) {
+    const long long tc0 = wait_cycles ? clock64() : 0;
     const TileDev& tl = P.tl;
     constexpr int VA = 16 / (int)sizeof(T);   // values per 16 bytes
     __syncthreads();  // every reader of the previous tile is done with the buffers
@@ -335,7 +340,6 @@ __device__ __forceinline__ void stage_tile(const Prob<T>& P, const T* src, const
     const unsigned lbytes = (unsigned)(((p1 - pl + 7) & ~7) * 2);
     st.va = st.vals_a - (unsigned)(pv * (int)sizeof(T));
     st.la = st.lcol_a - (unsigned)(pl * 2);
-    fence_proxy_async();
     if (threadIdx.x == 0) {
         mbar_expect_tx_a(st.bar_a, (unsigned)tl.ucnt[t] * rowbytes + vbytes + lbytes);
         bulk_g2s_a(st.lcol_a, tl.lcol + pl, lbytes, st.bar_a);
@@ -349,6 +353,7 @@ __device__ __forceinline__ void stage_tile(const Prob<T>& P, const T* src, const
     }
     mbar_wait_a(st.bar_a, st.parity);
     st.parity ^= 1u;
+    if (wait_cycles) *wait_cycles += clock64() - tc0;
 }
 
 // ---------------------------------------------------------------------------
@@ -870,9 +875,13 @@ __device__ void phase_term_staged(const Prob<T>& P, const Team& team, const T* B
     }
     const T cf = (T)coeff;
     double bmax = 0.0, fmaxv = 0.0, trp = 0.0;
+    const bool timed = team.rank() == 0 && threadIdx.x == 0;
+    long long wait_c = 0;
+    const long long tph0 = timed ? clock64() : 0;
+    fence_proxy_async();   // order this phase's bulk copies after the barrier that published their source
     for (int t = team.rank(); t < tl.ntiles; t += team.size()) {
         const int r0 = tl.trow[t], r1 = tl.trow[t + 1];
-        stage_tile(P, Bin, (const T*)P.Aval, t, st);
+        stage_tile(P, Bin, (const T*)P.Aval, t, st, timed ? &wait_c : nullptr);
         for (int kb = r0; kb < r1; kb += R) {   // block-uniform trip count
             const int k = kb + grp;
             const bool valid = k < r1;
@@ -952,6 +961,10 @@ __device__ void phase_term_staged(const Prob<T>& P, const Team& team, const T* B
         atomicMax(&ctrl->nrm_f[slot], dkey_pos(fmaxv));
         P.ptr[team.rank()] = trp;
     }
+    if (timed) {
+        ctrl->dbg[0] += wait_c;
+        ctrl->dbg[1] += clock64() - tph0 - wait_c;
+    }
 }
 
 // Staged Gram: the tile's rows of F (its own rows included: the diagonal is in the
@@ -973,9 +986,13 @@ __device__ void phase_gram_staged(const Prob<T>& P, const Team& team, double* sh
     const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
     const double tr = team_sum(P.ptr, 1, team.size(), sh) / K;
     const double inv_tr = 1.0 / tr;
+    const bool timed = team.rank() == 0 && threadIdx.x == 0;
+    long long wait_c = 0;
+    const long long tph0 = timed ? clock64() : 0;
+    fence_proxy_async();
     for (int t = team.rank(); t < tl.ntiles; t += team.size()) {
         const int r0 = tl.trow[t], r1 = tl.trow[t + 1];
-        stage_tile(P, (const T*)P.F, (const T*)nullptr, t, st);
+        stage_tile(P, (const T*)P.F, (const T*)nullptr, t, st, timed ? &wait_c : nullptr);
         for (int kb = r0; kb < r1; kb += NWARP) {   // block-uniform trip count
             const int k = kb + wrp;
             double rsum = 0.0;
@@ -1018,6 +1035,10 @@ __device__ void phase_gram_staged(const Prob<T>& P, const Team& team, double* sh
             rsum = warp_sum(rsum);
             if (k < r1 && lane == 0) P.r[k] = rsum;
         }
+    }
+    if (timed) {
+        P.ctrl->dbg[2] += wait_c;
+        P.ctrl->dbg[3] += clock64() - tph0 - wait_c;
     }
 }
 
@@ -1075,16 +1096,34 @@ __device__ void run_iterations(const Prob<T>& P, const Team& team, int n_iters, 
     Ctrl* ctrl = P.ctrl;
     long long terms = 0;
     const bool leader = team.rank() == 0 && threadIdx.x == 0;
+    long long sync_c = 0, c_dual = 0, c_exp = 0, c_loss = 0;
+#define TIMED_SYNC()                                   \
+    do {                                               \
+        const long long ts0_ = leader ? clock64() : 0; \
+        team.sync();                                   \
+        if (leader) sync_c += clock64() - ts0_;        \
+    } while (0)
     for (int it = 0; it < n_iters; ++it) {
         unsigned long long t0 = 0, t1 = 0, t2 = 0;
-        if (leader) t0 = globaltimer_ns();
+        long long cc = 0;
+        if (leader) {
+            t0 = globaltimer_ns();
+            cc = clock64();
+        }
         phase_dual<T, G>(P, team, sh);
-        team.sync();
+        if (leader) c_dual += clock64() - cc;
+        TIMED_SYNC();
+        if (leader) cc = clock64();
         phase_exp<T, G>(P, team, sh);
-        team.sync();
-        if (leader) t1 = globaltimer_ns();
+        if (leader) c_exp += clock64() - cc;
+        TIMED_SYNC();
+        if (leader) {
+            t1 = globaltimer_ns();
+            cc = clock64();
+        }
         phase_loss<T, G>(P, team, it, sh);
-        team.sync();
+        if (leader) c_loss += clock64() - cc;
+        TIMED_SYNC();
         if (leader) t2 = globaltimer_ns();
         TaylorState ts;
         taylor_begin(ctrl, ts);
@@ -1096,7 +1135,7 @@ __device__ void run_iterations(const Prob<T>& P, const Team& team, int n_iters, 
             if (si > 0) {
                 phase_copy<T, G>(P, team, bin);
                 c1 = fn_last;
-                team.sync();
+                TIMED_SYNC();
             }
             for (int j = 0; j < ts.m_star; ++j) {
                 const int slot = tcount % 3;
@@ -1105,7 +1144,7 @@ __device__ void run_iterations(const Prob<T>& P, const Team& team, int n_iters, 
                     phase_term_staged<T, G>(P, team, bin, bout, coeff, slot, sh, st);
                 else
                     phase_term<T, G>(P, team, bin, bout, coeff, ts.mu, slot, sh);
-                team.sync();
+                TIMED_SYNC();
                 const double c2 = dkey_pos_inv(ld_u64(&ctrl->nrm_b[slot]));
                 fn_last = dkey_pos_inv(ld_u64(&ctrl->nrm_f[slot]));
                 T* tmp = bin;
@@ -1121,7 +1160,7 @@ __device__ void run_iterations(const Prob<T>& P, const Team& team, int n_iters, 
             phase_gram_staged<T, G>(P, team, sh, st);
         else
             phase_gram<T, G>(P, team, sh);
-        team.sync();
+        TIMED_SYNC();
         if (leader) {
             const long long iter = ctrl->iter + it;
             record_history(P, iter, ts, tcount);
@@ -1132,9 +1171,14 @@ __device__ void run_iterations(const Prob<T>& P, const Team& team, int n_iters, 
             ht[2] = (double)(t3 - t2) * 1e-3;
         }
     }
+#undef TIMED_SYNC
     if (team.rank() == 0 && threadIdx.x == 0) {
         ctrl->iter += n_iters;
         ctrl->total_terms += terms;
+        ctrl->dbg[4] += sync_c;
+        ctrl->dbg[5] += c_dual;
+        ctrl->dbg[6] += c_exp;
+        ctrl->dbg[7] += c_loss;
     }
 }
 
