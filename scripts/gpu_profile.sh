@@ -9,7 +9,7 @@ FUSE="python bench.py --workload $WL --order $ORD --tiling $TIL --mode fused --s
 echo "$(date +%T) plain step" > $LOG
 timeout 300 $STEP >> $LOG 2>&1 || { echo "plain stepwise run failed" >> $LOG; tail -5 $LOG; exit 1; }
 echo "$(date +%T) ncu full step" >> $LOG
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k_term|k_gram|k_loss|k_dual|k_exp' -s 24 -c 6 -o gpurun_out/prof_step_$TAG -f $STEP >> $LOG 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_term -s 8 -c 2 -o gpurun_out/prof_step_$TAG -f $STEP >> $LOG 2>&1
 echo "$(date +%T) rc=$?" >> $LOG
 if [ "$FUSED" = "1" ]; then
   timeout 300 $FUSE >> $LOG 2>&1 || { echo "plain fused run failed" >> $LOG; exit 1; }

@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsigsdp_mmw.so")
+LIB_PATH = os.environ.get("SIGSDP_LIB") or os.path.join(_HERE, "libsigsdp_mmw.so")
 
 F64, F32 = 0, 1
 MODE_FUSED, MODE_STEPWISE = 0, 1

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <numeric>
 #include <queue>
 
@@ -337,6 +338,8 @@ int build_host_plan(int64_t n, const int32_t* Sp, const int32_t* Si, const doubl
 }
 
 void build_tiles(const HostPlan& P, int max_rows, int ucap, int nnzcap, HostTiles& T) {
+    int run_gap = 2;
+    if (const char* e = getenv("SIGSDP_RUN_GAP")) run_gap = std::max(0, atoi(e));
     const int64_t n = P.n;
     T = HostTiles();
     T.max_rows = max_rows;
@@ -372,21 +375,39 @@ void build_tiles(const HostPlan& P, int max_rows, int ucap, int nnzcap, HostTile
         }
         if (r1 == r0) return;  // a single row exceeds the caps: T.ok stays false
         std::sort(cols.begin(), cols.end());
-        for (size_t i = 0; i < cols.size(); ++i) local[cols[i]] = (int32_t)i;
-        for (int32_t q = P.rowptr[r0]; q < P.rowptr[r1]; ++q) T.lcol[q] = (uint16_t)local[P.col[q]];
+        // runs of (nearly) consecutive columns, one bulk copy each: columns separated by at most
+        // `gap` unneeded rows share a run (fewer, larger copies at the price of a few extra rows);
+        // the gap shrinks until the copied rows fit the cap
+        int gap = run_gap;
+        int copied = 0;
+        for (;; gap /= 2) {
+            copied = 0;
+            for (size_t i = 0; i < cols.size();) {
+                size_t j = i + 1;
+                while (j < cols.size() && cols[j] - cols[j - 1] <= gap + 1) ++j;
+                copied += cols[j - 1] - cols[i] + 1;
+                i = j;
+            }
+            if (copied <= T.ucap || gap == 0) break;
+        }
+        int slot = 0;
         for (size_t i = 0; i < cols.size();) {
             size_t j = i + 1;
-            while (j < cols.size() && cols[j] == cols[j - 1] + 1) ++j;
+            while (j < cols.size() && cols[j] - cols[j - 1] <= gap + 1) ++j;
+            const int len = cols[j - 1] - cols[i] + 1;
+            for (size_t k = i; k < j; ++k) local[cols[k]] = slot + (cols[k] - cols[i]);
             T.runs.push_back(cols[i]);
-            T.runs.push_back((int32_t)i);
-            T.runs.push_back((int32_t)(j - i));
+            T.runs.push_back(slot);
+            T.runs.push_back(len);
             T.runs.push_back(0);
+            slot += len;
             i = j;
         }
+        for (int32_t q = P.rowptr[r0]; q < P.rowptr[r1]; ++q) T.lcol[q] = (uint16_t)local[P.col[q]];
         T.rptr.push_back((int32_t)(T.runs.size() / 4));
-        T.ucnt.push_back((int32_t)cols.size());
+        T.ucnt.push_back((int32_t)copied);
         T.trow.push_back((int32_t)r1);
-        T.umax = std::max<int>(T.umax, (int)cols.size());
+        T.umax = std::max<int>(T.umax, copied);
         T.nnzmax = std::max<int>(T.nnzmax, P.rowptr[r1] - P.rowptr[r0]);
         r0 = r1;
         ++t;
