@@ -43,6 +43,7 @@ extern "C" {
 
 typedef struct sigsdp_plan sigsdp_plan;     /* graph plan: Z-independent (reused across the binary search) */
 typedef struct sigsdp_solver sigsdp_solver; /* MMW state for one (plan, Z, D, eta, dtype) */
+typedef struct sigsdp_batch sigsdp_batch;   /* many independent small instances, one thread block each */
 
 const char* sigsdp_last_error(void);
 int sigsdp_version(void);
@@ -188,6 +189,17 @@ int sigsdp_round_greedy(int64_t n, int Z,
                         int32_t* z_vec_host, int64_t* remainder);
 int sigsdp_round_conflicts(const sigsdp_plan* plan, const int32_t* z_dev, double* I_dev_or_null,
                            int64_t counts_host[2], void* stream);
+
+/* ------------------------------------------------------------------ batch ----
+ * Monte-Carlo sweeps (sim_script/journal_version/sim_all_bler.py:30-40 run `for seed in
+ * range(REPEAT)` sequentially): many independent instances advanced by ONE launch, one
+ * thread block per instance running the same phases with block-level barriers, no
+ * communication.  The solvers stay owned by the caller (fetch results through the
+ * sigsdp_solver_get_* calls); they must share the device, the dtype and the lane width.
+ * Omega is always generated on device (instance i uses a stream derived from `seed` and i). */
+int sigsdp_batch_create(sigsdp_solver* const* solvers, int count, sigsdp_batch** out);
+void sigsdp_batch_destroy(sigsdp_batch* b);
+int sigsdp_batch_iterate(sigsdp_batch* b, int n_iters, uint64_t seed, void* stream);
 
 #ifdef __cplusplus
 }

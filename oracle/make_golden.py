@@ -164,9 +164,30 @@ def run_case(ref, c):
     return out
 
 
+def run_binary_search_case(ref):
+    """Whole driver chain (binary_search_relaxation.run -> mmw.run_with_state -> rounding) of
+    the unmodified reference on the n=75 topology, np.random.seed(77): probe sequence
+    [left, right, mid, Z, remainder], bounds, final colouring."""
+    import contextlib
+    import io
+    e = ref.env(cell_size=5, sta_density_per_1m2=75e-4, seed=0)
+    state = e.generate_S_Q_hmax()
+    bs = ref.binary_search_relaxation()
+    alg = ref.mmw(nit=40, eta=0.04)
+    bs.feasibility_check_alg = alg
+    np.random.seed(77)
+    with contextlib.redirect_stdout(io.StringIO()):
+        z_vec, Z, rem = bs.run(state)
+    np.savez_compressed(os.path.join(GOLD, "bs_n75.npz"), z_vec=z_vec, Z=Z, rem=rem,
+                        per_it=bs.LOGGED_NP_DATA["bs_search_per_it"][:, 3:8],
+                        bounds=bs.LOGGED_NP_DATA["bs_set_bounds"][0, 3:5], seed=77, nit=40, eta=0.04)
+    print("bs_n75: Z=%d rem=%d probes=%d" % (Z, rem, bs.LOGGED_NP_DATA["bs_search_per_it"].shape[0]))
+
+
 def main():
     ref = load_reference()
     os.makedirs(GOLD, exist_ok=True)
+    run_binary_search_case(ref)
     for c in CASES:
         out = run_case(ref, c)
         path = os.path.join(GOLD, c["name"] + ".npz")

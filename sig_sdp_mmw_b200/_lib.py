@@ -62,6 +62,8 @@ def load():
         "sigsdp_solver_get_matrix": [vp, f64p],
         "sigsdp_plan_pattern": [vp, i32p, i32p],
         "sigsdp_debug_normals": [C.c_uint64, C.c_int64, C.c_int, C.c_int, C.c_int, f64p],
+        "sigsdp_batch_create": [C.POINTER(vp), C.c_int, C.POINTER(vp)],
+        "sigsdp_batch_iterate": [vp, C.c_int, C.c_uint64, vp],
         "sigsdp_round_project": [vp, vp, C.c_int, vp, C.c_int, vp, vp, vp],
         "sigsdp_round_greedy": [C.c_int64, C.c_int, i32p, i32p, f64p, i32p, i32p, f64p, f64p, i32p, i32p, i32p, i64p],
         "sigsdp_round_conflicts": [vp, vp, vp, i64p, vp],
@@ -74,6 +76,8 @@ def load():
     lib.sigsdp_plan_destroy.restype = None
     lib.sigsdp_solver_destroy.argtypes = [vp]
     lib.sigsdp_solver_destroy.restype = None
+    lib.sigsdp_batch_destroy.argtypes = [vp]
+    lib.sigsdp_batch_destroy.restype = None
     _lib = lib
     return lib
 
@@ -243,6 +247,27 @@ class Solver:
         v = C.c_int64()
         check(load().sigsdp_solver_total_terms(self.handle, C.byref(v)))
         return int(v.value)
+
+
+class Batch:
+    """Independent instances advanced together, one thread block each (sigsdp_batch_*)."""
+
+    def __init__(self, solvers):
+        self.solvers = list(solvers)
+        arr = (C.c_void_p * len(self.solvers))(*[s.handle for s in self.solvers])
+        self.handle = C.c_void_p()
+        check(load().sigsdp_batch_create(arr, len(self.solvers), C.byref(self.handle)))
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                load().sigsdp_batch_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def iterate(self, n_iters, seed=0, stream=None):
+        check(load().sigsdp_batch_iterate(self.handle, int(n_iters), int(seed), stream))
 
 
 def debug_normals(seed, it, n, D, dtype=F64):

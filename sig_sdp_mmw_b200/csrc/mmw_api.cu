@@ -98,6 +98,13 @@ struct sigsdp_solver {
     unsigned long long* gkey = nullptr;
 };
 
+struct sigsdp_batch {
+    std::vector<sigsdp_solver*> solvers;
+    int device = 0, dtype = 0, G = 0;
+    size_t smem = 0;
+    void* d_probs = nullptr;
+};
+
 // ---------------------------------------------------------------------------
 // kernels
 template <typename T, int G>
@@ -149,6 +156,26 @@ __global__ void __launch_bounds__(NT, 2) k_gram(Prob<T> P) {
         phase_gram<T, G>(P, StepTeam(), sh);
     }
 }
+// batch: one thread block per independent instance, __syncthreads as the team barrier
+template <typename T, int G>
+__global__ void __launch_bounds__(NT, 2) k_batch(const Prob<T>* probs, int n_iters, unsigned long long seed) {
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    __shared__ Prob<T> Ps;
+    {
+        const int* src = reinterpret_cast<const int*>(probs + blockIdx.x);
+        int* dst = reinterpret_cast<int*>(&Ps);
+        for (int i = threadIdx.x; i < (int)(sizeof(Prob<T>) / sizeof(int)); i += NT) dst[i] = src[i];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            Ps.omega = nullptr;
+            Ps.seed = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(blockIdx.x + 1);
+        }
+        __syncthreads();
+    }
+    CtaTeam team;
+    run_iterations<T, G>(Ps, team, n_iters, dyn_smem);
+}
+
 // stepwise controller: single-thread kernels that publish decisions for the host
 __global__ void k_begin(Ctrl* ctrl) {
     TaylorState ts;
@@ -1164,6 +1191,78 @@ int sigsdp_round_conflicts(const sigsdp_plan* plan, const int32_t* z_dev, double
     counts_host[0] = (int64_t)hcounts[0];
     counts_host[1] = (int64_t)hcounts[1];
     return SIGSDP_OK;
+}
+
+
+// ---- batch -------------------------------------------------------------------
+extern "C++" {
+template <typename T, int G>
+static int launch_batch(sigsdp_batch* b, int n_iters, unsigned long long seed, cudaStream_t st) {
+    if (b->smem > 48 * 1024)
+        CK(cudaFuncSetAttribute(k_batch<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem));
+    k_batch<T, G><<<dim3((unsigned)b->solvers.size()), dim3(NT), b->smem, st>>>(
+        reinterpret_cast<const Prob<T>*>(b->d_probs), n_iters, seed);
+    CK(cudaGetLastError());
+    return SIGSDP_OK;
+}
+}
+
+int sigsdp_batch_create(sigsdp_solver* const* solvers, int count, sigsdp_batch** out) {
+    if (!out) return fail(SIGSDP_EINVAL, "out is null");
+    *out = nullptr;
+    if (!solvers || count < 1) return fail(SIGSDP_EINVAL, "empty batch");
+    sigsdp_batch* b = new sigsdp_batch();
+    b->device = solvers[0]->plan->device;
+    b->dtype = solvers[0]->dtype;
+    b->G = solvers[0]->G;
+    for (int i = 0; i < count; ++i) {
+        sigsdp_solver* s = solvers[i];
+        if (!s || s->plan->device != b->device || s->dtype != b->dtype || s->G != b->G) {
+            delete b;
+            return fail(SIGSDP_EINVAL, "batched solvers must share the device, the dtype and the sketch width class");
+        }
+        b->smem = std::max(b->smem, s->smem);
+        b->solvers.push_back(s);
+    }
+    cudaSetDevice(b->device);
+    const size_t psz = b->dtype == SIGSDP_F64 ? sizeof(Prob<double>) : sizeof(Prob<float>);
+    std::vector<unsigned char> host(psz * count);
+    for (int i = 0; i < count; ++i)
+        std::memcpy(host.data() + psz * i,
+                    b->dtype == SIGSDP_F64 ? (const void*)&solvers[i]->p64 : (const void*)&solvers[i]->p32, psz);
+    cudaError_t e = cudaMalloc(&b->d_probs, host.size());
+    if (e == cudaSuccess) e = cudaMemcpy(b->d_probs, host.data(), host.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        if (b->d_probs) cudaFree(b->d_probs);
+        delete b;
+        return fail(SIGSDP_ECUDA, cudaGetErrorString(e));
+    }
+    *out = b;
+    return SIGSDP_OK;
+}
+
+void sigsdp_batch_destroy(sigsdp_batch* b) {
+    if (!b) return;
+    cudaSetDevice(b->device);
+    if (b->d_probs) cudaFree(b->d_probs);
+    delete b;
+}
+
+int sigsdp_batch_iterate(sigsdp_batch* b, int n_iters, uint64_t seed, void* stream) {
+    if (!b) return fail(SIGSDP_EINVAL, "null batch");
+    if (n_iters < 0) return fail(SIGSDP_EINVAL, "n_iters < 0");
+    if (n_iters == 0) return SIGSDP_OK;
+    CK(cudaSetDevice(b->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = SIGSDP_OK;
+    if (b->dtype == SIGSDP_F64) {
+        FOR_G(b->G, rc = (launch_batch<double, G>(b, n_iters, seed, st)));
+    } else {
+        FOR_G(b->G, rc = (launch_batch<float, G>(b, n_iters, seed, st)));
+    }
+    if (rc == SIGSDP_OK)
+        for (sigsdp_solver* s : b->solvers) s->iters_done += n_iters;
+    return rc;
 }
 
 int sigsdp_round_greedy(int64_t n, int Z, const int32_t* Sp, const int32_t* Si, const double* Sx, const int32_t* Qp,
