@@ -308,7 +308,12 @@ def run_ours(args):
                          "edge_dual_loss_omega_bytes_per_iter": rest_b},
             "e2e": {"value": world * args.steps / (e2e_ms_max * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps,
                     "d2h_bytes_per_step": d2h / args.steps,
-                    "what": "mmw(nit=K).run_with_state(state): plan build, upload, K iterations, Lanczos factor, download"},
+                    "what": "mmw(nit=K).run_with_state(state): plan build, upload, K iterations, Lanczos factor, download",
+                    "breakdown_ms": {"state_process": float(alg.LOGGED_NP_DATA["mmw_state_process"][-1, 5]) / 1e3,
+                                     "iterations_device": float(alg.LOGGED_NP_DATA["mmw_per_it"][:, 5].sum()) / 1e3,
+                                     "final_factor": float(alg.LOGGED_NP_DATA["mmw_xavg"][-1, 5]) / 1e3,
+                                     "total": e2e_s * 1e3,
+                                     "lanczos": getattr(alg, "last_eig_info", None)}},
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu:

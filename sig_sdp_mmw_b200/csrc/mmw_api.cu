@@ -1,5 +1,6 @@
 // C ABI of libsigsdp_mmw.so: handles, device workspace, kernel launches, host fetches.
 // See include/sigsdp_mmw.h for the contract and the reference lines each entry replaces.
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -27,6 +28,18 @@ static int fail(int code, const std::string& msg) {
         if (e_ != cudaSuccess)                                                                     \
             return fail(SIGSDP_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));         \
     } while (0)
+
+struct ApiTimer {
+    bool on = getenv("SIGSDP_PLAN_TIMING") != nullptr;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    void lap(const char* what) {
+        if (!on) return;
+        cudaDeviceSynchronize();
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[api ] %-24s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
 
 struct DevArena {
     std::vector<void*> ptrs;
@@ -489,11 +502,13 @@ int sigsdp_plan_create(int64_t n, const int32_t* Sp, const int32_t* Si, const do
     *out = nullptr;
     sigsdp_plan* pl = new sigsdp_plan();
     std::string err;
+    ApiTimer tm;
     int rc = build_host_plan(n, Sp, Si, Sx, Qp, Qi, Qx, h_max, order, pl->h, err);
     if (rc != SIGSDP_OK) {
         delete pl;
         return fail(rc, err);
     }
+    tm.lap("host plan");
     pl->device = device;
     auto bail = [&](cudaError_t e, const char* what) {
         std::string m = std::string(what) + ": " + cudaGetErrorString(e);
@@ -540,6 +555,7 @@ int sigsdp_plan_create(int64_t n, const int32_t* Sp, const int32_t* Si, const do
     d.tnorm = tnorm;
     d.h_max = hm;
     d.perm = perm;
+    tm.lap("plan upload");
     // S^T without its diagonal / explicit zeros, caller numbering (rounding.py:56-60)
     {
         std::vector<int32_t> sp(n + 1, 0), si;
@@ -566,6 +582,7 @@ int sigsdp_plan_create(int64_t n, const int32_t* Sp, const int32_t* Si, const do
         if ((e = pl->mem.upload(&pl->d_aj, h.aj)) != cudaSuccess) return bail(e, "upload asso");
         if ((e = pl->mem.upload(&pl->d_hmax_caller, hc)) != cudaSuccess) return bail(e, "upload h_max");
     }
+    tm.lap("S^T build + upload");
     *out = pl;
     return SIGSDP_OK;
 }
@@ -631,6 +648,7 @@ static int solver_alloc(sigsdp_solver* s) {
     const HostPlan& h = pl->h;
     const int64_t n = h.n, E = h.E_g + h.E_a;
     Prob<T>& P = prob_of<T>(s);
+    ApiTimer tm;
     P.g = pl->d;
     P.Z = s->Z;
     P.D = s->D;
@@ -679,6 +697,7 @@ static int solver_alloc(sigsdp_solver* s) {
     CK(s->mem.alloc(&P.hist_t, (size_t)HIST * 3));
     P.omega = nullptr;
     P.seed = 0;
+    tm.lap("solver alloc");
     // row tiles for the staged (shared-memory) kernels: tiles of up to `max_rows` consecutive
     // rows, capped so that a tile's distinct sketch rows, its L_accu slice and its local
     // column indices fit the per-block shared-memory budget (two blocks per SM)
@@ -729,6 +748,7 @@ static int solver_alloc(sigsdp_solver* s) {
             }
         }
     }
+    tm.lap("tiles build + upload");
     // launch geometry: persistent grid, one tile per block iteration
     int occ = 0, rc = SIGSDP_OK;
     FOR_G(s->G, rc = (occupancy_fused<T, G>(&occ, s->smem)));

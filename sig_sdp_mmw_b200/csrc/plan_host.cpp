@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <chrono>
 #include <cstdlib>
 #include <numeric>
 #include <queue>
@@ -97,9 +98,23 @@ void locality_order(const HostPlan& P, int cluster, std::vector<int32_t>& perm) 
 
 }  // namespace
 
+namespace {
+struct StageTimer {
+    bool on = getenv("SIGSDP_PLAN_TIMING") != nullptr;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    void lap(const char* what) {
+        if (!on) return;
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[plan] %-24s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+}  // namespace
+
 int build_host_plan(int64_t n, const int32_t* Sp, const int32_t* Si, const double* Sx,
                     const int32_t* Qp, const int32_t* Qi, const double* Qx, const double* h_max,
                     int order, HostPlan& P, std::string& err) {
+    StageTimer tm;
     if (n <= 1 || n > (int64_t)1 << 30) {
         err = "n must be in [2, 2^30]";
         return SIGSDP_EINVAL;
@@ -129,26 +144,35 @@ int build_host_plan(int64_t n, const int32_t* Sp, const int32_t* Si, const doubl
             }
         }
 
+    tm.lap("validate");
     // ---- T = S^T with association pairs and the diagonal zeroed (mmw.py:28-33)
     std::vector<int32_t> Tp(n + 1, 0), Ti;
     std::vector<double> Tx;
     {
-        for (int64_t j = 0; j < n; ++j)
+        // S entry (j, i) becomes T[i][j] unless i == j, the value is zero, or Q[i][j] != 0.
+        // Q is symmetric (checked above), so Q[i][j] != 0 <=> Q[j][i] != 0: merge S row j with
+        // Q row j (both sorted) instead of searching Q row i.
+        std::vector<uint8_t> keep(Sp[n], 0);
+        for (int64_t j = 0; j < n; ++j) {
+            int32_t qq = Qp[j];
+            const int32_t qe = Qp[j + 1];
             for (int32_t q = Sp[j]; q < Sp[j + 1]; ++q) {
-                int32_t i = Si[q];
+                const int32_t i = Si[q];
                 if (Sx[q] == 0.0 || i == j) continue;
-                if (csr_at(Qp, Qi, Qx, i, (int32_t)j) != 0.0) continue;
+                while (qq < qe && Qi[qq] < i) ++qq;
+                if (qq < qe && Qi[qq] == i && Qx[qq] != 0.0) continue;
+                keep[q] = 1;
                 Tp[i + 1]++;
             }
+        }
         for (int64_t i = 0; i < n; ++i) Tp[i + 1] += Tp[i];
         Ti.resize(Tp[n]);
         Tx.resize(Tp[n]);
         std::vector<int32_t> fill(Tp.begin(), Tp.end() - 1);
         for (int64_t j = 0; j < n; ++j)
             for (int32_t q = Sp[j]; q < Sp[j + 1]; ++q) {
-                int32_t i = Si[q];
-                if (Sx[q] == 0.0 || i == j) continue;
-                if (csr_at(Qp, Qi, Qx, i, (int32_t)j) != 0.0) continue;
+                if (!keep[q]) continue;
+                const int32_t i = Si[q];
                 Ti[fill[i]] = (int32_t)j;
                 Tx[fill[i]] = Sx[q];
                 fill[i]++;
@@ -171,6 +195,7 @@ int build_host_plan(int64_t n, const int32_t* Sp, const int32_t* Si, const doubl
             }
     }
 
+    tm.lap("T and T^T");
     // ---- S_sum = T 1 and sqrt((T o T) 1) (mmw.py:34-39)
     std::vector<double> S_sum(n), tnorm(n);
     for (int64_t i = 0; i < n; ++i) {
@@ -235,6 +260,7 @@ int build_host_plan(int64_t n, const int32_t* Sp, const int32_t* Si, const doubl
     P.E_a = a_ut[n];
     P.nnz = (int64_t)ents.size();
 
+    tm.lap("union pattern");
     // ---- edge ids in the reference's order (row-major upper triangle, mmw.py:56-57)
     std::vector<int32_t> col(P.nnz), eid(P.nnz);
     std::vector<double> tfwd(P.nnz), tbwd(P.nnz);
@@ -259,19 +285,23 @@ int build_host_plan(int64_t n, const int32_t* Sp, const int32_t* Si, const doubl
             }
         }
     }
-    for (int64_t i = 0; i < n; ++i)
-        for (int32_t q = rowptr[i]; q < rowptr[i + 1]; ++q) {
-            int32_t j = col[q];
-            if (j >= i) continue;
-            const int32_t* b = col.data() + rowptr[j];
-            const int32_t* e = col.data() + rowptr[j + 1];
-            const int32_t* it = std::lower_bound(b, e, (int32_t)i);
-            if (it == e || *it != i) {
-                err = "internal: asymmetric union pattern";
-                return SIGSDP_EINVAL;
+    {
+        // the pattern is symmetric: scanning the upper entries (j, i), j ascending, visits every
+        // row i's lower entries in ascending column order, so a cursor per row finds the mirror
+        std::vector<int32_t> cursor(rowptr.begin(), rowptr.end() - 1);
+        for (int64_t j = 0; j < n; ++j)
+            for (int32_t q = rowptr[j]; q < rowptr[j + 1]; ++q) {
+                const int32_t i = col[q];
+                if (i <= j) continue;
+                int32_t& c = cursor[i];
+                if (c >= rowptr[i + 1] || col[c] != j) {
+                    err = "internal: asymmetric union pattern";
+                    return SIGSDP_EINVAL;
+                }
+                eid[c] = eid[q];
+                ++c;
             }
-            eid[q] = eid[it - col.data()];
-        }
+    }
 
     P.rowptr.swap(rowptr);
     P.col.swap(col);
@@ -286,6 +316,7 @@ int build_host_plan(int64_t n, const int32_t* Sp, const int32_t* Si, const doubl
     std::iota(P.perm.begin(), P.perm.end(), 0);
     std::iota(P.iperm.begin(), P.iperm.end(), 0);
 
+    tm.lap("edge ids");
     if (order != 0) {
         // renumber nodes for locality; edge ids and edge lists keep the caller's order
         std::vector<int32_t> perm;
@@ -294,15 +325,16 @@ int build_host_plan(int64_t n, const int32_t* Sp, const int32_t* Si, const doubl
         for (int64_t k = 0; k < n; ++k) iperm[perm[k]] = (int32_t)k;
         std::vector<int32_t> rp(n + 1, 0), c2(P.nnz), e2(P.nnz);
         std::vector<double> f2(P.nnz), b2(P.nnz);
-        std::vector<int32_t> ord;
+        std::vector<uint64_t> ord;
         int32_t w = 0;
         for (int64_t k = 0; k < n; ++k) {
             int32_t o = perm[k];
             int32_t b = P.rowptr[o], e = P.rowptr[o + 1];
             ord.resize(e - b);
-            std::iota(ord.begin(), ord.end(), b);
-            std::sort(ord.begin(), ord.end(), [&](int32_t x, int32_t y) { return iperm[P.col[x]] < iperm[P.col[y]]; });
-            for (int32_t q : ord) {
+            for (int32_t q = b; q < e; ++q) ord[q - b] = ((uint64_t)(uint32_t)iperm[P.col[q]] << 32) | (uint32_t)q;
+            std::sort(ord.begin(), ord.end());
+            for (uint64_t key : ord) {
+                const int32_t q = (int32_t)(key & 0xffffffffu);
                 c2[w] = iperm[P.col[q]];
                 e2[w] = P.eid[q];
                 f2[w] = P.tfwd[q];
@@ -327,6 +359,7 @@ int build_host_plan(int64_t n, const int32_t* Sp, const int32_t* Si, const doubl
         P.perm.swap(perm);
         P.iperm.swap(iperm);
     }
+    tm.lap("locality renumbering");
     P.dpos.assign(n, -1);
     P.apos.assign(P.E_a, -1);
     for (int64_t k = 0; k < n; ++k)

@@ -1,8 +1,11 @@
 """Eigen-solvers over the library's symmetric mat-vec (sigsdp_solver_symv), replacing the
 reference's ARPACK calls: eigsh(k=1, which='SA') for the gap (mmw.py:115) and svds(k=r)
 for the final factor (mmw.py:215).  Thick-restart Lanczos with full (CGS2)
-re-orthogonalisation; all vectors stay on the device (torch fp64 tensors, cuBLAS GEMV /
-GEMM for the dense algebra), one host synchronisation per restart."""
+re-orthogonalisation.  All n-sized vectors stay on the device (torch fp64 tensors; cuBLAS
+GEMV / GEMM for the dense algebra); the Lanczos basis has a fixed shape so every step is the
+same short sequence of launches; the small projected eigenproblem (ncv x ncv) is solved on
+the host once per restart, which is the only synchronisation."""
+import numpy as np
 import torch
 
 
@@ -26,7 +29,7 @@ def eig_dense(matmat, n, k, which, device):
     return lam[idx], V[:, idx]
 
 
-def thick_restart_lanczos(matmat, n, k, which, v0, ncv=None, tol=1e-13, max_restarts=500):
+def thick_restart_lanczos(matmat, n, k, which, v0, ncv=None, tol=1e-12, max_restarts=500):
     """k extreme eigenpairs of a symmetric operator.
 
     matmat(X): X is (nvec, n) row-stacked vectors -> (nvec, n) of M x.
@@ -35,57 +38,70 @@ def thick_restart_lanczos(matmat, n, k, which, v0, ncv=None, tol=1e-13, max_rest
     Returns (lam (k,), V (n, k), info dict)."""
     dev = v0.device
     if ncv is None:
-        ncv = max(2 * k + 20, 40)
+        ncv = max(2 * k + 40, 48)
     m = int(min(ncv, n))
     if m >= n or k >= m - 1:
         lam, V = eig_dense(matmat, n, k, which, dev)
         return lam, V, dict(restarts=0, matvecs=n, dense=True)
-    Q = torch.zeros((m + 1, n), dtype=torch.float64, device=dev)   # basis, one vector per row
-    Tm = torch.zeros((m, m), dtype=torch.float64, device=dev)
+    # basis: one vector per row; rows beyond the current step are kept at zero so the
+    # orthogonalisation can always use the whole array (fixed shapes, no slicing)
+    Q = torch.zeros((m + 1, n), dtype=torch.float64, device=dev)
+    Qt = Q.T
+    al = torch.zeros(m, dtype=torch.float64, device=dev)
+    be = torch.zeros(m, dtype=torch.float64, device=dev)
     Q[0] = v0 / torch.linalg.norm(v0)
     nkeep = 0
     matvecs = 0
-    theta = S = None
+    arrow = None
+    theta_keep = None
     for restart in range(max_restarts):
         for j in range(nkeep, m):
             w = matmat(Q[j:j + 1])[0]
-            matvecs += 1
-            basis = Q[:j + 1]
-            h = basis @ w
-            w = w - basis.T @ h
-            h2 = basis @ w                       # second Gram-Schmidt pass
-            w = w - basis.T @ h2
-            Tm[j, j] = h[j] + h2[j]
+            h = torch.mv(Q, w)
+            w = torch.addmv(w, Qt, h, alpha=-1.0)
+            h2 = torch.mv(Q, w)                       # second Gram-Schmidt pass
+            w = torch.addmv(w, Qt, h2, alpha=-1.0)
+            al[j] = h[j] + h2[j]
             beta = torch.linalg.norm(w)
+            be[j] = beta
             Q[j + 1] = w / beta
+        matvecs += m - nkeep
+        # projected matrix on the host: diag(theta_keep) with its arrow row, then the tridiagonal tail
+        al_h, be_h = al.cpu().numpy(), be.cpu().numpy()
+        Tm = np.zeros((m, m))
+        if nkeep:
+            Tm[np.arange(nkeep), np.arange(nkeep)] = theta_keep
+            Tm[nkeep, :nkeep] = arrow
+            Tm[:nkeep, nkeep] = arrow
+        for j in range(nkeep, m):
+            Tm[j, j] = al_h[j]
             if j + 1 < m:
-                Tm[j, j + 1] = beta
-                Tm[j + 1, j] = beta
-        theta, S = torch.linalg.eigh(Tm)
-        if which == "LM":
-            order = torch.argsort(theta.abs(), descending=True)
-        else:
-            order = torch.arange(m, device=dev)
+                Tm[j, j + 1] = Tm[j + 1, j] = be_h[j]
+        theta, S = np.linalg.eigh(Tm)
+        order = np.argsort(-np.abs(theta)) if which == "LM" else np.arange(m)
         want = order[:k]
-        resid = (beta * S[m - 1, want]).abs()
-        scale = theta.abs().max()
-        if bool((resid <= tol * scale).all()):
+        beta_m = be_h[m - 1]
+        resid = np.abs(beta_m * S[m - 1, want])
+        scale = np.abs(theta).max()
+        if np.all(resid <= tol * scale):
             break
         # thick restart: keep the wanted Ritz vectors plus a buffer of the next best
         nk = int(min(k + max(8, (m - k) // 3), m - 2))
         keep = order[:nk]
-        Q[:nk] = S[:, keep].T @ Q[:m]
-        Q[nk] = Q[m]
-        arrow = beta * S[m - 1, keep]
-        Tm.zero_()
-        Tm[torch.arange(nk), torch.arange(nk)] = theta[keep]
-        Tm[nk, :nk] = arrow
-        Tm[:nk, nk] = arrow
+        Sk = torch.from_numpy(np.ascontiguousarray(S[:, keep].T)).to(dev)
+        last = Q[m].clone()
+        Qnew = Sk @ Q[:m]
+        Q.zero_()
+        Q[:nk] = Qnew
+        Q[nk] = last
+        theta_keep = theta[keep]
+        arrow = beta_m * S[m - 1, keep]
         nkeep = nk
-    lam = theta[want]
-    V = (S[:, want].T @ Q[:m]).T
+    Sw = torch.from_numpy(np.ascontiguousarray(S[:, want].T)).to(dev)
+    lam = torch.from_numpy(np.ascontiguousarray(theta[want])).to(dev)
+    V = (Sw @ Q[:m]).T
     if which == "LM":
         o = torch.argsort(lam.abs())
         lam, V = lam[o], V[:, o]
     return lam, V, dict(restarts=restart, matvecs=matvecs, dense=False,
-                        resid=float(resid.max()), scale=float(scale))
+                        resid=float(resid.max()), scale=float(scale), ncv=m)
