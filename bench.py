@@ -258,6 +258,9 @@ def run_ours(args):
         return
 
     # ---- end to end through the drop-in object, host buffers in, host factor out
+    # one untimed call warms the process (cuBLAS handle, allocator pools); the timed call uses a
+    # fresh solver object, so its graph plan is built from the host matrices again
+    mmw(nit=3, eta=ETA, rank_radio=rr, dtype=dtype, omega="device", device=local, order=args.order, seed=1).run_with_state(0, Z, state)
     alg = mmw(nit=args.steps, eta=ETA, rank_radio=rr, dtype=dtype, omega="device", device=local, order=args.order, seed=1)
     barrier()
     t0 = time.perf_counter()

@@ -162,6 +162,13 @@ int sigsdp_solver_xavg_matrix(sigsdp_solver* s, double scale, void* stream);
 int sigsdp_solver_gap_prepare(sigsdp_solver* s, double* e_max_host, void* stream);
 int sigsdp_solver_symv(sigsdp_solver* s, const double* x_dev, double* y_dev, int nvec, void* stream);
 int sigsdp_solver_get_matrix(sigsdp_solver* s, double* vals_host);
+/* Lanczos steps j0 .. j1-1 on the prepared matrix M with full re-orthogonalisation (classical
+ * Gram-Schmidt twice, fixed-order reductions): w = M q_j; w -= Q_j^T (Q_j w) twice;
+ * alpha[j] = <q_j, M q_j>; beta[j] = ||w||; q_{j+1} = w / beta[j].  Q_dev is (m+1) x n
+ * row-major in the internal numbering, rows 0..j0 filled by the caller; alpha_dev / beta_dev
+ * are device arrays of length m.  Asynchronous on `stream`. */
+int sigsdp_solver_lanczos_steps(sigsdp_solver* s, double* Q_dev, int m, int j0, int j1, double* alpha_dev,
+                                double* beta_dev, void* stream);
 /* the symmetric union pattern in the internal numbering: rowptr (n+1), col (nnzL) */
 int sigsdp_plan_pattern(const sigsdp_plan* plan, int32_t* rowptr_host, int32_t* col_host);
 

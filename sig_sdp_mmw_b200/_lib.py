@@ -60,6 +60,7 @@ def load():
         "sigsdp_solver_gap_prepare": [vp, f64p, vp],
         "sigsdp_solver_symv": [vp, vp, vp, C.c_int, vp],
         "sigsdp_solver_get_matrix": [vp, f64p],
+        "sigsdp_solver_lanczos_steps": [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp],
         "sigsdp_plan_pattern": [vp, i32p, i32p],
         "sigsdp_debug_normals": [C.c_uint64, C.c_int64, C.c_int, C.c_int, C.c_int, f64p],
         "sigsdp_batch_create": [C.POINTER(vp), C.c_int, C.POINTER(vp)],
@@ -231,6 +232,9 @@ class Solver:
 
     def symv(self, x_ptr, y_ptr, nvec=1, stream=None):
         check(load().sigsdp_solver_symv(self.handle, x_ptr, y_ptr, int(nvec), stream))
+
+    def lanczos_steps(self, Q_ptr, m, j0, j1, al_ptr, be_ptr, stream=None):
+        check(load().sigsdp_solver_lanczos_steps(self.handle, Q_ptr, int(m), int(j0), int(j1), al_ptr, be_ptr, stream))
 
     def matrix_values(self):
         v = np.empty(self.plan.nnz)

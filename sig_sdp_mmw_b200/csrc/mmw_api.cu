@@ -41,12 +41,28 @@ struct ApiTimer {
     }
 };
 
+// Device allocations go through the stream-ordered allocator with a pool that keeps freed
+// memory (release threshold = max): the binary search creates and destroys a solver per
+// probe, and plain cudaMalloc after cudaFree re-maps memory every time (hundreds of ms at
+// n = 1e5).  Allocation is ordered on the legacy default stream and followed by a
+// synchronising copy or memset, frees are preceded by a device synchronisation.
+static void pool_setup(int device) {
+    static bool done[64] = {false};
+    if (device < 0 || device >= 64 || done[device]) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    done[device] = true;
+}
+
 struct DevArena {
     std::vector<void*> ptrs;
     template <typename U>
     cudaError_t alloc(U** p, size_t count) {
         void* q = nullptr;
-        cudaError_t e = cudaMalloc(&q, (count ? count : 1) * sizeof(U));
+        cudaError_t e = cudaMallocAsync(&q, (count ? count : 1) * sizeof(U), (cudaStream_t)0);
         if (e == cudaSuccess) ptrs.push_back(q);
         *p = (U*)q;
         return e;
@@ -59,7 +75,9 @@ struct DevArena {
         return e;
     }
     void release() {
-        for (void* p : ptrs) cudaFree(p);
+        if (ptrs.empty()) return;
+        cudaDeviceSynchronize();
+        for (void* p : ptrs) cudaFreeAsync(p, (cudaStream_t)0);
         ptrs.clear();
     }
 };
@@ -109,6 +127,9 @@ struct sigsdp_solver {
     double* rtmp = nullptr;      // n
     double* gscal = nullptr;     // 8 scalars
     unsigned long long* gkey = nullptr;
+    // Lanczos step workspace (allocated on first use)
+    double *lz_w = nullptr, *lz_part = nullptr, *lz_h = nullptr, *lz_partn = nullptr;
+    int lz_rows = 0;
 };
 
 struct sigsdp_batch {
@@ -321,6 +342,79 @@ __global__ void k_symv(PlanDev g, const double* Mval, const double* x, double* y
         }
     }
 }
+
+// ---------------------------------------------------------------------------
+// One Lanczos step with full re-orthogonalisation (classical Gram-Schmidt, twice), native:
+//   w = M q_j;  h = Q_j w;  w -= Q_j^T h;  h2 = Q_j w;  w -= Q_j^T h2;  alpha_j = h_j + h2_j;
+//   beta_j = ||w||;  q_{j+1} = w / beta_j
+// Q is (m+1) x n row-major (one basis vector per row), only rows 0..j are read.  Reductions
+// are two-stage with a fixed order (bit-reproducible).
+constexpr int LZ_SLICE = 512;   // elements of w per block in the dot kernel
+__global__ void k_lz_dot(const double* Q, int n, int nrows, const double* w, double* part, int ldp) {
+    __shared__ double ws[LZ_SLICE];
+    const int i0 = blockIdx.x * LZ_SLICE;
+    const int cnt = min(LZ_SLICE, n - i0);
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) ws[i] = w[i0 + i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int r = wrp; r < nrows; r += nw) {
+        const double* q = Q + (size_t)r * n + i0;
+        double acc = 0.0;
+        for (int i = lane; i < cnt; i += 32) acc += q[i] * ws[i];
+        acc = warp_sum(acc);
+        if (lane == 0) part[(size_t)blockIdx.x * ldp + r] = acc;
+    }
+}
+__global__ void k_lz_reduce(const double* part, int nblk, int ldp, int nrows, double* h, double* alpha, int j, int second) {
+    for (int r = threadIdx.x; r < nrows; r += blockDim.x) {
+        double acc = 0.0;
+        for (int b = 0; b < nblk; ++b) acc += part[(size_t)b * ldp + r];
+        h[r] = acc;
+        if (r == j) *alpha = second ? *alpha + acc : acc;
+    }
+}
+__global__ void k_lz_sub(const double* Q, int n, int nrows, const double* h, double* w, double* partn) {
+    extern __shared__ double hs[];
+    __shared__ double sh[32 + 1];
+    for (int r = threadIdx.x; r < nrows; r += blockDim.x) hs[r] = h[r];
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double v = 0.0;
+    if (i < n) {
+        double acc = 0.0;
+        for (int r = 0; r < nrows; ++r) acc += hs[r] * Q[(size_t)r * n + i];
+        v = w[i] - acc;
+        w[i] = v;
+    }
+    if (partn) {   // second pass: ||w||^2 partials
+        double t = warp_sum(v * v);
+        if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = t;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            t = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.0;
+            t = warp_sum(t);
+            if (threadIdx.x == 0) partn[blockIdx.x] = t;
+        }
+    }
+}
+__global__ void k_lz_finish(const double* w, int n, const double* partn, int nblk, double* qnext, const double* alpha,
+                            double* al, double* be, int j) {
+    __shared__ double s_beta;
+    if (threadIdx.x < 32) {
+        double t = 0.0;
+        for (int b = threadIdx.x; b < nblk; b += 32) t += partn[b];
+        t = warp_sum(t);
+        if (threadIdx.x == 0) s_beta = sqrt(t);
+    }
+    __syncthreads();
+    const double beta = s_beta;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) qnext[i] = w[i] / beta;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        al[j] = *alpha;
+        be[j] = beta;
+    }
+}
 // running means at the start of iteration i (N = i + 1): X~ = (X_avgd + X)/N, Y~ likewise
 __global__ void k_gap_rowsum(SolverView v, double N, double* rtmp) {
     const PlanDev& g = v.g;
@@ -522,6 +616,7 @@ int sigsdp_plan_create(int64_t n, const int32_t* Sp, const int32_t* Si, const do
         return SIGSDP_OK;
     }
     if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(e, "cudaSetDevice");
+    pool_setup(device);
     cudaDeviceProp prop;
     if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail(e, "cudaGetDeviceProperties");
     pl->num_sms = prop.multiProcessorCount;
@@ -1114,6 +1209,7 @@ static int ensure_scratch(sigsdp_solver* s) {
     CK(s->mem.alloc(&s->rtmp, s->plan->h.n));
     CK(s->mem.alloc(&s->gscal, 8));
     CK(s->mem.alloc(&s->gkey, 1));
+    CK(cudaStreamSynchronize((cudaStream_t)0));   // allocations are ordered on the default stream
     return SIGSDP_OK;
 }
 
@@ -1154,6 +1250,42 @@ int sigsdp_solver_symv(sigsdp_solver* s, const double* x_dev, double* y_dev, int
     if (!s->Mval) return fail(SIGSDP_ESTATE, "no matrix prepared (call xavg_matrix or gap_prepare first)");
     CK(cudaSetDevice(s->plan->device));
     k_symv<<<s->plan->num_sms * 8, 256, 0, (cudaStream_t)stream>>>(s->plan->d, s->Mval, x_dev, y_dev, nvec);
+    CK(cudaGetLastError());
+    return SIGSDP_OK;
+}
+
+
+int sigsdp_solver_lanczos_steps(sigsdp_solver* s, double* Q_dev, int m, int j0, int j1, double* alpha_dev,
+                                double* beta_dev, void* stream) {
+    if (!s || !Q_dev || !alpha_dev || !beta_dev || m < 1 || j0 < 0 || j1 > m || j0 > j1)
+        return fail(SIGSDP_EINVAL, "bad argument");
+    if (!s->Mval) return fail(SIGSDP_ESTATE, "no matrix prepared (call xavg_matrix or gap_prepare first)");
+    CK(cudaSetDevice(s->plan->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = (int)s->plan->h.n;
+    const int nb_dot = (n + LZ_SLICE - 1) / LZ_SLICE, nb_sub = (n + 255) / 256;
+    if (s->lz_rows < m + 1) {
+        CK(s->mem.alloc(&s->lz_w, n));
+        CK(s->mem.alloc(&s->lz_part, (size_t)nb_dot * (m + 1)));
+        CK(s->mem.alloc(&s->lz_h, m + 2));   // [m + 1] = the running alpha
+        CK(s->mem.alloc(&s->lz_partn, nb_sub));
+        CK(cudaStreamSynchronize((cudaStream_t)0));
+        s->lz_rows = m + 1;
+    }
+    double* alpha = s->lz_h + s->lz_rows;
+    const int ldp = s->lz_rows;
+    for (int j = j0; j < j1; ++j) {
+        const int nrows = j + 1;
+        k_symv<<<s->plan->num_sms * 8, 256, 0, st>>>(s->plan->d, s->Mval, Q_dev + (size_t)j * n, s->lz_w, 1);
+        for (int pass = 0; pass < 2; ++pass) {
+            k_lz_dot<<<nb_dot, 256, 0, st>>>(Q_dev, n, nrows, s->lz_w, s->lz_part, ldp);
+            k_lz_reduce<<<1, 128, 0, st>>>(s->lz_part, nb_dot, ldp, nrows, s->lz_h, alpha, j, pass);
+            k_lz_sub<<<nb_sub, 256, nrows * sizeof(double), st>>>(Q_dev, n, nrows, s->lz_h, s->lz_w,
+                                                                   pass ? s->lz_partn : nullptr);
+        }
+        k_lz_finish<<<nb_sub, 256, 0, st>>>(s->lz_w, n, s->lz_partn, nb_sub, Q_dev + (size_t)(j + 1) * n, alpha,
+                                            alpha_dev, beta_dev, j);
+    }
     CK(cudaGetLastError());
     return SIGSDP_OK;
 }

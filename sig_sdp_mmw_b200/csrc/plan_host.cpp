@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <numeric>
 #include <queue>
+#include <thread>
 
 #include "../../include/sigsdp_mmw.h"
 
@@ -55,6 +56,27 @@ struct Ent {
     int32_t kind;  // 0 diag, 1 gain, 2 asso
     double tf, tb;
 };
+
+// fn(begin, end) over [0, n) on the host's cores (contiguous chunks; fn must only touch
+// its own rows' outputs)
+template <class F>
+void parallel_rows(int64_t n, F fn) {
+    unsigned nt = std::thread::hardware_concurrency();
+    if (const char* e = getenv("SIGSDP_HOST_THREADS")) nt = (unsigned)std::max(1, atoi(e));
+    nt = std::max(1u, std::min(nt, 32u));
+    if (n < 4096 || nt == 1) {
+        fn(0, n);
+        return;
+    }
+    std::vector<std::thread> th;
+    const int64_t chunk = (n + nt - 1) / nt;
+    for (unsigned t = 0; t < nt; ++t) {
+        const int64_t b = t * chunk, e = std::min<int64_t>(n, b + chunk);
+        if (b >= e) break;
+        th.emplace_back([=] { fn(b, e); });
+    }
+    for (auto& x : th) x.join();
+}
 
 // Clustered BFS ordering: grow clusters of ~cluster nodes breadth-first, visiting the
 // graph cluster by cluster so that the rows of one CTA tile are a compact patch of
@@ -208,83 +230,104 @@ int build_host_plan(int64_t n, const int32_t* Sp, const int32_t* Si, const doubl
         tnorm[i] = std::sqrt(s2);
     }
 
-    // ---- union pattern: diag + gain (T + T^T != 0) + asso, per row, columns ascending
-    std::vector<int32_t> rowptr(n + 1, 0);
-    std::vector<Ent> ents;
-    ents.reserve((size_t)Tp[n] * 2 + n + Qp[n]);
-    std::vector<Ent> row;
-    std::vector<int64_t> g_ut(n + 1, 0), a_ut(n + 1, 0);
-    for (int64_t i = 0; i < n; ++i) {
+    // ---- union pattern: diag + gain (T + T^T != 0) + asso, per row, columns ascending.
+    // Each row is a 3-way merge of sorted lists; rows are independent, so they are built on
+    // all host cores: pass 1 counts, pass 2 fills.
+    auto build_row = [&](int64_t i, std::vector<Ent>& row) -> bool {
         row.clear();
-        row.push_back(Ent{(int32_t)i, 0, 0.0, 0.0});
-        // merge T row i (forward) and T^T row i (backward)
-        int32_t a = Tp[i], ae = Tp[i + 1], b = TTp[i], be = TTp[i + 1];
-        while (a < ae || b < be) {
-            int32_t ca = a < ae ? Ti[a] : INT32_MAX, cb = b < be ? TTi[b] : INT32_MAX;
-            Ent e{0, 1, 0.0, 0.0};
-            if (ca == cb) {
-                e.col = ca; e.tf = Tx[a]; e.tb = TTx[b]; ++a; ++b;
-            } else if (ca < cb) {
-                e.col = ca; e.tf = Tx[a]; ++a;
-            } else {
-                e.col = cb; e.tb = TTx[b]; ++b;
+        int32_t a = Tp[i], ae = Tp[i + 1], b = TTp[i], be = TTp[i + 1], q = Qp[i], qe = Qp[i + 1];
+        bool diag_done = false;
+        while (true) {
+            while (q < qe && Qx[q] == 0.0) ++q;
+            const int32_t ca = a < ae ? Ti[a] : INT32_MAX, cb = b < be ? TTi[b] : INT32_MAX;
+            const int32_t cq = q < qe ? Qi[q] : INT32_MAX, cd = diag_done ? INT32_MAX : (int32_t)i;
+            const int32_t c = std::min(std::min(ca, cb), std::min(cq, cd));
+            if (c == INT32_MAX) break;
+            int hits = 0;
+            Ent e{c, 1, 0.0, 0.0};
+            if (ca == c) { e.tf = Tx[a]; ++a; hits |= 1; }
+            if (cb == c) { e.tb = TTx[b]; ++b; hits |= 1; }
+            if (cq == c) { ++q; hits |= 2; e.kind = 2; }
+            if (cd == c) { diag_done = true; hits |= 4; e.kind = 0; }
+            if (hits == 1) {
+                if (e.tf + e.tb == 0.0) continue;   // eliminate_zeros on T + T^T (mmw.py:54)
+            } else if (hits != 2 && hits != 4) {
+                return false;   // a pair that is both gain and asso (or on the diagonal)
             }
-            if (e.tf + e.tb == 0.0) continue;  // eliminate_zeros on T + T^T (mmw.py:54)
             row.push_back(e);
         }
-        for (int32_t q = Qp[i]; q < Qp[i + 1]; ++q)
-            if (Qx[q] != 0.0) row.push_back(Ent{Qi[q], 2, 0.0, 0.0});
-        std::sort(row.begin(), row.end(), [](const Ent& x, const Ent& y) { return x.col < y.col; });
-        for (size_t k = 1; k < row.size(); ++k)
-            if (row[k].col == row[k - 1].col) {
-                err = "a node pair is both a gain edge and an association edge";
-                return SIGSDP_EINVAL;
+        return true;
+    };
+    std::vector<int32_t> rowptr(n + 1, 0);
+    std::vector<int64_t> g_ut(n + 1, 0), a_ut(n + 1, 0);
+    std::vector<int> bad(1, 0);
+    parallel_rows(n, [&](int64_t r0, int64_t r1) {
+        std::vector<Ent> row;
+        for (int64_t i = r0; i < r1; ++i) {
+            if (!build_row(i, row)) {
+                bad[0] = 1;
+                continue;
             }
-        for (const Ent& e : row) {
-            if (e.col > i && e.kind == 1) g_ut[i + 1]++;
-            if (e.col > i && e.kind == 2) a_ut[i + 1]++;
-            ents.push_back(e);
+            rowptr[i + 1] = (int32_t)row.size();
+            int64_t g = 0, a = 0;
+            for (const Ent& e : row) {
+                g += e.col > i && e.kind == 1;
+                a += e.col > i && e.kind == 2;
+            }
+            g_ut[i + 1] = g;
+            a_ut[i + 1] = a;
         }
-        rowptr[i + 1] = (int32_t)ents.size();
-        P.max_row = std::max<int>(P.max_row, (int)row.size());
-    }
-    if (ents.size() > (size_t)INT32_MAX) {
-        err = "pattern too large for int32 indices";
+    });
+    if (bad[0]) {
+        err = "a node pair is both a gain edge and an association edge";
         return SIGSDP_EINVAL;
     }
+    int64_t total = 0;
     for (int64_t i = 0; i < n; ++i) {
+        P.max_row = std::max<int>(P.max_row, rowptr[i + 1]);
+        total += rowptr[i + 1];
+        if (total > (int64_t)INT32_MAX) {
+            err = "pattern too large for int32 indices";
+            return SIGSDP_EINVAL;
+        }
+        rowptr[i + 1] = (int32_t)total;
         g_ut[i + 1] += g_ut[i];
         a_ut[i + 1] += a_ut[i];
     }
     P.E_g = g_ut[n];
     P.E_a = a_ut[n];
-    P.nnz = (int64_t)ents.size();
-
+    P.nnz = total;
     tm.lap("union pattern");
+
     // ---- edge ids in the reference's order (row-major upper triangle, mmw.py:56-57)
     std::vector<int32_t> col(P.nnz), eid(P.nnz);
     std::vector<double> tfwd(P.nnz), tbwd(P.nnz);
     P.gi.resize(P.E_g); P.gj.resize(P.E_g); P.tij.resize(P.E_g); P.tji.resize(P.E_g);
     P.ai.resize(P.E_a); P.aj.resize(P.E_a);
-    for (int64_t i = 0; i < n; ++i) {
-        int64_t g = g_ut[i], a = a_ut[i];
-        for (int32_t q = rowptr[i]; q < rowptr[i + 1]; ++q) {
-            const Ent& e = ents[q];
-            col[q] = e.col;
-            tfwd[q] = e.tf;
-            tbwd[q] = e.tb;
-            eid[q] = -1;
-            if (e.col > i) {
-                if (e.kind == 1) {
-                    P.gi[g] = (int32_t)i; P.gj[g] = e.col; P.tij[g] = e.tf; P.tji[g] = e.tb;
-                    eid[q] = (int32_t)g++;
-                } else {
-                    P.ai[a] = (int32_t)i; P.aj[a] = e.col;
-                    eid[q] = (int32_t)(P.E_g + a++);
+    parallel_rows(n, [&](int64_t r0, int64_t r1) {
+        std::vector<Ent> row;
+        for (int64_t i = r0; i < r1; ++i) {
+            build_row(i, row);
+            int64_t g = g_ut[i], a = a_ut[i];
+            int32_t q = rowptr[i];
+            for (const Ent& e : row) {
+                col[q] = e.col;
+                tfwd[q] = e.tf;
+                tbwd[q] = e.tb;
+                eid[q] = -1;
+                if (e.col > i) {
+                    if (e.kind == 1) {
+                        P.gi[g] = (int32_t)i; P.gj[g] = e.col; P.tij[g] = e.tf; P.tji[g] = e.tb;
+                        eid[q] = (int32_t)g++;
+                    } else {
+                        P.ai[a] = (int32_t)i; P.aj[a] = e.col;
+                        eid[q] = (int32_t)(P.E_g + a++);
+                    }
                 }
+                ++q;
             }
         }
-    }
+    });
     {
         // the pattern is symmetric: scanning the upper entries (j, i), j ascending, visits every
         // row i's lower entries in ascending column order, so a cursor per row finds the mirror
@@ -325,24 +368,26 @@ int build_host_plan(int64_t n, const int32_t* Sp, const int32_t* Si, const doubl
         for (int64_t k = 0; k < n; ++k) iperm[perm[k]] = (int32_t)k;
         std::vector<int32_t> rp(n + 1, 0), c2(P.nnz), e2(P.nnz);
         std::vector<double> f2(P.nnz), b2(P.nnz);
-        std::vector<uint64_t> ord;
-        int32_t w = 0;
-        for (int64_t k = 0; k < n; ++k) {
-            int32_t o = perm[k];
-            int32_t b = P.rowptr[o], e = P.rowptr[o + 1];
-            ord.resize(e - b);
-            for (int32_t q = b; q < e; ++q) ord[q - b] = ((uint64_t)(uint32_t)iperm[P.col[q]] << 32) | (uint32_t)q;
-            std::sort(ord.begin(), ord.end());
-            for (uint64_t key : ord) {
-                const int32_t q = (int32_t)(key & 0xffffffffu);
-                c2[w] = iperm[P.col[q]];
-                e2[w] = P.eid[q];
-                f2[w] = P.tfwd[q];
-                b2[w] = P.tbwd[q];
-                ++w;
+        for (int64_t k = 0; k < n; ++k) rp[k + 1] = rp[k] + (P.rowptr[perm[k] + 1] - P.rowptr[perm[k]]);
+        parallel_rows(n, [&](int64_t k0, int64_t k1) {
+            std::vector<uint64_t> ord;
+            for (int64_t k = k0; k < k1; ++k) {
+                const int32_t o = perm[k];
+                const int32_t b = P.rowptr[o], e = P.rowptr[o + 1];
+                ord.resize(e - b);
+                for (int32_t q = b; q < e; ++q) ord[q - b] = ((uint64_t)(uint32_t)iperm[P.col[q]] << 32) | (uint32_t)q;
+                std::sort(ord.begin(), ord.end());
+                int32_t w = rp[k];
+                for (uint64_t key : ord) {
+                    const int32_t q = (int32_t)(key & 0xffffffffu);
+                    c2[w] = (int32_t)(key >> 32);
+                    e2[w] = P.eid[q];
+                    f2[w] = P.tfwd[q];
+                    b2[w] = P.tbwd[q];
+                    ++w;
+                }
             }
-            rp[k + 1] = w;
-        }
+        });
         auto permute = [&](std::vector<double>& v) {
             std::vector<double> t(n);
             for (int64_t k = 0; k < n; ++k) t[k] = v[perm[k]];

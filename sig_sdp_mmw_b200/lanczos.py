@@ -29,12 +29,14 @@ def eig_dense(matmat, n, k, which, device):
     return lam[idx], V[:, idx]
 
 
-def thick_restart_lanczos(matmat, n, k, which, v0, ncv=None, tol=1e-12, max_restarts=500):
+def thick_restart_lanczos(matmat, n, k, which, v0, ncv=None, tol=1e-12, max_restarts=500, native_steps=None):
     """k extreme eigenpairs of a symmetric operator.
 
     matmat(X): X is (nvec, n) row-stacked vectors -> (nvec, n) of M x.
     which: 'LM' (largest magnitude, ascending |lambda| on return) or 'SA' (smallest algebraic).
     v0: start vector (n,), device fp64.
+    native_steps(Q, m, j0, j1, al, be): optional; runs Lanczos steps j0..j1-1 in the library
+        (sigsdp_solver_lanczos_steps) instead of the torch launches below.
     Returns (lam (k,), V (n, k), info dict)."""
     dev = v0.device
     if ncv is None:
@@ -54,8 +56,11 @@ def thick_restart_lanczos(matmat, n, k, which, v0, ncv=None, tol=1e-12, max_rest
     matvecs = 0
     arrow = None
     theta_keep = None
-    for restart in range(max_restarts):
-        for j in range(nkeep, m):
+    def cycle(j0):
+        if native_steps is not None:
+            native_steps(Q, m, j0, m, al, be)
+            return
+        for j in range(j0, m):
             w = matmat(Q[j:j + 1])[0]
             h = torch.mv(Q, w)
             w = torch.addmv(w, Qt, h, alpha=-1.0)
@@ -65,9 +70,18 @@ def thick_restart_lanczos(matmat, n, k, which, v0, ncv=None, tol=1e-12, max_rest
             beta = torch.linalg.norm(w)
             be[j] = beta
             Q[j + 1] = w / beta
+
+    import time as _t
+    t_cycle = t_host = 0.0
+    t_all = _t.perf_counter()
+    for restart in range(max_restarts):
+        t0 = _t.perf_counter()
+        cycle(nkeep)
+        al_h, be_h = al.cpu().numpy(), be.cpu().numpy()   # synchronises: the cycle's kernels are done
+        t_cycle += _t.perf_counter() - t0
+        t0 = _t.perf_counter()
         matvecs += m - nkeep
         # projected matrix on the host: diag(theta_keep) with its arrow row, then the tridiagonal tail
-        al_h, be_h = al.cpu().numpy(), be.cpu().numpy()
         Tm = np.zeros((m, m))
         if nkeep:
             Tm[np.arange(nkeep), np.arange(nkeep)] = theta_keep
@@ -84,6 +98,7 @@ def thick_restart_lanczos(matmat, n, k, which, v0, ncv=None, tol=1e-12, max_rest
         resid = np.abs(beta_m * S[m - 1, want])
         scale = np.abs(theta).max()
         if np.all(resid <= tol * scale):
+            t_host += _t.perf_counter() - t0
             break
         # thick restart: keep the wanted Ritz vectors plus a buffer of the next best
         nk = int(min(k + max(8, (m - k) // 3), m - 2))
@@ -97,6 +112,7 @@ def thick_restart_lanczos(matmat, n, k, which, v0, ncv=None, tol=1e-12, max_rest
         theta_keep = theta[keep]
         arrow = beta_m * S[m - 1, keep]
         nkeep = nk
+        t_host += _t.perf_counter() - t0
     Sw = torch.from_numpy(np.ascontiguousarray(S[:, want].T)).to(dev)
     lam = torch.from_numpy(np.ascontiguousarray(theta[want])).to(dev)
     V = (Sw @ Q[:m]).T
@@ -104,4 +120,5 @@ def thick_restart_lanczos(matmat, n, k, which, v0, ncv=None, tol=1e-12, max_rest
         o = torch.argsort(lam.abs())
         lam, V = lam[o], V[:, o]
     return lam, V, dict(restarts=restart, matvecs=matvecs, dense=False,
-                        resid=float(resid.max()), scale=float(scale), ncv=m)
+                        resid=float(resid.max()), scale=float(scale), ncv=m, cycle_s=round(t_cycle, 4),
+                        restart_s=round(t_host, 4), total_s=round(_t.perf_counter() - t_all, 4))

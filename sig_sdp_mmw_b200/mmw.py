@@ -42,6 +42,7 @@ class mmw(STATS_OBJECT, sdp_solver):
         self.plan_order = order
         self.seed = seed
         self.mode = _lib.MODE_FUSED
+        self.eig_tol = 1e-10          # relative residual of the final factor's eigenpairs
         self.last_solver = None
 
     def run_with_state(self, bs_iteration, Z, state):
@@ -70,13 +71,21 @@ class mmw(STATS_OBJECT, sdp_solver):
             return Y
         return mm
 
+    @staticmethod
+    def _native_steps(solver, torch):
+        def steps(Q, m, j0, j1, al, be):
+            solver.lanczos_steps(Q.data_ptr(), m, j0, j1, al.data_ptr(), be.data_ptr(),
+                                 torch.cuda.current_stream().cuda_stream)
+        return steps
+
     def _gap_row(self, solver, torch, dev):
         """mmw.py:79-117 for the state at the start of the next iteration."""
         e_max = solver.gap_prepare(torch.cuda.current_stream().cuda_stream)
         n = solver.plan.n
         g = torch.Generator(device="cpu").manual_seed(12345)
         v0 = torch.randn(n, dtype=torch.float64, generator=g).to(dev)
-        lam, _, _ = thick_restart_lanczos(self._matmat(solver, torch, dev), n, 1, "SA", v0, ncv=40, tol=1e-10)
+        lam, _, _ = thick_restart_lanczos(self._matmat(solver, torch, dev), n, 1, "SA", v0, ncv=40, tol=1e-10,
+                                          native_steps=self._native_steps(solver, torch))
         lam_min = float(lam[0]) * n
         return np.array([e_max, lam_min, e_max - lam_min])
 
@@ -146,7 +155,8 @@ class mmw(STATS_OBJECT, sdp_solver):
                 g = torch.Generator(device="cpu").manual_seed(int(self.seed) + 1)
                 v0 = torch.randn(K, dtype=torch.float64, generator=g).to(dev)
             perm = torch.from_numpy(plan.perm().astype(np.int64)).to(dev)
-            lam, V, info = thick_restart_lanczos(self._matmat(solver, torch, dev), K, rank, "LM", v0[perm])
+            lam, V, info = thick_restart_lanczos(self._matmat(solver, torch, dev), K, rank, "LM", v0[perm], tol=self.eig_tol,
+                                                native_steps=self._native_steps(solver, torch))
             self.last_eig_info = info
             X_half_int = V * torch.sqrt(lam.abs())[None, :]
             X_half = torch.empty_like(X_half_int)

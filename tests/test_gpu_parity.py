@@ -290,6 +290,10 @@ def test_argmax_colours_and_conflict_counts():
         assert alg.conflict_counts(zz, g["state"])[1] == 0
 
 
+def Gd_ref(V, lam):
+    return (V * lam.abs()) @ V.T
+
+
 def test_lanczos_path_equals_dense_path():
     """Final factor through thick-restart Lanczos (forced) vs the dense route."""
     from sig_sdp_mmw_b200.lanczos import eig_dense, thick_restart_lanczos
@@ -309,6 +313,12 @@ def test_lanczos_path_equals_dense_path():
     v0 = torch.randn(n, dtype=torch.float64, device=dev)
     lam_l, V_l, info = thick_restart_lanczos(mm, n, k, "LM", v0, ncv=70)
     assert not info["dense"]
+    # the same recurrence with the steps run natively in the library
+    lam_n, V_n, info_n = thick_restart_lanczos(mm, n, k, "LM", v0, ncv=70, native_steps=mmw._native_steps(sol, torch))
+    assert not info_n["dense"]
+    np.testing.assert_allclose(lam_n.cpu().numpy(), lam_d.cpu().numpy(), rtol=1e-10)
+    Gn = (V_n * lam_n.abs()) @ V_n.T
+    assert float((Gd_ref(V_d, lam_d) - Gn).abs().max()) < 1e-9
     np.testing.assert_allclose(lam_l.cpu().numpy(), lam_d.cpu().numpy(), rtol=1e-10)
     Gd = (V_d * lam_d.abs()) @ V_d.T
     Gl = (V_l * lam_l.abs()) @ V_l.T
