@@ -257,6 +257,28 @@ def run_ours(args):
                               "block0_Mcycles": {k: round(v / 1e6, 3) for k, v in sol.debug_cycles().items()}}))
         return
 
+    # ---- time-to-epsilon (second half of the BASELINE metric): e_max of the running mean X_avgd/i
+    # (mmw.py:80-96, the quantity plot_convergence_rho.py:47-50 plots) sampled every 10
+    # iterations of a fresh run; device time accumulated with CUDA events around each chunk
+    tte = None
+    if not args.skip_e2e:
+        sol.reset(stream)
+        torch.cuda.synchronize()
+        curve, t_acc = [], 0.0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for it in range(10, args.tte_iters + 1, 10):
+            e0.record()
+            sol.iterate(10, None, 1, stream)
+            e1.record()
+            torch.cuda.synchronize()
+            t_acc += e0.elapsed_time(e1)
+            curve.append((it, t_acc, sol.gap_prepare(stream)))
+        tte = {"quantity": "e_max(X_avgd / i) at Z=%d, eta=%g" % (Z, ETA), "curve_every": 10,
+               "e_max": [round(c[2], 5) for c in curve]}
+        for eps in (1.0, 0.5, 0.25):
+            hit = next((c for c in curve if c[2] <= eps), None)
+            tte["eps_%g" % eps] = {"iterations": hit[0], "device_ms": round(hit[1], 3)} if hit else None
+
     # ---- end to end through the drop-in object, host buffers in, host factor out
     # one untimed call warms the process (cuBLAS handle, allocator pools); the timed call uses a
     # fresh solver object, so its graph plan is built from the host matrices again
@@ -318,6 +340,7 @@ def run_ours(args):
                                      "total": e2e_s * 1e3,
                                      "lanczos": getattr(alg, "last_eig_info", None)}},
             "clocks": clocks,
+            "time_to_eps": tte,
         }
         if world == 1 and not args.no_cpu:
             ips, it, dt, cterms = time_oracle(state, Z, rr, args.cpu_budget, args.steps)
@@ -342,6 +365,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--ref-budget", type=float, default=60.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--tte-iters", type=int, default=300, help="iterations of the time-to-epsilon run")
     ap.add_argument("--mode", default="fused", choices=["fused", "stepwise"],
                     help="stepwise = one kernel per phase / Taylor term (profiling only, not a bench value)")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs: only the device-timed region")

@@ -92,6 +92,26 @@ int sigsdp_solver_create(const sigsdp_plan* plan, int Z, int D, double eta, int 
  * kernels, > 0 = that many rows per tile. */
 int sigsdp_solver_create_tiled(const sigsdp_plan* plan, int Z, int D, double eta, int dtype, int tiling,
                                sigsdp_solver** out);
+
+/* ------------------------------------------------- sketch-column sharding ----
+ * One graph across several GPUs: the columns of the D_total-wide sketch are split, rank r
+ * owning [col0, col0 + D).  The columns of exp(L/2) Omega are independent, so the Taylor
+ * terms need NO exchange; the dual / loss state is replicated (every rank computes the same
+ * bits); the only exchange is one all-reduce (sum) per iteration of the un-normalised Gram
+ * partials and the partial ||y_k||^2 -- sigsdp_solver_exchange_buffer(), nnzL + n doubles.
+ * Protocol per iteration on every rank:
+ *     sigsdp_solver_split_step(s, 1, ...)   finishes the previous iteration's Gram from the
+ *                                           reduced buffer (if any), runs dual..Taylor terms,
+ *                                           writes this rank's partials to the buffer
+ *     all-reduce(sum) of the buffer         (NCCL, by the host language)
+ * and, before reading any state, sigsdp_solver_split_step(s, 0, ...) to finish the last Gram.
+ * col0 and D must be multiples of 2 (fp64) / 4 (fp32).  Omega (injected or Philox) is the
+ * same D_total-wide matrix on every rank; a rank reads / generates all of a row only to
+ * normalise it. */
+int sigsdp_solver_create_sharded(const sigsdp_plan* plan, int Z, int D_total, int col0, int D, double eta, int dtype,
+                                 int tiling, sigsdp_solver** out);
+int sigsdp_solver_split_step(sigsdp_solver* s, int do_iter, const double* omega_dev, uint64_t seed, void* stream);
+int sigsdp_solver_exchange_buffer(sigsdp_solver* s, void** dev_ptr, int64_t* count);
 void sigsdp_solver_destroy(sigsdp_solver* s);
 int sigsdp_solver_reset(sigsdp_solver* s, void* stream);
 int sigsdp_solver_set_mode(sigsdp_solver* s, int mode);

@@ -44,6 +44,9 @@ def load():
         "sigsdp_plan_perm": [vp, i32p],
         "sigsdp_solver_create": [vp, C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(vp)],
         "sigsdp_solver_create_tiled": [vp, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.POINTER(vp)],
+        "sigsdp_solver_create_sharded": [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.POINTER(vp)],
+        "sigsdp_solver_split_step": [vp, C.c_int, vp, C.c_uint64, vp],
+        "sigsdp_solver_exchange_buffer": [vp, C.POINTER(vp), i64p],
         "sigsdp_solver_reset": [vp, vp],
         "sigsdp_solver_set_mode": [vp, C.c_int],
         "sigsdp_solver_info": [vp, i64p],
@@ -155,12 +158,15 @@ class Plan:
 class Solver:
     """MMW state for one (plan, Z, D, eta, dtype), see sigsdp_solver_create."""
 
-    def __init__(self, plan, Z, D, eta, dtype=F64, mode=MODE_FUSED, tiling=-1):
+    def __init__(self, plan, Z, D, eta, dtype=F64, mode=MODE_FUSED, tiling=-1, D_total=None, col0=0):
         lib = load()
         self.plan = plan
         self.handle = C.c_void_p()
-        check(lib.sigsdp_solver_create_tiled(plan.handle, int(Z), int(D), float(eta), int(dtype), int(tiling),
-                                             C.byref(self.handle)))
+        if D_total is None:
+            D_total = D
+        check(lib.sigsdp_solver_create_sharded(plan.handle, int(Z), int(D_total), int(col0), int(D), float(eta),
+                                               int(dtype), int(tiling), C.byref(self.handle)))
+        self.D_total, self.col0 = int(D_total), int(col0)
         if mode != MODE_FUSED:
             check(lib.sigsdp_solver_set_mode(self.handle, mode))
         self.Z, self.D = int(Z), int(D)
@@ -187,6 +193,16 @@ class Solver:
 
     def iterate(self, n_iters, omega_dev_ptr=None, seed=0, stream=None):
         check(load().sigsdp_solver_iterate(self.handle, int(n_iters), omega_dev_ptr, int(seed), stream))
+
+    def split_step(self, do_iter=True, omega_dev_ptr=None, seed=0, stream=None):
+        check(load().sigsdp_solver_split_step(self.handle, int(bool(do_iter)), omega_dev_ptr, int(seed), stream))
+
+    def exchange_buffer(self):
+        """(device pointer, number of doubles) of the per-iteration all-reduce buffer."""
+        ptr = C.c_void_p()
+        cnt = C.c_int64()
+        check(load().sigsdp_solver_exchange_buffer(self.handle, C.byref(ptr), C.byref(cnt)))
+        return int(ptr.value), int(cnt.value)
 
     def dual(self):
         Y = np.empty(self.C); e = np.empty(self.C); Yb = np.empty(self.C)

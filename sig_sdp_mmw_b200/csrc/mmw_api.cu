@@ -122,6 +122,9 @@ struct sigsdp_solver {
     void* F = nullptr;
     long long iters_done = 0;
     bool owned_by_batch = false;
+    // sketch-column shard: columns [col0, col0 + D) of a Dtot-wide sketch (Dtot == D: unsharded)
+    int Dtot = 0, col0 = 0;
+    bool pending_finish = false;   // split mode: a raw Gram is waiting for its all-reduce + finish
     // scratch of the eigen-solver building blocks (allocated on first use)
     double* Mval = nullptr;      // nnz: a symmetric matrix on the plan's pattern
     double* rtmp = nullptr;      // n
@@ -142,10 +145,10 @@ struct sigsdp_batch {
 // ---------------------------------------------------------------------------
 // kernels
 template <typename T, int G>
-__global__ void __launch_bounds__(NT, 2) k_fused(Prob<T> P, int n_iters) {
+__global__ void __launch_bounds__(NT, 2) k_fused(Prob<T> P, int n_iters, int do_finish) {
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     GridTeam team;
-    run_iterations<T, G>(P, team, n_iters, dyn_smem);
+    run_iterations<T, G>(P, team, n_iters, dyn_smem, do_finish);
 }
 template <typename T, int G>
 __global__ void __launch_bounds__(NT, 2) k_dual(Prob<T> P) {
@@ -521,9 +524,9 @@ static int occupancy_fused(int* occ, size_t smem) {
 }
 
 template <typename T, int G>
-static int launch_fused(sigsdp_solver* s, int n_iters, cudaStream_t st) {
+static int launch_fused(sigsdp_solver* s, int n_iters, cudaStream_t st, int do_finish = 0) {
     Prob<T> P = prob_of<T>(s);
-    void* args[] = {(void*)&P, (void*)&n_iters};
+    void* args[] = {(void*)&P, (void*)&n_iters, (void*)&do_finish};
     CK(cudaLaunchCooperativeKernel((void*)k_fused<T, G>, dim3(s->grid), dim3(NT), args, s->smem, st));
     return SIGSDP_OK;
 }
@@ -773,7 +776,11 @@ static int solver_alloc(sigsdp_solver* s) {
     CK(s->mem.alloc(&P.Xv, h.nnz));
     CK(s->mem.alloc(&P.Xbarv, h.nnz));
     CK(s->mem.alloc(&P.r, n));
-    CK(s->mem.alloc(&P.dsq, n));
+    CK(s->mem.alloc(&P.graw, h.nnz + n));   // [graw | dsq]: one buffer, so one all-reduce in split mode
+    P.dsq = P.graw + h.nnz;
+    P.Dtot = s->Dtot;
+    P.col0 = s->col0;
+    P.split = s->Dtot != s->D ? 1 : 0;
     CK(s->mem.alloc(&P.B0, (size_t)n * s->Dp));
     CK(s->mem.alloc(&P.B1, (size_t)n * s->Dp));
     CK(s->mem.alloc(&P.F, (size_t)n * s->Dp));
@@ -874,7 +881,8 @@ static int solver_reset_impl(sigsdp_solver* s, cudaStream_t st) {
     CK(cudaMemsetAsync(P.Xv, 0, h.nnz * sizeof(double), st));
     CK(cudaMemsetAsync(P.Xbarv, 0, h.nnz * sizeof(double), st));
     CK(cudaMemsetAsync(P.r, 0, n * sizeof(double), st));
-    CK(cudaMemsetAsync(P.dsq, 0, n * sizeof(double), st));
+    CK(cudaMemsetAsync(P.graw, 0, (h.nnz + n) * sizeof(double), st));
+    s->pending_finish = false;
     CK(cudaMemsetAsync(P.B0, 0, (size_t)n * s->Dp * sizeof(T), st));
     CK(cudaMemsetAsync(P.B1, 0, (size_t)n * s->Dp * sizeof(T), st));
     CK(cudaMemsetAsync(P.F, 0, (size_t)n * s->Dp * sizeof(T), st));
@@ -899,6 +907,11 @@ int sigsdp_solver_create(const sigsdp_plan* plan, int Z, int D, double eta, int 
 
 int sigsdp_solver_create_tiled(const sigsdp_plan* plan, int Z, int D, double eta, int dtype, int tiling,
                                sigsdp_solver** out) {
+    return sigsdp_solver_create_sharded(plan, Z, D, 0, D, eta, dtype, tiling, out);
+}
+
+int sigsdp_solver_create_sharded(const sigsdp_plan* plan, int Z, int D_total, int col0, int D, double eta, int dtype,
+                                 int tiling, sigsdp_solver** out) {
     if (!out) return fail(SIGSDP_EINVAL, "out is null");
     *out = nullptr;
     if (!plan) return fail(SIGSDP_EINVAL, "null plan");
@@ -907,8 +920,15 @@ int sigsdp_solver_create_tiled(const sigsdp_plan* plan, int Z, int D, double eta
     if (D < 1 || D > 4096) return fail(SIGSDP_EINVAL, "D must be in [1, 4096]");
     if (dtype != SIGSDP_F64 && dtype != SIGSDP_F32) return fail(SIGSDP_EINVAL, "dtype must be SIGSDP_F64 or SIGSDP_F32");
     if (!(eta > 0.0)) return fail(SIGSDP_EINVAL, "eta must be positive");
+    {
+        const int V = dtype == SIGSDP_F64 ? 2 : 4;
+        if (col0 < 0 || D_total < D || col0 + D > D_total || (D != D_total && (col0 % V || D % V)))
+            return fail(SIGSDP_EINVAL, "column shard must lie inside the sketch and be aligned to 16 bytes");
+    }
     CK(cudaSetDevice(plan->device));
     sigsdp_solver* s = new sigsdp_solver();
+    s->Dtot = D_total;
+    s->col0 = col0;
     s->plan = plan;
     s->Z = Z;
     s->D = D;
@@ -989,8 +1009,43 @@ static int iterate_impl(sigsdp_solver* s, int n_iters, const double* omega_dev, 
 }
 }  // extern "C++"
 
+int sigsdp_solver_exchange_buffer(sigsdp_solver* s, void** dev_ptr, int64_t* count) {
+    if (!s || !dev_ptr || !count) return fail(SIGSDP_EINVAL, "null argument");
+    *dev_ptr = s->dtype == SIGSDP_F64 ? (void*)s->p64.graw : (void*)s->p32.graw;
+    *count = s->plan->h.nnz + s->plan->h.n;
+    return SIGSDP_OK;
+}
+
+extern "C++" {
+template <typename T>
+static int split_step_impl(sigsdp_solver* s, int do_iter, const double* omega_dev, uint64_t seed, cudaStream_t st) {
+    Prob<T>& P = prob_of<T>(s);
+    P.omega = omega_dev;
+    P.seed = seed;
+    const int do_finish = s->pending_finish ? 1 : 0;
+    int rc = SIGSDP_OK;
+    FOR_G(s->G, rc = (launch_fused<T, G>(s, do_iter ? 1 : 0, st, do_finish)));
+    return rc;
+}
+}
+
+int sigsdp_solver_split_step(sigsdp_solver* s, int do_iter, const double* omega_dev, uint64_t seed, void* stream) {
+    if (!s) return fail(SIGSDP_EINVAL, "null solver");
+    if (s->Dtot == s->D) return fail(SIGSDP_ESTATE, "not a column shard (use sigsdp_solver_iterate)");
+    if (!do_iter && !s->pending_finish) return SIGSDP_OK;
+    CK(cudaSetDevice(s->plan->device));
+    int rc = s->dtype == SIGSDP_F64 ? split_step_impl<double>(s, do_iter, omega_dev, seed, (cudaStream_t)stream)
+                                    : split_step_impl<float>(s, do_iter, omega_dev, seed, (cudaStream_t)stream);
+    if (rc == SIGSDP_OK) {
+        s->pending_finish = do_iter != 0;
+        if (do_iter) s->iters_done += 1;
+    }
+    return rc;
+}
+
 int sigsdp_solver_iterate(sigsdp_solver* s, int n_iters, const double* omega_dev, uint64_t seed, void* stream) {
     if (!s) return fail(SIGSDP_EINVAL, "null solver");
+    if (s->Dtot != s->D) return fail(SIGSDP_ESTATE, "column shard: drive it with sigsdp_solver_split_step");
     if (n_iters < 0) return fail(SIGSDP_EINVAL, "n_iters < 0");
     if (n_iters == 0) return SIGSDP_OK;
     CK(cudaSetDevice(s->plan->device));

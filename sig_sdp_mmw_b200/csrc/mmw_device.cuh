@@ -106,6 +106,12 @@ struct Prob {
     const double* omega;   // raw normals for this call (caller numbering) or nullptr
     unsigned long long seed;
     TileDev tl;
+    // sketch-column sharding across GPUs: this solver holds columns [col0, col0 + D) of a
+    // Dtot-wide sketch.  split != 0: the Gram phase writes un-normalised partial dot products
+    // to graw (the terms' partial ||F_k||^2 go to dsq, which then lives right behind graw);
+    // the ranks all-reduce that buffer and phase_gram_finish completes X, X_avgd and r.
+    int Dtot, col0, split;
+    double* graw;          // nnz (+ n: dsq)
 };
 
 // ---------------------------------------------------------------------------
@@ -612,20 +618,39 @@ __device__ void phase_loss(const Prob<T>& P, const Team& team, int it_local, dou
 
     // ---- Omega_hat -> B0, F; ||.||_inf; ||row||^2
     double c1 = 0.0, trp = 0.0;
-    const double sqrtD = sqrt((double)D);
+    const int Dtot = P.Dtot, col0 = P.col0;
+    const double sqrtD = sqrt((double)Dtot);
     for (int t = team.rank(); t < ntiles; t += team.size()) {
         const int k = t * R + grp;
         if (k < K) {
             const int ko = g.perm ? g.perm[k] : k;
             double ss = 0.0;
+            // the row norm runs over all Dtot columns of the sketch: a column shard generates
+            // (or reads) the columns it does not own only for that
+            if (Dtot != D)
+                for (int c0 = lane * VEC; c0 < Dtot; c0 += G * VEC) {
+                    if (c0 >= col0 && c0 < col0 + D) continue;
+                    T raw[VEC];
+                    if (P.omega) {
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v)
+                            raw[v] = (c0 + v < Dtot) ? (T)(P.omega[((size_t)it_local * K + ko) * Dtot + c0 + v] / sqrtD) : (T)0;
+                    } else {
+                        philox_normals(P.seed, iter, ko, c0 / VEC, raw);
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) raw[v] = (c0 + v < Dtot) ? (T)((double)raw[v] / sqrtD) : (T)0;
+                    }
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) ss += (double)raw[v] * (double)raw[v];
+                }
             for (int c0 = lane * VEC; c0 < Dp; c0 += G * VEC) {
                 T raw[VEC];
                 if (P.omega) {
 #pragma unroll
                     for (int v = 0; v < VEC; ++v)
-                        raw[v] = (c0 + v < D) ? (T)(P.omega[((size_t)it_local * K + ko) * D + c0 + v] / sqrtD) : (T)0;
+                        raw[v] = (c0 + v < D) ? (T)(P.omega[((size_t)it_local * K + ko) * Dtot + col0 + c0 + v] / sqrtD) : (T)0;
                 } else {
-                    philox_normals(P.seed, iter, ko, c0 / VEC, raw);
+                    philox_normals(P.seed, iter, ko, (col0 + c0) / VEC, raw);
 #pragma unroll
                     for (int v = 0; v < VEC; ++v) raw[v] = (c0 + v < D) ? (T)((double)raw[v] / sqrtD) : (T)0;
                 }
@@ -788,7 +813,7 @@ __device__ void phase_gram(const Prob<T>& P, const Team& team, double* sh) {
     const int lane = tile.thread_rank();
     const int grp = threadIdx.x / G;
     constexpr int R = NT / G;
-    const double tr = team_sum(P.ptr, 1, team.size(), sh) / K;
+    const double tr = P.split ? 1.0 : team_sum(P.ptr, 1, team.size(), sh) / K;
     const bool one_chunk = Dp <= G * VEC;
     const int ntiles = (K + R - 1) / R;
     for (int t = team.rank(); t < ntiles; t += team.size()) {
@@ -834,14 +859,18 @@ __device__ void phase_gram(const Prob<T>& P, const Team& team, double* sh) {
                     if (j == lane) mine = dot;
                 }
                 if (p < p1) {
-                    const double x = ee >= 0 ? mine / tr : P.dsq[k] / tr;
-                    if (ee >= 0) rsum += x;
-                    P.Xbarv[p] += P.Xv[p];
-                    P.Xv[p] = x;
+                    if (P.split) {
+                        P.graw[p] = ee >= 0 ? mine : 0.0;
+                    } else {
+                        const double x = ee >= 0 ? mine / tr : P.dsq[k] / tr;
+                        if (ee >= 0) rsum += x;
+                        P.Xbarv[p] += P.Xv[p];
+                        P.Xv[p] = x;
+                    }
                 }
             }
             rsum = group_sum<G>(tile, rsum);
-            if (lane == 0) P.r[k] = rsum;
+            if (lane == 0 && !P.split) P.r[k] = rsum;
         }
     }
 }
@@ -984,7 +1013,8 @@ __device__ void phase_gram_staged(const Prob<T>& P, const Team& team, double* sh
     const unsigned rowb = (unsigned)(Dp * W);
     const int nc = Dp / VEC;
     const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-    const double tr = team_sum(P.ptr, 1, team.size(), sh) / K;
+    const bool raw = P.split != 0;
+    const double tr = raw ? 1.0 : team_sum(P.ptr, 1, team.size(), sh) / K;
     const double inv_tr = 1.0 / tr;
     const bool timed = team.rank() == 0 && threadIdx.x == 0;
     long long wait_c = 0;
@@ -1000,10 +1030,14 @@ __device__ void phase_gram_staged(const Prob<T>& P, const Team& team, double* sh
                 const int p0 = g.rowptr[k], p1 = g.rowptr[k + 1], pd = g.dpos[k];
                 const unsigned abase = st.rows_a + lds_u16(st.la + 2u * (unsigned)pd) * rowb;
                 for (int p = p0 + lane; p < p1; p += 32) {
-                    const double xold = P.Xv[p], xbar = P.Xbarv[p];   // in flight during the dot product
+                    double xold = 0.0, xbar = 0.0;
+                    if (!raw) {   // in flight during the dot product
+                        xold = P.Xv[p];
+                        xbar = P.Xbarv[p];
+                    }
                     double x;
                     if (p == pd) {
-                        x = P.dsq[k] * inv_tr;
+                        x = raw ? 0.0 : P.dsq[k] * inv_tr;
                     } else {
                         const unsigned bbase = st.rows_a + lds_u16(st.la + 2u * (unsigned)p) * rowb;
                         T d0 = (T)0, d1 = (T)0;
@@ -1028,17 +1062,57 @@ __device__ void phase_gram_staged(const Prob<T>& P, const Team& team, double* sh
                         x = ((double)d0 + (double)d1) * inv_tr;
                         rsum += x;
                     }
-                    P.Xbarv[p] = xbar + xold;
-                    P.Xv[p] = x;
+                    if (raw) {
+                        P.graw[p] = x;
+                    } else {
+                        P.Xbarv[p] = xbar + xold;
+                        P.Xv[p] = x;
+                    }
                 }
             }
             rsum = warp_sum(rsum);
-            if (k < r1 && lane == 0) P.r[k] = rsum;
+            if (k < r1 && lane == 0 && !raw) P.r[k] = rsum;
         }
     }
     if (timed) {
         P.ctrl->dbg[2] += wait_c;
         P.ctrl->dbg[3] += clock64() - tph0 - wait_c;
+    }
+}
+
+
+// ===========================================================================
+// Sketch-column sharding: after the ranks all-reduced [graw | dsq] (partial dot products and
+// partial ||F_k||^2 over each rank's columns), every rank completes the Gram phase the same
+// way: tr = sum dsq / K; X = graw / tr (diagonal: dsq / tr); X_avgd += X_prev; r = row sums.
+template <typename T, int G, class Team>
+__device__ void phase_gram_finish(const Prob<T>& P, const Team& team, double* sh) {
+    const PlanDev& g = P.g;
+    const int K = g.n;
+    double trp = 0.0;
+    for (int k = team.rank() * NT + threadIdx.x; k < K; k += team.size() * NT) trp += P.dsq[k];
+    trp = block_sum(trp, sh);
+    if (threadIdx.x == 0) P.ptr[team.rank()] = trp;
+    team.sync();
+    const double tr = team_sum(P.ptr, 1, team.size(), sh) / K;
+    const int lane = threadIdx.x & (G - 1), grp = threadIdx.x / G;
+    constexpr int R = NT / G;
+    const int ntiles = (K + R - 1) / R;
+    for (int t = team.rank(); t < ntiles; t += team.size()) {   // block-uniform: shuffles below are convergent
+        const int k = t * R + grp;
+        double rsum = 0.0;
+        if (k < K) {
+            const int pd = g.dpos[k], p1 = g.rowptr[k + 1];
+            for (int p = g.rowptr[k] + lane; p < p1; p += G) {
+                const double x = (p == pd ? P.dsq[k] : P.graw[p]) / tr;
+                if (p != pd) rsum += x;
+                P.Xbarv[p] += P.Xv[p];
+                P.Xv[p] = x;
+            }
+        }
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) rsum += __shfl_xor_sync(0xffffffffu, rsum, o);
+        if (k < K && lane == 0) P.r[k] = rsum;
     }
 }
 
@@ -1088,7 +1162,7 @@ __device__ __forceinline__ void stage_setup(const Prob<T>& P, unsigned char* dyn
 }
 
 template <typename T, int G, class Team>
-__device__ void run_iterations(const Prob<T>& P, const Team& team, int n_iters, unsigned char* dyn) {
+__device__ void run_iterations(const Prob<T>& P, const Team& team, int n_iters, unsigned char* dyn, int do_finish = 0) {
     __shared__ double sh[NWARP + 2];
     Stage<T> st;
     stage_setup(P, dyn, st);
@@ -1103,6 +1177,10 @@ __device__ void run_iterations(const Prob<T>& P, const Team& team, int n_iters, 
         team.sync();                                   \
         if (leader) sync_c += clock64() - ts0_;        \
     } while (0)
+    if (do_finish) {   // split mode: complete the previous iteration's Gram from the all-reduced buffer
+        phase_gram_finish<T, G>(P, team, sh);
+        TIMED_SYNC();
+    }
     for (int it = 0; it < n_iters; ++it) {
         unsigned long long t0 = 0, t1 = 0, t2 = 0;
         long long cc = 0;

@@ -45,6 +45,19 @@ def test_binary_search_twin_follows_reference_probe_log():
     assert bs.set_bounds(state) == (1, 75)
 
 
+def test_column_shards_tile_the_sketch():
+    from sig_sdp_mmw_b200.sharded import column_shard
+    for D, w, vec in [(32, 8, 2), (32, 4, 2), (64, 8, 4), (26, 2, 2), (32, 1, 2)]:
+        cols = []
+        for r in range(w):
+            c0, dl = column_shard(D, r, w, vec)
+            assert c0 % vec == 0 and dl % vec == 0 and dl > 0
+            cols += list(range(c0, c0 + dl))
+        assert cols == list(range(D))
+    with pytest.raises(ValueError):
+        column_shard(6, 4, 2, 2) if False else column_shard(6, 0, 4, 2)
+
+
 def test_shard_partitions_every_instance_once():
     for n, w in [(1024, 8), (10, 4), (3, 8), (7, 2)]:
         seen = []
@@ -144,3 +157,61 @@ def test_batch_mode_equals_standalone_solvers():
                 np.testing.assert_allclose(x, y, rtol=tol, atol=tol * 1e-2)
             np.testing.assert_array_equal(a.history(nit)["m_star"], b.history(nit)["m_star"])
             assert a.info()["iters"] == nit
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world,dtype", [(2, "f64"), (4, "f64"), (2, "f32")])
+def test_sketch_column_shards_equal_single_solver(world, dtype):
+    """The multi-GPU protocol (split_step + all-reduce of the exchange buffer) emulated on one
+    GPU: `world` column-shard solvers whose buffers are summed between steps reproduce the
+    unsharded solver on the same injected Omega, and every shard holds identical state."""
+    import torch
+    from oracle import mmw_oracle as orc
+    from sig_sdp_mmw_b200 import _lib
+    from sig_sdp_mmw_b200.sharded import ShardedSolver
+    from tests.golden_util import omega_stream
+    g = load_case("n300_z10")
+    Z, rr, eta, nit = 8, 2, 0.04, 30
+    D = Z * rr
+    K = g["state"][0].shape[0]
+    code = _lib.F64 if dtype == "f64" else _lib.F32
+    om = np.stack(omega_stream(5, K, D, nit))
+    om_d = torch.from_numpy(om).cuda()
+    plan = _lib.Plan(g["state"], device=0, order=1)
+    bufs = []
+
+    def fake_reduce(t):          # collect; the sum is applied once all shards have stepped
+        bufs.append(t)
+    shards = [ShardedSolver(plan, Z, D, eta, r, world, dtype=code, reduce_fn=fake_reduce) for r in range(world)]
+    for i in range(nit):
+        bufs.clear()
+        for sh in shards:
+            sh.iterate(1, om_d[i:i + 1])
+        torch.cuda.synchronize()
+        total = torch.stack(bufs).sum(dim=0)
+        for b in bufs:
+            b.copy_(total)
+    for sh in shards:
+        sh.finish()
+    torch.cuda.synchronize()
+    ref = _lib.Solver(plan, Z, D, eta, code)
+    ref.iterate(nit, om_d.data_ptr(), 0, None)
+    torch.cuda.synchronize()
+    tol = 1e-9 if dtype == "f64" else 2e-3
+    a = shards[0].solver
+    np.testing.assert_allclose(a.dual()[0], ref.dual()[0], rtol=tol)
+    for x, y in zip(a.X(True) + a.L(), ref.X(True) + ref.L()):
+        np.testing.assert_allclose(x, y, rtol=tol, atol=tol * 1e-3)
+    for sh in shards[1:]:        # replicated state is bit-identical across the shards
+        for x, y in zip(sh.solver.dual() + sh.solver.X(True), a.dual() + a.X(True)):
+            np.testing.assert_array_equal(x, y)
+    # each shard's sketch block is its column slice of the full one
+    full = ref.sketch()
+    for sh in shards:
+        np.testing.assert_allclose(sh.solver.sketch(), full[:, sh.col0:sh.col0 + sh.Dl], rtol=tol, atol=1e-12 if dtype == "f64" else 1e-4)
+    if dtype == "f64":           # and the oracle agrees
+        p = orc.build_problem(Z, g["state"])
+        st = orc.MMWState(p, eta)
+        for i in range(nit):
+            st.step(om[i])
+        np.testing.assert_allclose(a.dual()[0], st.Y, rtol=1e-9)
