@@ -32,6 +32,7 @@ WORKLOADS = {
     "cfg1_500": (dict(cell_size=10, sta_density_per_1m2=125e-4), 4, 2, "float64"),
 }
 ETA = 0.04
+NCU_TRAFFIC_RATIO = 10.286 / 8.453   # measured DRAM bytes / algorithmic bytes of k_fused (see roofline.traffic_source)
 METRIC = "mmw_iters_per_s"
 UNIT = "iterations/s"
 
@@ -199,6 +200,92 @@ def run_batch(args):
         dist.destroy_process_group()
 
 
+def run_sharded(args):
+    """N > 1: ONE graph, the sketch columns sharded across the ranks (sig_sdp_mmw_b200/sharded.py):
+    no exchange inside the Taylor terms, one NCCL all-reduce of nnzL + n doubles per iteration.
+    Strong scaling: the job is the same 150-iteration solve as at N = 1."""
+    import torch
+    import torch.distributed as dist
+    from sig_sdp_mmw_b200 import _lib
+    from sig_sdp_mmw_b200.sharded import ShardedSolver
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    state, Z, rr, dtype = make_state(args.workload, 0)        # the same instance on every rank
+    K, D = state[0].shape[0], Z * rr
+    code = _lib.F64 if dtype == "float64" else _lib.F32
+    w = 8 if dtype == "float64" else 4
+    t0 = time.perf_counter()
+    plan = _lib.Plan(state, device=local, order=args.order)
+    sh = ShardedSolver(plan, Z, D, ETA, rank, world, dtype=code)
+    setup_s = time.perf_counter() - t0
+    stream = torch.cuda.current_stream().cuda_stream
+    sh.iterate(max(args.warmup, 3), None, 1, stream)
+    sh.finish(stream)
+    sh.solver.reset(stream)
+    torch.cuda.synchronize()
+    dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dist.barrier()
+    torch.cuda.synchronize()
+    ev0.record()
+    sh.iterate(args.steps, None, 1, stream)
+    sh.finish(stream)
+    ev1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms = ev0.elapsed_time(ev1)
+    terms = sh.solver.total_terms()
+    # end to end: host matrices in, plan + shard set-up, K iterations, running-mean diagonal out
+    dist.barrier()
+    t0 = time.perf_counter()
+    plan2 = _lib.Plan(state, device=local, order=args.order)
+    sh2 = ShardedSolver(plan2, Z, D, ETA, rank, world, dtype=code)
+    sh2.iterate(args.steps, None, 1, stream)
+    sh2.finish(stream)
+    xd, _, _ = sh2.solver.X(True)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max, e2e_ms = [float(x) for x in t.cpu()]
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        tot_bytes, spmm_b, rest_b = algorithmic_bytes(K, plan.E_g, plan.E_a, plan.nnzT, D, w, terms * world, args.steps)
+        S, Q, h = state
+        h2d = (S.indptr.nbytes + S.indices.nbytes + S.data.nbytes + Q.indptr.nbytes + Q.indices.nbytes + Q.data.nbytes + h.nbytes)
+        print(json.dumps({
+            "metric": METRIC, "value": args.steps / (ms_max * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64" if dtype == "float64" else "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "nodes": K, "Z": Z, "D": D, "eta": ETA, "nnzL": plan.nnz,
+                       "parallelism": "sketch columns sharded x%d (D/N = %d columns per GPU), dual/loss state replicated, "
+                                      "one NCCL all-reduce of %d doubles per iteration" % (world, D // world, plan.nnz + K),
+                       "taylor_terms_rank0": terms, "omega": "device Philox", "node_order": args.order,
+                       "launches_per_iteration": 1, "setup_s": setup_s},
+            "gpu_launches": args.steps + 1,
+            "roofline": {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,
+                         "note": "per-GPU roofline is reported at n_gpus = 1; here the replicated phases and the "
+                                 "all-reduce bound the step"},
+            "e2e": {"value": args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps,
+                    "d2h_bytes_per_step": xd.nbytes / args.steps,
+                    "what": "host state -> plan + shard set-up on every rank -> K iterations -> running-mean diagonal on host"},
+            "clocks": clocks}))
+    dist.destroy_process_group()
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -328,7 +415,11 @@ def run_ours(args):
                        "plan_build_s": plan_s},
             "gpu_launches": 1,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "k_fused (whole iteration)", "peak_source": peak_src,
+                         "traffic": tot_bytes * NCU_TRAFFIC_RATIO if args.workload == "cfg4_100k" else None,
+                         "traffic_source": "ncu --set full dram__bytes_read+write of k_fused on this workload "
+                                           "(profiles/r1_ncu_fused_cfg4_full.txt: 10.29 GB for a 12-iteration launch "
+                                           "whose algorithmic bytes are 8.45 GB), scaled to this launch's algorithmic bytes",
+                         "kernel": "k_fused (whole iteration)", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": tot_bytes, "spmm_term_bytes": spmm_b,
                          "edge_dual_loss_omega_bytes_per_iter": rest_b},
             "e2e": {"value": world * args.steps / (e2e_ms_max * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps,
@@ -365,13 +456,19 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--ref-budget", type=float, default=60.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--parallel", default="replicas", choices=["sketch", "replicas"],
+                    help="N > 1: one independent instance per GPU (weak scaling, default) or shard one graph's sketch "
+                         "columns across the GPUs (strong scaling, one all-reduce per iteration)")
     ap.add_argument("--tte-iters", type=int, default=300, help="iterations of the time-to-epsilon run")
     ap.add_argument("--mode", default="fused", choices=["fused", "stepwise"],
                     help="stepwise = one kernel per phase / Taylor term (profiling only, not a bench value)")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs: only the device-timed region")
     args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.workload == "cfg5_batch":
         run_batch(args)
+    elif args.impl == "ours" and world > 1 and args.parallel == "sketch":
+        run_sharded(args)
     elif args.impl == "reference":
         run_reference(args)
     else:
