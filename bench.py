@@ -341,7 +341,8 @@ def run_ours(args):
             print(json.dumps({"profiling_run": True, "mode": args.mode, "workload": args.workload, "steps": args.steps,
                               "ms": ms, "taylor_terms": terms, "phase_us": phase.tolist(), "grid": sol.grid,
                               "tile_rows": sol.tile_rows, "smem": sol.smem,
-                              "block0_Mcycles": {k: round(v / 1e6, 3) for k, v in sol.debug_cycles().items()}}))
+                              "block0_Mcycles": {k: round(v / 1e6, 3) for k, v in sol.debug_cycles().items()},
+                              "term_profile_Mcycles": sol.debug_term_profile()}))
         return
 
     # ---- time-to-epsilon (second half of the BASELINE metric): e_max of the running mean X_avgd/i

@@ -160,6 +160,10 @@ int sigsdp_solver_get_phase_times(sigsdp_solver* s, int count, double* us_host);
  * [0] Taylor-term staging wait, [1] Taylor-term compute, [2] Gram staging wait,
  * [3] Gram compute, [4] grid-barrier wait, [5] dual, [6] exp, [7] loss.  Diagnostics. */
 int sigsdp_solver_debug_cycles(sigsdp_solver* s, int64_t out8[8]);
+/* Diagnostics: cumulative SM cycles of block 0 / thread 0 inside the staged Taylor term since
+ * reset: [0] tile barrier, [1] metadata + copy issue, [2] copy wait, [3] row pointer loads,
+ * [4] multiply loop, [5] unused. */
+int sigsdp_solver_debug_term_profile(sigsdp_solver* s, double out6[6]);
 /* total Taylor terms (SpMM passes) executed since create/reset */
 int sigsdp_solver_total_terms(sigsdp_solver* s, int64_t* out);
 

@@ -1,5 +1,5 @@
 #!/bin/bash
 set -u
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -40 > gpurun_out/pytest_gpu.log; tail -4 gpurun_out/pytest_gpu.log
-timeout 600 python bench.py --workload cfg5_batch --instances 296 --steps 150 2>&1 | tail -2
+if [ "${TESTS:-1}" = "1" ]; then timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -30 > gpurun_out/pytest_gpu.log; tail -3 gpurun_out/pytest_gpu.log; fi
+for wl in cfg4_100k cfg3_20k cfg2_5k cfg1_500; do echo "== $wl"; timeout 300 python bench.py --workload $wl --skip-e2e 2>&1 | tail -1; done

@@ -58,6 +58,7 @@ def load():
         "sigsdp_solver_get_history": [vp, C.c_int, i32p, i32p, i32p, f64p, f64p],
         "sigsdp_solver_total_terms": [vp, i64p],
         "sigsdp_solver_debug_cycles": [vp, i64p],
+        "sigsdp_solver_debug_term_profile": [vp, f64p],
         "sigsdp_solver_get_phase_times": [vp, C.c_int, f64p],
         "sigsdp_solver_xavg_matrix": [vp, C.c_double, vp],
         "sigsdp_solver_gap_prepare": [vp, f64p, vp],
@@ -262,6 +263,11 @@ class Solver:
         check(load().sigsdp_solver_debug_cycles(self.handle, a))
         keys = ["term_wait", "term_compute", "gram_wait", "gram_compute", "grid_sync", "dual", "exp", "loss"]
         return dict(zip(keys, [int(x) for x in a]))
+
+    def debug_term_profile(self):
+        a = np.zeros(6)
+        check(load().sigsdp_solver_debug_term_profile(self.handle, _p(a, C.c_double)))
+        return dict(zip(["tile_barrier", "issue", "copy_wait", "rowptr", "multiply", "-"], (a / 1e6).round(3).tolist()))
 
     def total_terms(self):
         v = C.c_int64()

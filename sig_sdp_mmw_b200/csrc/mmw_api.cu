@@ -172,7 +172,10 @@ __global__ void __launch_bounds__(NT, 2) k_term(Prob<T> P, const T* bin, T* bout
     if (P.tl.enabled) {
         Stage<T> st;
         stage_setup(P, dyn_smem, st);
-        phase_term_staged<T, G>(P, StepTeam(), bin, bout, coeff, slot, sh, st);
+        if (G >= 8 && P.Dp == G * Vec<T>::N)
+            phase_term_staged2<T, G>(P, StepTeam(), bin, bout, coeff, slot, sh, st);
+        else
+            phase_term_staged<T, G>(P, StepTeam(), bin, bout, coeff, slot, sh, st);
     } else {
         phase_term<T, G>(P, StepTeam(), bin, bout, coeff, mu, slot, sh);
     }
@@ -620,9 +623,10 @@ int sigsdp_plan_create(int64_t n, const int32_t* Sp, const int32_t* Si, const do
     }
     if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(e, "cudaSetDevice");
     pool_setup(device);
-    cudaDeviceProp prop;
-    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail(e, "cudaGetDeviceProperties");
-    pl->num_sms = prop.multiProcessorCount;
+    int sms = 0;   // (cudaGetDeviceProperties costs ~100 ms; one attribute is all we need)
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess)
+        return bail(e, "cudaDeviceGetAttribute");
+    pl->num_sms = sms;
     HostPlan& h = pl->h;
     PlanDev& d = pl->d;
     d.n = (int)h.n;
@@ -804,7 +808,7 @@ static int solver_alloc(sigsdp_solver* s) {
     // rows, capped so that a tile's distinct sketch rows, its L_accu slice and its local
     // column indices fit the per-block shared-memory budget (two blocks per SM)
     const int R = NT / s->G;
-    P.tl = TileDev{0, 0, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr};
+    P.tl = TileDev{};
     s->smem = 0;
     s->RT = 0;
     if (s->tiling != 0) {
@@ -820,7 +824,10 @@ static int solver_alloc(sigsdp_solver* s) {
             if (it == pl->tiles.end()) {
                 sigsdp_plan::TileCache tc;
                 build_tiles(h, max_rows, ucap, nnzcap, tc.h);
-                tc.d = TileDev{0, tc.h.ntiles, ucap, nnzcap, nullptr, nullptr, nullptr, nullptr, nullptr};
+                tc.d = TileDev{};
+                tc.d.ntiles = tc.h.ntiles;
+                tc.d.ucap = ucap;
+                tc.d.nnzcap = nnzcap;
                 if (tc.h.ok) {
                     int *trow, *ucnt, *rptr, *runs;
                     unsigned short* lcol;
@@ -831,6 +838,9 @@ static int solver_alloc(sigsdp_solver* s) {
                     CK(pl->tile_mem.upload(&rptr, tc.h.rptr));
                     CK(pl->tile_mem.upload(&runs, tc.h.runs));
                     CK(pl->tile_mem.upload(&lcol, lpad));
+                    int* trec;
+                    CK(pl->tile_mem.upload(&trec, tc.h.trec));
+                    tc.d.trec = reinterpret_cast<const int4*>(trec);
                     tc.d.enabled = 1;
                     tc.d.trow = trow;
                     tc.d.ucnt = ucnt;
@@ -1219,6 +1229,15 @@ int sigsdp_solver_debug_cycles(sigsdp_solver* s, int64_t out8[8]) {
     Ctrl hc;
     CK(cudaMemcpy(&hc, s->dtype == SIGSDP_F64 ? s->p64.ctrl : s->p32.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost));
     for (int i = 0; i < 8; ++i) out8[i] = hc.dbg[i];
+    return SIGSDP_OK;
+}
+
+int sigsdp_solver_debug_term_profile(sigsdp_solver* s, double out6[6]) {
+    if (!s || !out6) return fail(SIGSDP_EINVAL, "null argument");
+    CK(cudaSetDevice(s->plan->device));
+    CK(cudaDeviceSynchronize());
+    const double* ht = s->dtype == SIGSDP_F64 ? s->p64.hist_t : s->p32.hist_t;
+    CK(cudaMemcpy(out6, ht + (size_t)(HIST - 1) * 3 - 6, 6 * sizeof(double), cudaMemcpyDeviceToHost));
     return SIGSDP_OK;
 }
 

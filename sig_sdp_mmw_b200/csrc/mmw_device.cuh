@@ -49,6 +49,7 @@ struct TileDev {
     const int* rptr;             // ntiles + 1: runs of consecutive distinct columns
     const int4* runs;            // {first column, first shared-memory slot, length, 0}
     const unsigned short* lcol;  // nnz (+ padding)
+    const int4* trec;            // 2 per tile: {r0, r1, p0, p1}, {run0, run1, distinct columns, 0}
 };
 
 // device-resident controller: reductions that must be order independent use
@@ -334,12 +335,14 @@ __device__ __forceinline__ void mbar_wait_a(unsigned bar, unsigned parity) {
 // on the mbarrier; the compute that follows reads shared memory only.
 template <typename T>
 __device__ __forceinline__ void stage_tile(const Prob<T>& P, const T* src, const T* vals_src, int t, Stage<T>& st,
-                                           long long* wait_cycles = nullptr) {
+                                           long long* wait_cycles = nullptr, long long* prof = nullptr) {
     const long long tc0 = wait_cycles ? clock64() : 0;
     const TileDev& tl = P.tl;
     constexpr int VA = 16 / (int)sizeof(T);   // values per 16 bytes
     __syncthreads();  // every reader of the previous tile is done with the buffers
-    const int p0 = P.g.rowptr[tl.trow[t]], p1 = P.g.rowptr[tl.trow[t + 1]];
+    const long long tc1 = prof ? clock64() : 0;
+    const int4 ra = tl.trec[2 * t], rb = tl.trec[2 * t + 1];   // one load level instead of rowptr[trow[t]] chains
+    const int p0 = ra.z, p1 = ra.w;
     const unsigned rowbytes = (unsigned)(P.Dp * sizeof(T));
     const int pv = p0 & ~(VA - 1), pl = p0 & ~7;
     const unsigned vbytes = vals_src ? (unsigned)(((p1 - pv + VA - 1) & ~(VA - 1)) * sizeof(T)) : 0u;
@@ -347,19 +350,29 @@ __device__ __forceinline__ void stage_tile(const Prob<T>& P, const T* src, const
     st.va = st.vals_a - (unsigned)(pv * (int)sizeof(T));
     st.la = st.lcol_a - (unsigned)(pl * 2);
     if (threadIdx.x == 0) {
-        mbar_expect_tx_a(st.bar_a, (unsigned)tl.ucnt[t] * rowbytes + vbytes + lbytes);
+        mbar_expect_tx_a(st.bar_a, (unsigned)rb.z * rowbytes + vbytes + lbytes);
         bulk_g2s_a(st.lcol_a, tl.lcol + pl, lbytes, st.bar_a);
         if (vals_src) bulk_g2s_a(st.vals_a, vals_src + pv, vbytes, st.bar_a);
     }
     // the row copies are spread over the warps (a bulk copy is a per-warp instruction with
     // uniform operands, so this spreads them over the SM's four schedulers)
-    for (int i = tl.rptr[t] + threadIdx.x; i < tl.rptr[t + 1]; i += NT) {
+    // run i goes to warp i % NWARP, lane i / NWARP: a bulk copy is a per-warp instruction with
+    // uniform operands (a warp issues its lanes' copies one after the other), so the runs
+    // are dealt across the warps first
+    for (int i = rb.x + (threadIdx.x >> 5) + NWARP * (threadIdx.x & 31); i < rb.y; i += NT) {
         const int4 r = tl.runs[i];
         bulk_g2s_a(st.rows_a + (unsigned)r.y * rowbytes, src + (size_t)r.x * P.Dp, (unsigned)r.z * rowbytes, st.bar_a);
     }
+    const long long tc2 = prof ? clock64() : 0;
     mbar_wait_a(st.bar_a, st.parity);
     st.parity ^= 1u;
     if (wait_cycles) *wait_cycles += clock64() - tc0;
+    if (prof) {
+        const long long tc3 = clock64();
+        prof[0] += tc1 - tc0;   // barrier: waiting for the block's slowest warp
+        prof[1] += tc2 - tc1;   // metadata loads + issuing the copies
+        prof[2] += tc3 - tc2;   // waiting for the copies to land
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -909,7 +922,8 @@ __device__ void phase_term_staged(const Prob<T>& P, const Team& team, const T* B
     const long long tph0 = timed ? clock64() : 0;
     fence_proxy_async();   // order this phase's bulk copies after the barrier that published their source
     for (int t = team.rank(); t < tl.ntiles; t += team.size()) {
-        const int r0 = tl.trow[t], r1 = tl.trow[t + 1];
+        const int4 trc = tl.trec[2 * t];
+        const int r0 = trc.x, r1 = trc.y;
         stage_tile(P, Bin, (const T*)P.Aval, t, st, timed ? &wait_c : nullptr);
         for (int kb = r0; kb < r1; kb += R) {   // block-uniform trip count
             const int k = kb + grp;
@@ -996,6 +1010,147 @@ __device__ void phase_term_staged(const Prob<T>& P, const Team& team, const T* B
     }
 }
 
+
+// Variant of phase_term_staged for rows that fill the lane group exactly (Dp == G * VEC,
+// G >= 8): G/2 lanes per row, each lane owns TWO 16-byte chunks of the row (columns
+// [lane*VEC, +VEC) and [(lane + G/2)*VEC, +VEC), so each of its two loads is conflict-free
+// across the group).  The per-non-zero index / value broadcasts are then shared by twice as
+// many columns: 2.5 instead of 3 shared-memory wavefronts and ~30 % fewer instructions per
+// non-zero, and a 64-row tile is one pass of a 512-thread block.
+template <typename T, int G, class Team>
+__device__ void phase_term_staged2(const Prob<T>& P, const Team& team, const T* Bin, T* Bout, double coeff, int slot,
+                                   double* sh, Stage<T>& st) {
+    using V = Vec<T>;
+    using LD = SmemLd<T>;
+    constexpr int VEC = V::N;
+    constexpr int W = (int)sizeof(T);
+    constexpr int GH = G / 2;
+    constexpr int R = NT / GH;
+    const PlanDev& g = P.g;
+    const TileDev& tl = P.tl;
+    const int Dp = P.Dp;
+    const unsigned rowb = (unsigned)(Dp * W);
+    const int lane = threadIdx.x & (GH - 1);
+    const int grp = threadIdx.x / GH;
+    Ctrl* ctrl = P.ctrl;
+    if (team.rank() == 0 && threadIdx.x == 0) {
+        ctrl->nrm_b[(slot + 1) % 3] = 0ull;
+        ctrl->nrm_f[(slot + 1) % 3] = 0ull;
+    }
+    const T cf = (T)coeff;
+    double bmax = 0.0, fmaxv = 0.0, trp = 0.0;
+    const bool timed = team.rank() == 0 && threadIdx.x == 0;
+    long long wait_c = 0;
+    const long long tph0 = timed ? clock64() : 0;
+    const int ca = lane * VEC, cb2 = (lane + GH) * VEC;
+    long long prof[6] = {0, 0, 0, 0, 0, 0};
+    fence_proxy_async();
+    for (int t = team.rank(); t < tl.ntiles; t += team.size()) {
+        const int4 trc = tl.trec[2 * t];
+        const int r0 = trc.x, r1 = trc.y;
+        stage_tile(P, Bin, (const T*)P.Aval, t, st, timed ? &wait_c : nullptr, timed ? prof : nullptr);
+        for (int kb = r0; kb < r1; kb += R) {   // block-uniform trip count
+            const long long tq0 = timed ? clock64() : 0;
+            const int k = kb + grp;
+            const bool valid = k < r1;
+            const int p0 = valid ? g.rowptr[k] : 0, len = valid ? g.rowptr[k + 1] - p0 : 0;
+            if (timed) prof[3] += clock64() - tq0 + (long long)(len & 0);   // row pointer loads
+            const long long tq1 = timed ? clock64() : 0;
+            double rsb = 0.0, rsf = 0.0, dd = 0.0;
+            if (valid) {
+                V fa, fb;
+                fa.load(P.F + (size_t)k * Dp + ca);   // consumed in the epilogue
+                fb.load(P.F + (size_t)k * Dp + cb2);
+                T acca[VEC], accb[VEC];
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) acca[v] = accb[v] = (T)0;
+                const unsigned la = st.la + 2u * (unsigned)p0, va = st.va + (unsigned)(W * p0);
+                const unsigned rba = st.rows_a + (unsigned)(ca * W), rbb = st.rows_a + (unsigned)(cb2 * W);
+                int j = 0;
+                for (; j + 4 <= len; j += 4) {
+                    unsigned lc[4];
+                    T a[4];
+                    V ba[4], bb[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        lc[i] = lds_u16(la + 2u * (unsigned)(j + i)) * rowb;
+                        a[i] = LD::val(va + (unsigned)(W * (j + i)));
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        LD::vec(ba[i], rba + lc[i]);
+                        LD::vec(bb[i], rbb + lc[i]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) {
+                            acca[v] = fma(a[i], ba[i].v[v], acca[v]);
+                            accb[v] = fma(a[i], bb[i].v[v], accb[v]);
+                        }
+                }
+                for (; j < len; ++j) {
+                    const unsigned lc = lds_u16(la + 2u * (unsigned)j) * rowb;
+                    const T a = LD::val(va + (unsigned)(W * j));
+                    V ba, bb;
+                    LD::vec(ba, rba + lc);
+                    LD::vec(bb, rbb + lc);
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) {
+                        acca[v] = fma(a, ba.v[v], acca[v]);
+                        accb[v] = fma(a, bb.v[v], accb[v]);
+                    }
+                }
+                if (timed) prof[4] += clock64() - tq1 + (long long)(acca[0] == (T)12345.678 ? 1 : 0);   // multiply loop
+                V bna, bnb;
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) {
+                    bna.v[v] = cf * acca[v];
+                    bnb.v[v] = cf * accb[v];
+                    fa.v[v] += bna.v[v];
+                    fb.v[v] += bnb.v[v];
+                    rsb += fabs((double)bna.v[v]) + fabs((double)bnb.v[v]);
+                    rsf += fabs((double)fa.v[v]) + fabs((double)fb.v[v]);
+                    dd += (double)fa.v[v] * (double)fa.v[v] + (double)fb.v[v] * (double)fb.v[v];
+                }
+                bna.store(Bout + (size_t)k * Dp + ca);
+                bnb.store(Bout + (size_t)k * Dp + cb2);
+                fa.store(P.F + (size_t)k * Dp + ca);
+                fb.store(P.F + (size_t)k * Dp + cb2);
+            }
+            // all 32 lanes are converged here: xor-shuffles below GH stay inside the group
+#pragma unroll
+            for (int o = GH / 2; o > 0; o >>= 1) {
+                rsb += __shfl_xor_sync(0xffffffffu, rsb, o);
+                rsf += __shfl_xor_sync(0xffffffffu, rsf, o);
+                dd += __shfl_xor_sync(0xffffffffu, dd, o);
+            }
+            bmax = fmax(bmax, rsb);
+            fmaxv = fmax(fmaxv, rsf);
+            if (valid && lane == 0) {
+                P.dsq[k] = dd;
+                trp += dd;
+            }
+        }
+    }
+    bmax = block_max(bmax, sh);
+    fmaxv = block_max(fmaxv, sh);
+    trp = block_sum(trp, sh);
+    if (threadIdx.x == 0) {
+        atomicMax(&ctrl->nrm_b[slot], dkey_pos(bmax));
+        atomicMax(&ctrl->nrm_f[slot], dkey_pos(fmaxv));
+        P.ptr[team.rank()] = trp;
+    }
+    if (timed) {
+        ctrl->dbg[0] += wait_c;
+        ctrl->dbg[1] += clock64() - tph0 - wait_c;
+        if (P.hist_t) {   // diagnostics: cumulative cycle split of block 0 / thread 0 in the last HIST slot
+            double* d = P.hist_t + (size_t)(HIST - 1) * 3 - 6;
+            for (int i = 0; i < 6; ++i) d[i] += (double)prof[i];
+        }
+    }
+}
+
 // Staged Gram: the tile's rows of F (its own rows included: the diagonal is in the
 // pattern) and its local column indices sit in shared memory; one warp per row, one lane
 // per non-zero, each lane accumulates its own dot product over the sketch columns.  No
@@ -1021,7 +1176,8 @@ __device__ void phase_gram_staged(const Prob<T>& P, const Team& team, double* sh
     const long long tph0 = timed ? clock64() : 0;
     fence_proxy_async();
     for (int t = team.rank(); t < tl.ntiles; t += team.size()) {
-        const int r0 = tl.trow[t], r1 = tl.trow[t + 1];
+        const int4 trc = tl.trec[2 * t];
+        const int r0 = trc.x, r1 = trc.y;
         stage_tile(P, (const T*)P.F, (const T*)nullptr, t, st, timed ? &wait_c : nullptr);
         for (int kb = r0; kb < r1; kb += NWARP) {   // block-uniform trip count
             const int k = kb + wrp;
@@ -1218,7 +1374,9 @@ __device__ void run_iterations(const Prob<T>& P, const Team& team, int n_iters, 
             for (int j = 0; j < ts.m_star; ++j) {
                 const int slot = tcount % 3;
                 const double coeff = 1.0 / ((double)ts.s * (double)(j + 1));
-                if (staged)
+                if (staged && G >= 8 && P.Dp == G * Vec<T>::N)
+                    phase_term_staged2<T, G>(P, team, bin, bout, coeff, slot, sh, st);
+                else if (staged)
                     phase_term_staged<T, G>(P, team, bin, bout, coeff, slot, sh, st);
                 else
                     phase_term<T, G>(P, team, bin, bout, coeff, ts.mu, slot, sh);

@@ -491,6 +491,18 @@ void build_tiles(const HostPlan& P, int max_rows, int ucap, int nnzcap, HostTile
         ++t;
     }
     T.ntiles = t;
+    T.trec.resize((size_t)t * 8);
+    for (int i = 0; i < t; ++i) {
+        int32_t* r = T.trec.data() + (size_t)i * 8;
+        r[0] = T.trow[i];
+        r[1] = T.trow[i + 1];
+        r[2] = P.rowptr[T.trow[i]];
+        r[3] = P.rowptr[T.trow[i + 1]];
+        r[4] = T.rptr[i];
+        r[5] = T.rptr[i + 1];
+        r[6] = T.ucnt[i];
+        r[7] = 0;
+    }
     T.ok = true;
 }
 
