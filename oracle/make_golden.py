@@ -184,10 +184,26 @@ def run_binary_search_case(ref):
     print("bs_n75: Z=%d rem=%d probes=%d" % (Z, rem, bs.LOGGED_NP_DATA["bs_search_per_it"].shape[0]))
 
 
+def run_evaluate_case(ref):
+    """env.evaluate_sinr / evaluate_bler (env.py:198-232) of the unmodified reference on two
+    topologies for a fixed random colouring."""
+    out = {}
+    for name, kw in [("a", dict(cell_size=5, sta_density_per_1m2=75e-4, seed=0)),
+                     ("b", dict(cell_size=10, sta_density_per_1m2=75e-4, seed=1))]:
+        e = ref.env(**kw)
+        Z = 9
+        z = np.random.RandomState(3).randint(Z, size=e.n_sta).astype(float)
+        out[name + "_z"], out[name + "_Z"] = z, Z
+        out[name + "_sinr"], out[name + "_bler"] = e.evaluate_sinr(z, Z), e.evaluate_bler(z, Z)
+        out[name + "_kw"] = np.array([kw["cell_size"], kw["sta_density_per_1m2"], kw["seed"]])
+    np.savez_compressed(os.path.join(GOLD, "evaluate_n75_n300.npz"), **out)
+
+
 def main():
     ref = load_reference()
     os.makedirs(GOLD, exist_ok=True)
     run_binary_search_case(ref)
+    run_evaluate_case(ref)
     for c in CASES:
         out = run_case(ref, c)
         path = os.path.join(GOLD, c["name"] + ".npz")

@@ -110,3 +110,83 @@ class sparse_env:
         Q.sort_indices()
         h_max = S_gain.diagonal() / self.min_sinr - 1.
         return S_gain, Q, h_max
+
+    # ---- evaluating a colouring (env.py:198-232) ------------------------------------
+    def _rx_power(self, stas, aps):
+        """Un-thresholded received SNR of stations `stas` at APs `aps` (pairwise arrays),
+        env.py:157-166 (_compute_state_real)."""
+        tree_d0 = self._d0 if hasattr(self, "_d0") else None
+        if tree_d0 is None:
+            tree = cKDTree(self.ap_locs)
+            _, near = tree.query(self.sta_locs, k=1)
+            self._near = near
+            d0 = np.sqrt(((self.sta_locs - self.ap_locs[near]) ** 2).sum(axis=1))
+            smax = -_loss_db(self.fre_Hz, d0)
+            self._txp = 10.0 * math.log10(self.min_sinr) - (smax - NOISE_FLOOR_DBM) + 10.0 * math.log10(self.txp_offset)
+            self._d0 = d0
+        diff = self.sta_locs[stas] - self.ap_locs[aps]
+        dis = np.sqrt(diff[:, 0] * diff[:, 0] + diff[:, 1] * diff[:, 1])
+        return 10 ** ((self._txp[stas] - _loss_db(self.fre_Hz, dis) - NOISE_FLOOR_DBM) / 10.)
+
+    def evaluate_sinr(self, z, Z, exact=None, floor_ratio=3e-2):
+        """SINR of every station under the colouring z (env.py:198-224): signal = own link,
+        interference = power received at the station's AP from every other station of the same
+        slot, noise = 1; among the stations of one AP that share a slot only the strongest keeps
+        its SINR, the others get 1e-3.
+        exact=True sums the interference over ALL same-slot stations like the reference (dense,
+        O(n^2 / Z)); exact=False only over stations whose power at that AP is above
+        floor_ratio * min_s_n_ratio (k-d tree; what makes 100k stations tractable).  Default:
+        exact for n <= 4000."""
+        z = np.asarray(z).astype(np.int64)
+        n = self.n_sta
+        if exact is None:
+            exact = n <= 4000
+        self._rx_power(np.arange(1), np.arange(1))          # initialise power control / association
+        asso = self._near
+        own = self._rx_power(np.arange(n), asso)
+        interf = np.zeros(n)
+        if exact:
+            for zz in range(Z):
+                idx = np.nonzero(z == zz)[0]
+                if idx.size == 0:
+                    continue
+                J, Kk = np.meshgrid(idx, idx, indexing="ij")       # power of j at k's AP
+                M = self._rx_power(J.ravel(), asso[Kk.ravel()]).reshape(idx.size, idx.size)
+                np.fill_diagonal(M, 0.0)
+                interf[idx] = M.sum(axis=0)
+        else:
+            L0 = 20.0 * math.log10(self.fre_Hz / 1e6) + 16 - 28
+            budget = self._txp - NOISE_FLOOR_DBM - 10.0 * math.log10(self.min_s_n_ratio * floor_ratio)
+            reach = 10.0 ** ((budget - L0) / 28.0) - 1.0
+            tree = cKDTree(self.ap_locs)
+            cand = tree.query_ball_point(self.sta_locs, reach)
+            cnt = np.fromiter((len(c) for c in cand), dtype=np.int64, count=n)
+            js = np.repeat(np.arange(n), cnt)
+            aps = np.fromiter((a for c in cand for a in c), dtype=np.int64, count=int(cnt.sum()))
+            pw = self._rx_power(js, aps)
+            # total power per (AP, slot), then subtract the station's own contribution
+            tot = sp.csr_matrix((pw, (aps, z[js])), shape=(self.n_ap, Z))
+            interf = np.asarray(tot[asso, z]).ravel() - own
+            interf = np.maximum(interf, 0.0)
+        sinr = own / (interf + 1.0)
+        # one winner per (AP, slot)
+        # one winner per (AP, slot): the arg-max, first index on exact ties (the reference's
+        # masked argmax).  Stations of one AP have the same power-controlled signal up to
+        # rounding, so their SINRs differ in the last bits only: the exact path reproduces the
+        # reference's pick, the truncated path may pick another, physically equivalent, one.
+        key = asso * Z + z
+        order = np.lexsort((np.arange(n), -sinr, key))
+        first = np.ones(n, dtype=bool)
+        first[1:] = key[order][1:] != key[order][:-1]
+        out = np.full(n, 1e-3)
+        win = order[first]
+        out[win] = sinr[win]
+        return out
+
+    def evaluate_bler(self, z, Z, **kw):
+        """Finite-blocklength block error rate of every station (env.py:226-232)."""
+        snr = self.evaluate_sinr(z, Z, **kw)
+        B, T, L = self.bandwidth, self.slot_time, self.packet_bit
+        nu = -L * math.log(2.) + B * T * np.log(1 + snr)
+        do = np.sqrt(B * T * (1. - 1. / ((1. + snr) ** 2)))
+        return scipy.stats.norm.sf(nu / do)

@@ -215,3 +215,27 @@ def test_sketch_column_shards_equal_single_solver(world, dtype):
         for i in range(nit):
             st.step(om[i])
         np.testing.assert_allclose(a.dual()[0], st.Y, rtol=1e-9)
+
+
+def test_csv_writer_rows(tmp_path):
+    from sig_sdp_mmw_b200.util import CSV_WRITER_OBJECT
+    log = CSV_WRITER_OBJECT(path=str(tmp_path / "run"))
+    log.log_mul_scalar("a", 3, [1.5, 2.5], g_iteration=7)
+    log.log_one_scalar("b", 1, 9.0)
+    log.close()
+    assert open(tmp_path / "run" / "a").read().strip() == "7,3,1.5,2.5"      # [g_it, it, *values] (util.py:242-251)
+    assert open(tmp_path / "run" / "b").read().strip() == "0,1,9.0"
+    CSV_WRITER_OBJECT(path=None).log_mul_scalar("x", 0, [1])                   # path None: no-op
+
+
+@pytest.mark.gpu
+def test_example_driver_runs(tmp_path):
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(os.path.dirname(GOLD), "..", "examples", "sim_mmw_time.py"),
+                          "--cells", "5", "--repeat", "1", "--out", str(tmp_path / "log")],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "cell  5 seed 0" in out.stdout
+    rows = open(tmp_path / "log" / "mmw150-time-5-75").read().strip().split(",")
+    assert len(rows) == 8 and float(rows[2]) > 0

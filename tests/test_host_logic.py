@@ -163,3 +163,18 @@ def test_sparse_topology_large_is_bounded_degree():
     deg = np.diff((S + S.T).tocsr().indptr)
     assert deg.max() < 200 and 10 < deg.mean() < 60
     assert (h > 0).all()
+
+
+@pytest.mark.parametrize("name", ["a", "b"])
+def test_sparse_evaluate_sinr_bler_matches_reference(name):
+    """env.evaluate_sinr / evaluate_bler twins against fixtures from the unmodified reference."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "evaluate_n75_n300.npz"))
+    cs, rho, seed = g[name + "_kw"]
+    e = sparse_env(cell_size=int(cs), sta_density_per_1m2=float(rho), seed=int(seed))
+    z, Z = g[name + "_z"], int(g[name + "_Z"])
+    np.testing.assert_allclose(e.evaluate_sinr(z, Z, exact=True), g[name + "_sinr"], rtol=1e-12)
+    np.testing.assert_allclose(e.evaluate_bler(z, Z, exact=True), g[name + "_bler"], rtol=1e-9, atol=1e-300)
+    # the truncated (k-d tree) evaluation drops only far-field power below 1e-3 x the link
+    # threshold; which of several equal-SINR stations of an AP wins a slot may differ
+    approx = e.evaluate_sinr(z, Z, exact=False)
+    np.testing.assert_allclose(np.sort(approx), np.sort(g[name + "_sinr"]), rtol=1e-2)
