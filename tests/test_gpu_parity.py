@@ -374,3 +374,94 @@ def test_properties_at_5k_nodes():
     for i in range(4):
         st.step(om[i])
     _assert_state_close(sol, st, RTOL64)
+
+
+# ------------------------------------------------------------- ragged / degenerate inputs
+def _synthetic_state(n, seed, p_gain=0.3, groups=3, isolated=0, no_gain=False, no_asso=False):
+    """A state tuple with the reference's structure (positive gains, S diagonal = own link,
+    Q = cliques of stations sharing an AP) but arbitrary sparsity, to exercise ragged cases."""
+    rs = np.random.RandomState(seed)
+    S = sp.random(n, n, density=0.0 if no_gain else p_gain, random_state=rs, format="lil")
+    S = (S * 2.0).tolil()
+    for i in range(n):
+        S[i, i] = 3.0 + rs.rand()
+    grp = rs.randint(groups, size=n)
+    if isolated:
+        S = S.tolil()
+        for i in range(isolated):            # stations with no link to anybody
+            S[i, :] = 0
+            S[:, i] = 0
+            S[i, i] = 3.5
+            grp[i] = groups + i
+    Q = sp.lil_matrix((n, n))
+    if not no_asso:
+        for a in range(groups):
+            idx = np.nonzero(grp == a)[0]
+            for i in idx:
+                for j in idx:
+                    if i != j:
+                        Q[i, j] = 1.0
+    S = S.tocsr()
+    S.eliminate_zeros()
+    S.sort_indices()
+    Q = Q.tocsr()
+    Q.sort_indices()
+    h = S.diagonal() / 1.85 - 1.0
+    return S, Q, h
+
+
+@pytest.mark.parametrize("kw,Z,rr", [
+    (dict(n=2, seed=0, p_gain=1.0, groups=1), 3, 2),            # the smallest graph the solver accepts
+    (dict(n=9, seed=1, p_gain=0.4, groups=2), 5, 1),            # odd sketch width (D = 5, padded rows)
+    (dict(n=40, seed=2, no_asso=True), 4, 2),                   # no association edges at all
+    (dict(n=40, seed=3, no_gain=True, groups=5), 9, 2),         # no interference edges at all
+    (dict(n=60, seed=4, p_gain=0.15, isolated=7), 6, 2),        # isolated stations (diagonal-only rows)
+    (dict(n=33, seed=5, p_gain=0.9, groups=2), 17, 3),          # dense rows, D = 51 > one lane-group pass
+])
+def test_ragged_and_degenerate_graphs_match_oracle(kw, Z, rr):
+    _require_gpu()
+    state = _synthetic_state(**kw)
+    K = state[0].shape[0]
+    D = Z * rr
+    nit = 8
+    om = np.random.RandomState(9).randn(nit, K, D)
+    om_d = torch.from_numpy(om).cuda()
+    p = orc.build_problem(Z, state)
+    st = orc.MMWState(p, 0.05)
+    for i in range(nit):
+        st.step(om[i])
+    for order, tiling in ((0, 0), (1, -1)):
+        plan = _lib.Plan(state, device=0, order=order)
+        assert (plan.E_g, plan.E_a) == (p.E_g, p.E_a)
+        sol = _lib.Solver(plan, Z, D, 0.05, _lib.F64, _lib.MODE_FUSED, tiling)
+        sol.iterate(nit, om_d.data_ptr(), 0, None)
+        torch.cuda.synchronize()
+        _assert_state_close(sol, st, RTOL64)
+    # and the drop-in object end to end (dense eigen path at these sizes)
+    alg = mmw(nit=nit, rank_radio=rr, eta=0.05)
+    np.random.seed(4)
+    ok, X_half = alg.run_with_state(0, Z, state)
+    assert ok and X_half.shape == (K, min(K - 1, (Z - 1) * rr)) and np.isfinite(X_half).all()
+    z, _, rem = alg.rounding(Z, X_half, state)
+    assert z.shape == (K,) and 0 <= rem <= K
+
+
+def test_bad_arguments_raise():
+    _require_gpu()
+    g = load_case("n75_z8")
+    plan = _lib.Plan(g["state"], device=0)
+    with pytest.raises(_lib.SigSdpError):
+        _lib.Solver(plan, 1, 2, 0.1)             # Z < 2
+    with pytest.raises(_lib.SigSdpError):
+        _lib.Solver(plan, 4, 8, -1.0)            # eta <= 0
+    with pytest.raises(_lib.SigSdpError):
+        _lib.Solver(plan, 4, 8, 0.1, 7)          # unknown dtype
+    sol = _lib.Solver(plan, 4, 8, 0.1)
+    with pytest.raises(_lib.SigSdpError):
+        sol.sketch()                             # nothing computed yet
+    with pytest.raises(_lib.SigSdpError):
+        sol.history(5)
+    with pytest.raises(_lib.SigSdpError):
+        sol.split_step(True)                     # not a column shard
+    with pytest.raises(_lib.SigSdpError):
+        _lib.Solver(plan, 4, 4, 0.1, D_total=8, col0=1)   # misaligned shard
