@@ -90,12 +90,17 @@ struct sigsdp_plan {
     DevArena mem;
     // CSR of S^T (diag and explicit zeros dropped), asso-UT edges and h_max in the
     // caller's numbering, for the conflict counter
-    int* d_STp = nullptr;
-    int* d_STi = nullptr;
-    double* d_STx = nullptr;
-    int* d_ai = nullptr;
-    int* d_aj = nullptr;
-    double* d_hmax_caller = nullptr;
+    mutable int* d_STp = nullptr;
+    mutable int* d_STi = nullptr;
+    mutable double* d_STx = nullptr;
+    mutable int* d_ai = nullptr;
+    mutable int* d_aj = nullptr;
+    mutable double* d_hmax_caller = nullptr;
+    // host copy of S / h_max (caller numbering) so that data is only built when the conflict
+    // counter is first used (it is not needed by the solve)
+    std::vector<int32_t> hSp, hSi;
+    std::vector<double> hSx, hh;
+    mutable bool conflict_ready = false;
     // row tiles per (max_rows, ucap, nnzcap), built on first use (see TileDev)
     struct TileCache {
         HostTiles h;
@@ -658,33 +663,11 @@ int sigsdp_plan_create(int64_t n, const int32_t* Sp, const int32_t* Si, const do
     d.h_max = hm;
     d.perm = perm;
     tm.lap("plan upload");
-    // S^T without its diagonal / explicit zeros, caller numbering (rounding.py:56-60)
-    {
-        std::vector<int32_t> sp(n + 1, 0), si;
-        std::vector<double> sx;
-        for (int64_t r = 0; r < n; ++r)
-            for (int32_t q = Sp[r]; q < Sp[r + 1]; ++q)
-                if (Si[q] != r && Sx[q] != 0.0) sp[Si[q] + 1]++;
-        for (int64_t r = 0; r < n; ++r) sp[r + 1] += sp[r];
-        si.resize(sp[n]);
-        sx.resize(sp[n]);
-        std::vector<int32_t> fill(sp.begin(), sp.end() - 1);
-        for (int64_t r = 0; r < n; ++r)
-            for (int32_t q = Sp[r]; q < Sp[r + 1]; ++q)
-                if (Si[q] != r && Sx[q] != 0.0) {
-                    si[fill[Si[q]]] = (int32_t)r;
-                    sx[fill[Si[q]]] = Sx[q];
-                    fill[Si[q]]++;
-                }
-        std::vector<double> hc(h_max, h_max + n);
-        if ((e = pl->mem.upload(&pl->d_STp, sp)) != cudaSuccess) return bail(e, "upload S^T");
-        if ((e = pl->mem.upload(&pl->d_STi, si)) != cudaSuccess) return bail(e, "upload S^T");
-        if ((e = pl->mem.upload(&pl->d_STx, sx)) != cudaSuccess) return bail(e, "upload S^T");
-        if ((e = pl->mem.upload(&pl->d_ai, h.ai)) != cudaSuccess) return bail(e, "upload asso");
-        if ((e = pl->mem.upload(&pl->d_aj, h.aj)) != cudaSuccess) return bail(e, "upload asso");
-        if ((e = pl->mem.upload(&pl->d_hmax_caller, hc)) != cudaSuccess) return bail(e, "upload h_max");
-    }
-    tm.lap("S^T build + upload");
+    pl->hSp.assign(Sp, Sp + n + 1);
+    pl->hSi.assign(Si, Si + Sp[n]);
+    pl->hSx.assign(Sx, Sx + Sp[n]);
+    pl->hh.assign(h_max, h_max + n);
+    tm.lap("host copies");
     *out = pl;
     return SIGSDP_OK;
 }
@@ -1398,10 +1381,50 @@ int sigsdp_round_project(const sigsdp_plan* plan, const double* gX_dev, int r, c
     return SIGSDP_OK;
 }
 
+
+// S^T without its diagonal / explicit zeros, asso-UT edges and h_max in the caller's numbering
+// (rounding.py:56-60), built and uploaded when the conflict counter is first used
+static int ensure_conflict_data(const sigsdp_plan* pl) {
+    if (pl->conflict_ready) return SIGSDP_OK;
+    const int64_t n = pl->h.n;
+    const int32_t* Sp = pl->hSp.data();
+    const int32_t* Si = pl->hSi.data();
+    const double* Sx = pl->hSx.data();
+    std::vector<int32_t> sp(n + 1, 0), si;
+    std::vector<double> sx;
+    for (int64_t r = 0; r < n; ++r)
+        for (int32_t q = Sp[r]; q < Sp[r + 1]; ++q)
+            if (Si[q] != r && Sx[q] != 0.0) sp[Si[q] + 1]++;
+    for (int64_t r = 0; r < n; ++r) sp[r + 1] += sp[r];
+    si.resize(sp[n]);
+    sx.resize(sp[n]);
+    std::vector<int32_t> fill(sp.begin(), sp.end() - 1);
+    for (int64_t r = 0; r < n; ++r)
+        for (int32_t q = Sp[r]; q < Sp[r + 1]; ++q)
+            if (Si[q] != r && Sx[q] != 0.0) {
+                si[fill[Si[q]]] = (int32_t)r;
+                sx[fill[Si[q]]] = Sx[q];
+                fill[Si[q]]++;
+            }
+    DevArena& mem = const_cast<DevArena&>(pl->mem);
+    CK(mem.upload(&pl->d_STp, sp));
+    CK(mem.upload(&pl->d_STi, si));
+    CK(mem.upload(&pl->d_STx, sx));
+    CK(mem.upload(&pl->d_ai, pl->h.ai));
+    CK(mem.upload(&pl->d_aj, pl->h.aj));
+    CK(mem.upload(&pl->d_hmax_caller, pl->hh));
+    pl->conflict_ready = true;
+    return SIGSDP_OK;
+}
+
 int sigsdp_round_conflicts(const sigsdp_plan* plan, const int32_t* z_dev, double* I_dev_or_null, int64_t counts_host[2],
                            void* stream) {
     if (!plan || !z_dev || !counts_host) return fail(SIGSDP_EINVAL, "null argument");
     CK(cudaSetDevice(plan->device));
+    {
+        int rc = ensure_conflict_data(plan);
+        if (rc != SIGSDP_OK) return rc;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     unsigned long long* d_counts = nullptr;
     CK(cudaMalloc(&d_counts, 2 * sizeof(unsigned long long)));

@@ -170,11 +170,11 @@ int build_host_plan(int64_t n, const int32_t* Sp, const int32_t* Si, const doubl
     // ---- T = S^T with association pairs and the diagonal zeroed (mmw.py:28-33)
     std::vector<int32_t> Tp(n + 1, 0), Ti;
     std::vector<double> Tx;
+    std::vector<uint8_t> keep(Sp[n], 0);   // S entries that survive into T (= T^T entries of their own row)
     {
         // S entry (j, i) becomes T[i][j] unless i == j, the value is zero, or Q[i][j] != 0.
         // Q is symmetric (checked above), so Q[i][j] != 0 <=> Q[j][i] != 0: merge S row j with
         // Q row j (both sorted) instead of searching Q row i.
-        std::vector<uint8_t> keep(Sp[n], 0);
         for (int64_t j = 0; j < n; ++j) {
             int32_t qq = Qp[j];
             const int32_t qe = Qp[j + 1];
@@ -201,23 +201,7 @@ int build_host_plan(int64_t n, const int32_t* Sp, const int32_t* Si, const doubl
             }
     }
     P.nnzT = Tp[n];
-    // transpose of T (rows = columns of T), for the symmetric pattern
-    std::vector<int32_t> TTp(n + 1, 0), TTi(Tp[n]);
-    std::vector<double> TTx(Tp[n]);
-    {
-        for (int32_t q = 0; q < Tp[n]; ++q) TTp[Ti[q] + 1]++;
-        for (int64_t i = 0; i < n; ++i) TTp[i + 1] += TTp[i];
-        std::vector<int32_t> fill(TTp.begin(), TTp.end() - 1);
-        for (int64_t i = 0; i < n; ++i)
-            for (int32_t q = Tp[i]; q < Tp[i + 1]; ++q) {
-                int32_t j = Ti[q];
-                TTi[fill[j]] = (int32_t)i;
-                TTx[fill[j]] = Tx[q];
-                fill[j]++;
-            }
-    }
-
-    tm.lap("T and T^T");
+    // T^T needs no second transpose: row i of T^T is row i of S restricted to the kept entries
     // ---- S_sum = T 1 and sqrt((T o T) 1) (mmw.py:34-39)
     std::vector<double> S_sum(n), tnorm(n);
     for (int64_t i = 0; i < n; ++i) {
@@ -235,18 +219,19 @@ int build_host_plan(int64_t n, const int32_t* Sp, const int32_t* Si, const doubl
     // all host cores: pass 1 counts, pass 2 fills.
     auto build_row = [&](int64_t i, std::vector<Ent>& row) -> bool {
         row.clear();
-        int32_t a = Tp[i], ae = Tp[i + 1], b = TTp[i], be = TTp[i + 1], q = Qp[i], qe = Qp[i + 1];
+        int32_t a = Tp[i], ae = Tp[i + 1], b = Sp[i], be = Sp[i + 1], q = Qp[i], qe = Qp[i + 1];
         bool diag_done = false;
         while (true) {
             while (q < qe && Qx[q] == 0.0) ++q;
-            const int32_t ca = a < ae ? Ti[a] : INT32_MAX, cb = b < be ? TTi[b] : INT32_MAX;
+            while (b < be && !keep[b]) ++b;
+            const int32_t ca = a < ae ? Ti[a] : INT32_MAX, cb = b < be ? Si[b] : INT32_MAX;
             const int32_t cq = q < qe ? Qi[q] : INT32_MAX, cd = diag_done ? INT32_MAX : (int32_t)i;
             const int32_t c = std::min(std::min(ca, cb), std::min(cq, cd));
             if (c == INT32_MAX) break;
             int hits = 0;
             Ent e{c, 1, 0.0, 0.0};
             if (ca == c) { e.tf = Tx[a]; ++a; hits |= 1; }
-            if (cb == c) { e.tb = TTx[b]; ++b; hits |= 1; }
+            if (cb == c) { e.tb = Sx[b]; ++b; hits |= 1; }
             if (cq == c) { ++q; hits |= 2; e.kind = 2; }
             if (cd == c) { diag_done = true; hits |= 4; e.kind = 0; }
             if (hits == 1) {
