@@ -138,6 +138,14 @@ struct sigsdp_solver {
     // Lanczos step workspace (allocated on first use)
     double *lz_w = nullptr, *lz_part = nullptr, *lz_h = nullptr, *lz_partn = nullptr;
     int lz_rows = 0;
+    // a restart cycle (same steps on the same buffers every time) is captured once into a CUDA
+    // graph on an internal stream and replayed
+    cudaStream_t lz_stream = nullptr;
+    cudaEvent_t lz_ev_in = nullptr, lz_ev_out = nullptr;
+    cudaGraphExec_t lz_graph = nullptr;
+    const void* lz_key[3] = {nullptr, nullptr, nullptr};
+    int lz_key_j[3] = {0, 0, 0};
+    int lz_seen = 0;   // times the current key was requested
 };
 
 struct sigsdp_batch {
@@ -360,7 +368,7 @@ __global__ void k_symv(PlanDev g, const double* Mval, const double* x, double* y
 //   beta_j = ||w||;  q_{j+1} = w / beta_j
 // Q is (m+1) x n row-major (one basis vector per row), only rows 0..j are read.  Reductions
 // are two-stage with a fixed order (bit-reproducible).
-constexpr int LZ_SLICE = 512;   // elements of w per block in the dot kernel
+constexpr int LZ_SLICE = 256;   // elements of w per block in the dot kernel
 __global__ void k_lz_dot(const double* Q, int n, int nrows, const double* w, double* part, int ldp) {
     __shared__ double ws[LZ_SLICE];
     const int i0 = blockIdx.x * LZ_SLICE;
@@ -368,12 +376,23 @@ __global__ void k_lz_dot(const double* Q, int n, int nrows, const double* w, dou
     for (int i = threadIdx.x; i < cnt; i += blockDim.x) ws[i] = w[i0 + i];
     __syncthreads();
     const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    for (int r = wrp; r < nrows; r += nw) {
+    // two rows per warp iteration: twice the loads in flight
+    for (int r = wrp; r < nrows; r += 2 * nw) {
+        const int r2 = r + nw;
         const double* q = Q + (size_t)r * n + i0;
-        double acc = 0.0;
-        for (int i = lane; i < cnt; i += 32) acc += q[i] * ws[i];
+        const double* q2 = Q + (size_t)(r2 < nrows ? r2 : r) * n + i0;
+        double acc = 0.0, acc2 = 0.0;
+#pragma unroll 4
+        for (int i = lane; i < cnt; i += 32) {
+            acc += q[i] * ws[i];
+            acc2 += q2[i] * ws[i];
+        }
         acc = warp_sum(acc);
-        if (lane == 0) part[(size_t)blockIdx.x * ldp + r] = acc;
+        acc2 = warp_sum(acc2);
+        if (lane == 0) {
+            part[(size_t)blockIdx.x * ldp + r] = acc;
+            if (r2 < nrows) part[(size_t)blockIdx.x * ldp + r2] = acc2;
+        }
     }
 }
 __global__ void k_lz_reduce(const double* part, int nblk, int ldp, int nrows, double* h, double* alpha, int j, int second) {
@@ -392,9 +411,16 @@ __global__ void k_lz_sub(const double* Q, int n, int nrows, const double* h, dou
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double v = 0.0;
     if (i < n) {
-        double acc = 0.0;
-        for (int r = 0; r < nrows; ++r) acc += hs[r] * Q[(size_t)r * n + i];
-        v = w[i] - acc;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int r = 0;
+        for (; r + 4 <= nrows; r += 4) {   // four independent loads in flight per thread
+            a0 += hs[r] * Q[(size_t)r * n + i];
+            a1 += hs[r + 1] * Q[(size_t)(r + 1) * n + i];
+            a2 += hs[r + 2] * Q[(size_t)(r + 2) * n + i];
+            a3 += hs[r + 3] * Q[(size_t)(r + 3) * n + i];
+        }
+        for (; r < nrows; ++r) a0 += hs[r] * Q[(size_t)r * n + i];
+        v = w[i] - ((a0 + a1) + (a2 + a3));
         w[i] = v;
     }
     if (partn) {   // second pass: ||w||^2 partials
@@ -950,6 +976,13 @@ int sigsdp_solver_create_sharded(const sigsdp_plan* plan, int Z, int D_total, in
 void sigsdp_solver_destroy(sigsdp_solver* s) {
     if (!s || s->owned_by_batch) return;
     cudaSetDevice(s->plan->device);
+    if (s->lz_graph) cudaGraphExecDestroy(s->lz_graph);
+    if (s->lz_stream) {
+        cudaStreamSynchronize(s->lz_stream);
+        cudaStreamDestroy(s->lz_stream);
+        cudaEventDestroy(s->lz_ev_in);
+        cudaEventDestroy(s->lz_ev_out);
+    }
     s->mem.release();
     delete s;
 }
@@ -1331,19 +1364,62 @@ int sigsdp_solver_lanczos_steps(sigsdp_solver* s, double* Q_dev, int m, int j0, 
     }
     double* alpha = s->lz_h + s->lz_rows;
     const int ldp = s->lz_rows;
-    for (int j = j0; j < j1; ++j) {
-        const int nrows = j + 1;
-        k_symv<<<s->plan->num_sms * 8, 256, 0, st>>>(s->plan->d, s->Mval, Q_dev + (size_t)j * n, s->lz_w, 1);
-        for (int pass = 0; pass < 2; ++pass) {
-            k_lz_dot<<<nb_dot, 256, 0, st>>>(Q_dev, n, nrows, s->lz_w, s->lz_part, ldp);
-            k_lz_reduce<<<1, 128, 0, st>>>(s->lz_part, nb_dot, ldp, nrows, s->lz_h, alpha, j, pass);
-            k_lz_sub<<<nb_sub, 256, nrows * sizeof(double), st>>>(Q_dev, n, nrows, s->lz_h, s->lz_w,
-                                                                   pass ? s->lz_partn : nullptr);
+    auto enqueue = [&](cudaStream_t q) {
+        for (int j = j0; j < j1; ++j) {
+            const int nrows = j + 1;
+            k_symv<<<s->plan->num_sms * 8, 256, 0, q>>>(s->plan->d, s->Mval, Q_dev + (size_t)j * n, s->lz_w, 1);
+            for (int pass = 0; pass < 2; ++pass) {
+                k_lz_dot<<<nb_dot, 256, 0, q>>>(Q_dev, n, nrows, s->lz_w, s->lz_part, ldp);
+                k_lz_reduce<<<1, 128, 0, q>>>(s->lz_part, nb_dot, ldp, nrows, s->lz_h, alpha, j, pass);
+                k_lz_sub<<<nb_sub, 256, nrows * sizeof(double), q>>>(Q_dev, n, nrows, s->lz_h, s->lz_w,
+                                                                      pass ? s->lz_partn : nullptr);
+            }
+            k_lz_finish<<<nb_sub, 256, 0, q>>>(s->lz_w, n, s->lz_partn, nb_sub, Q_dev + (size_t)(j + 1) * n, alpha,
+                                               alpha_dev, beta_dev, j);
         }
-        k_lz_finish<<<nb_sub, 256, 0, st>>>(s->lz_w, n, s->lz_partn, nb_sub, Q_dev + (size_t)(j + 1) * n, alpha,
-                                            alpha_dev, beta_dev, j);
+    };
+    // identical request as last time (a thick-restart cycle): replay it as a CUDA graph
+    const bool same = s->lz_key[0] == Q_dev && s->lz_key[1] == alpha_dev && s->lz_key[2] == beta_dev &&
+                      s->lz_key_j[0] == j0 && s->lz_key_j[1] == j1 && s->lz_key_j[2] == m;
+    if (!same) {
+        if (s->lz_graph) {
+            cudaGraphExecDestroy(s->lz_graph);
+            s->lz_graph = nullptr;
+        }
+        s->lz_key[0] = Q_dev;
+        s->lz_key[1] = alpha_dev;
+        s->lz_key[2] = beta_dev;
+        s->lz_key_j[0] = j0;
+        s->lz_key_j[1] = j1;
+        s->lz_key_j[2] = m;
+        s->lz_seen = 0;
     }
-    CK(cudaGetLastError());
+    s->lz_seen++;
+    const bool use_graph = s->lz_seen >= 2 && j1 - j0 >= 8 && getenv("SIGSDP_NO_GRAPH") == nullptr;
+    if (!use_graph) {
+        enqueue(st);
+        CK(cudaGetLastError());
+        return SIGSDP_OK;
+    }
+    if (!s->lz_stream) {
+        CK(cudaStreamCreateWithFlags(&s->lz_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&s->lz_ev_in, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&s->lz_ev_out, cudaEventDisableTiming));
+    }
+    if (!s->lz_graph) {
+        cudaGraph_t g = nullptr;
+        CK(cudaStreamBeginCapture(s->lz_stream, cudaStreamCaptureModeThreadLocal));
+        enqueue(s->lz_stream);
+        CK(cudaStreamEndCapture(s->lz_stream, &g));
+        cudaError_t e = cudaGraphInstantiate(&s->lz_graph, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) return fail(SIGSDP_ECUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+    }
+    CK(cudaEventRecord(s->lz_ev_in, st));
+    CK(cudaStreamWaitEvent(s->lz_stream, s->lz_ev_in, 0));
+    CK(cudaGraphLaunch(s->lz_graph, s->lz_stream));
+    CK(cudaEventRecord(s->lz_ev_out, s->lz_stream));
+    CK(cudaStreamWaitEvent(st, s->lz_ev_out, 0));
     return SIGSDP_OK;
 }
 
