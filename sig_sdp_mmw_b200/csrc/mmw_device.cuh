@@ -1167,6 +1167,8 @@ __device__ void phase_gram_staged(const Prob<T>& P, const Team& team, double* sh
     const int K = g.n, Dp = P.Dp;
     const unsigned rowb = (unsigned)(Dp * W);
     const int nc = Dp / VEC;
+    const bool pow2 = (rowb & (rowb - 1u)) == 0u && nc >= 2;
+    const unsigned rmask = rowb - 1u;
     const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
     const bool raw = P.split != 0;
     const double tr = raw ? 1.0 : team_sum(P.ptr, 1, team.size(), sh) / K;
@@ -1197,6 +1199,24 @@ __device__ void phase_gram_staged(const Prob<T>& P, const Team& team, double* sh
                     } else {
                         const unsigned bbase = st.rows_a + lds_u16(st.la + 2u * (unsigned)p) * rowb;
                         T d0 = (T)0, d1 = (T)0;
+                        if (pow2) {   // row bytes are a power of two: the rotation is a mask
+                            unsigned off = (unsigned)(lane * 16) & rmask;
+#pragma unroll 2
+                            for (int s2 = 0; s2 < nc; s2 += 2) {
+                                V a0, b0, a1, b1;
+                                const unsigned off1 = (off + 16u) & rmask;
+                                LD::vec(a0, abase + off);
+                                LD::vec(b0, bbase + off);
+                                LD::vec(a1, abase + off1);
+                                LD::vec(b1, bbase + off1);
+                                off = (off1 + 16u) & rmask;
+#pragma unroll
+                                for (int v = 0; v < VEC; ++v) {
+                                    d0 = fma(a0.v[v], b0.v[v], d0);
+                                    d1 = fma(a1.v[v], b1.v[v], d1);
+                                }
+                            }
+                        } else {
                         int ch = lane % nc;
                         for (int s2 = 0; s2 < nc; s2 += 2) {
                             V a, b;
@@ -1214,6 +1234,7 @@ __device__ void phase_gram_staged(const Prob<T>& P, const Team& team, double* sh
                                 for (int v = 0; v < VEC; ++v) d1 = fma(a.v[v], b.v[v], d1);
                                 ch = ch + 1 == nc ? 0 : ch + 1;
                             }
+                        }
                         }
                         x = ((double)d0 + (double)d1) * inv_tr;
                         rsum += x;
