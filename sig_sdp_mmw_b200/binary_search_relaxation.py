@@ -1,14 +1,31 @@
-"""Outer search over the number of slots Z with the reference's surface
-(sim_src/alg/binary_search_relaxation.py:8-71): `set_bounds`, `run`, `search`, the
-`force_lower_bound` / `force_full_bound` switches and the `bs_*` log rows.  Pure control
-flow around `feasibility_check_alg.run_with_state` / `.rounding`; shipped so the drivers'
-whole call chain can be exercised where the reference tree is not present.  The solver's
-graph plan is Z-independent and cached, so every probe after the first skips the set-up."""
-import math
+"""Outer search for the smallest number of slots Z that the solver + rounding can colour.
 
+Same surface as the reference's driver (sim_src/alg/binary_search_relaxation.py:8-71:
+`feasibility_check_alg`, `force_lower_bound`, `force_full_bound`, `set_bounds`, `run`,
+`search`, log keys `bs_set_bounds`, `bs_search`, `bs_search_per_it`) so scripts written
+against it work with this package where the reference tree is absent.  It is control flow
+only; the window update is written as a small transition function and checked against the
+reference's own probe log (tests/test_driver_chain.py).  The solver keeps its graph plan
+across probes (it does not depend on Z), so only the first probe pays for the set-up."""
 import numpy as np
 
 from .stats import STATS_OBJECT
+
+
+def next_window(left, right, mid, feasible):
+    """One step of the search window [left, right] after probing `mid`.
+
+    feasible (rounding left nobody unassigned): shrink from above while the window is wider
+    than two values, otherwise the probe is the answer.  Infeasible: move the lower end past
+    the probe, or -- once the window has collapsed -- slide it up by one slot.
+    Returns (left, right, finished)."""
+    if feasible:
+        if right - left >= 2:
+            return left, mid, False
+        return left, right, True
+    if left < right:
+        return mid + 1, right, False
+    return left + 1, right + 1, False
 
 
 class binary_search_relaxation(STATS_OBJECT):
@@ -19,54 +36,45 @@ class binary_search_relaxation(STATS_OBJECT):
         self.verbose = False
 
     def set_bounds(self, state):
-        """Lower bound: largest association clique (max row length of Q_asso) + 1; upper bound:
-        max degree of the symmetrised interference graph + 1 (:13-29)."""
-        lb = int(np.max(np.diff(state[1].indptr))) + 1
+        """(lower, upper) for Z.  Lower: the largest group of stations that share an access
+        point needs one slot each, i.e. the longest row of Q_asso plus one.  Upper: one more than
+        the largest degree of the symmetrised interference pattern (entries on the diagonal are
+        stored and counted, as the reference does)."""
+        S_gain, Q_asso = state[0], state[1]
+        lower = int(np.diff(Q_asso.indptr).max()) + 1
         if self.force_lower_bound:
-            return lb, lb
+            return lower, lower
         if self.force_full_bound:
-            return 1, state[0].shape[0]
-        S = state[0] + state[0].transpose()
-        S = S.tocsr()
-        S.setdiag(0)          # stored zeros are kept: the reference counts them too (:22-25)
-        ub = int(np.max(np.diff(S.indptr))) + 1
-        return lb, ub
+            return 1, S_gain.shape[0]
+        sym = (S_gain + S_gain.T).tocsr()
+        sym.setdiag(0)
+        upper = int(np.diff(sym.indptr).max()) + 1
+        return lower, upper
 
     def run(self, state):
-        tic = self._get_tic()
-        left, right = self.set_bounds(state)
-        self._add_np_log("bs_set_bounds", 0, np.array([left, right, self._get_tim(tic)]))
-        tic = self._get_tic()
-        Z, z_vec, rem, it = self.search(left, right, state)
-        self._add_np_log("bs_search", 0, np.array([left, right, Z, rem, it, self._get_tim(tic)]))
+        t = self._get_tic()
+        lo, hi = self.set_bounds(state)
+        self._add_np_log("bs_set_bounds", 0, np.array([lo, hi, self._get_tim(t)]))
+        t = self._get_tic()
+        Z, z_vec, rem, probes = self.search(lo, hi, state)
+        self._add_np_log("bs_search", 0, np.array([lo, hi, Z, rem, probes, self._get_tim(t)]))
         return z_vec, Z, rem
 
     def search(self, left, right, state):
-        it = 0
-        alg = self.feasibility_check_alg
-        while True:
-            mid = math.floor(float(left + right) / 2.)
-            tic = self._get_tic()
-            _, gX = alg.run_with_state(it, mid, state)
-            t_slv = self._get_tim(tic)
-            tic = self._get_tic()
-            z_vec, Z, rem = alg.rounding(mid, gX, state)
-            t_rnd = self._get_tim(tic)
-            self._add_np_log("bs_search_per_it", it, np.array([left, right, mid, Z, rem, t_slv, t_rnd]))
-            it += 1
-            done = False
-            if left < right and rem > 0:
-                left = mid + 1
-            elif left + 1 < right and rem == 0:
-                right = mid
-            elif left + 1 == right and rem == 0:
-                done = True
-            elif left >= right and rem == 0:
-                done = True
-            elif left >= right and rem > 0:
-                left += 1
-                right += 1
+        solver = self.feasibility_check_alg
+        probes = 0
+        finished = False
+        while not finished:
+            mid = (left + right) // 2
+            t = self._get_tic()
+            _, gX = solver.run_with_state(probes, mid, state)
+            us_solve = self._get_tim(t)
+            t = self._get_tic()
+            z_vec, Z, rem = solver.rounding(mid, gX, state)
+            us_round = self._get_tim(t)
+            self._add_np_log("bs_search_per_it", probes, np.array([left, right, mid, Z, rem, us_solve, us_round]))
+            probes += 1
+            left, right, finished = next_window(left, right, mid, rem == 0)
             if self.verbose:
-                self._printalltime(left, right, mid, Z, rem, "++++++++++++++++++++")
-            if done:
-                return Z, z_vec, rem, it
+                self._printalltime(left, right, mid, Z, rem, "+" * 20)
+        return Z, z_vec, rem, probes

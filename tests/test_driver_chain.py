@@ -45,6 +45,32 @@ def test_binary_search_twin_follows_reference_probe_log():
     assert bs.set_bounds(state) == (1, 75)
 
 
+def test_window_update_equals_reference_rule():
+    """next_window against the reference's if/elif chain (binary_search_relaxation.py:58-68),
+    restated here, on every small window and outcome."""
+    import math
+    from sig_sdp_mmw_b200.binary_search_relaxation import next_window
+
+    def ref_rule(left, right, mid, rem):
+        stop = False
+        if left < right and rem > 0:
+            left = mid + 1
+        elif left + 1 < right and rem == 0:
+            right = mid
+        elif left + 1 == right and rem == 0:
+            stop = True
+        elif left >= right and rem == 0:
+            stop = True
+        elif left >= right and rem > 0:
+            left, right = left + 1, right + 1
+        return left, right, stop
+    for left in range(1, 30):
+        for right in range(left - 1, 45):
+            mid = math.floor(float(left + right) / 2.)
+            for rem in (0, 2):
+                assert next_window(left, right, mid, rem == 0) == ref_rule(left, right, mid, rem)
+
+
 def test_column_shards_tile_the_sketch():
     from sig_sdp_mmw_b200.sharded import column_shard
     for D, w, vec in [(32, 8, 2), (32, 4, 2), (64, 8, 4), (26, 2, 2), (32, 1, 2)]:
