@@ -229,6 +229,9 @@ int sigsdp_round_conflicts(const sigsdp_plan* plan, const int32_t* z_dev, double
  * sigsdp_solver_get_* calls); they must share the device, the dtype and the lane width.
  * Omega is always generated on device (instance i uses a stream derived from `seed` and i). */
 int sigsdp_batch_create(sigsdp_solver* const* solvers, int count, sigsdp_batch** out);
+/* Same with explicit instance ids (default: the position in `solvers`): instance id i draws its
+ * Omega from the stream keyed by seed + 0x9E3779B97F4A7C15 * (i + 1), whichever launch it is in. */
+int sigsdp_batch_create_ids(sigsdp_solver* const* solvers, const int64_t* ids, int count, sigsdp_batch** out);
 void sigsdp_batch_destroy(sigsdp_batch* b);
 int sigsdp_batch_iterate(sigsdp_batch* b, int n_iters, uint64_t seed, void* stream);
 

@@ -68,6 +68,7 @@ def load():
         "sigsdp_plan_pattern": [vp, i32p, i32p],
         "sigsdp_debug_normals": [C.c_uint64, C.c_int64, C.c_int, C.c_int, C.c_int, f64p],
         "sigsdp_batch_create": [C.POINTER(vp), C.c_int, C.POINTER(vp)],
+        "sigsdp_batch_create_ids": [C.POINTER(vp), i64p, C.c_int, C.POINTER(vp)],
         "sigsdp_batch_iterate": [vp, C.c_int, C.c_uint64, vp],
         "sigsdp_round_project": [vp, vp, C.c_int, vp, C.c_int, vp, vp, vp],
         "sigsdp_round_greedy": [C.c_int64, C.c_int, i32p, i32p, f64p, i32p, i32p, f64p, f64p, i32p, i32p, i32p, i64p],
@@ -278,11 +279,15 @@ class Solver:
 class Batch:
     """Independent instances advanced together, one thread block each (sigsdp_batch_*)."""
 
-    def __init__(self, solvers):
+    def __init__(self, solvers, ids=None):
         self.solvers = list(solvers)
         arr = (C.c_void_p * len(self.solvers))(*[s.handle for s in self.solvers])
         self.handle = C.c_void_p()
-        check(load().sigsdp_batch_create(arr, len(self.solvers), C.byref(self.handle)))
+        if ids is None:
+            check(load().sigsdp_batch_create(arr, len(self.solvers), C.byref(self.handle)))
+        else:
+            ida = np.ascontiguousarray(ids, dtype=np.int64)
+            check(load().sigsdp_batch_create_ids(arr, _p(ida, C.c_int64), len(self.solvers), C.byref(self.handle)))
 
     def __del__(self):
         try:

@@ -32,11 +32,17 @@ class BatchSolver:
         code = _lib.F64 if dtype in ("float64", "f64") else _lib.F32
         self.plans = [_lib.Plan(st, device=device, order=order) for st in states]
         self.solvers = [_lib.Solver(p, Z, Z * rank_radio, eta, code) for p, Z in zip(self.plans, Zs)]
-        self.batch = _lib.Batch(self.solvers)
+        # one launch per lane-width class (instances with different Z may need different kernels);
+        # every instance keeps the Omega stream of its global index
+        groups = {}
+        for i, s in enumerate(self.solvers):
+            groups.setdefault(s.lanes, []).append(i)
+        self.batches = [_lib.Batch([self.solvers[i] for i in idx], ids=idx) for idx in groups.values()]
         self.Zs, self.rank_radio = list(Zs), rank_radio
 
     def iterate(self, n_iters, seed=0, stream=None):
-        self.batch.iterate(n_iters, seed, stream)
+        for b in self.batches:
+            b.iterate(n_iters, seed, stream)
 
     def total_terms(self):
         return sum(s.total_terms() for s in self.solvers)

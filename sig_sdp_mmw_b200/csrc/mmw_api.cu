@@ -220,8 +220,8 @@ __global__ void __launch_bounds__(NT, 2) k_batch(const Prob<T>* probs, int n_ite
         for (int i = threadIdx.x; i < (int)(sizeof(Prob<T>) / sizeof(int)); i += NT) dst[i] = src[i];
         __syncthreads();
         if (threadIdx.x == 0) {
-            Ps.omega = nullptr;
-            Ps.seed = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(blockIdx.x + 1);
+            Ps.omega = nullptr;   // (the uploaded descriptor carries the instance id in its seed field)
+            Ps.seed = seed + 0x9E3779B97F4A7C15ull * (Ps.seed + 1ull);
         }
         __syncthreads();
     }
@@ -1533,6 +1533,10 @@ static int launch_batch(sigsdp_batch* b, int n_iters, unsigned long long seed, c
 }
 
 int sigsdp_batch_create(sigsdp_solver* const* solvers, int count, sigsdp_batch** out) {
+    return sigsdp_batch_create_ids(solvers, nullptr, count, out);
+}
+
+int sigsdp_batch_create_ids(sigsdp_solver* const* solvers, const int64_t* ids, int count, sigsdp_batch** out) {
     if (!out) return fail(SIGSDP_EINVAL, "out is null");
     *out = nullptr;
     if (!solvers || count < 1) return fail(SIGSDP_EINVAL, "empty batch");
@@ -1552,9 +1556,18 @@ int sigsdp_batch_create(sigsdp_solver* const* solvers, int count, sigsdp_batch**
     cudaSetDevice(b->device);
     const size_t psz = b->dtype == SIGSDP_F64 ? sizeof(Prob<double>) : sizeof(Prob<float>);
     std::vector<unsigned char> host(psz * count);
-    for (int i = 0; i < count; ++i)
-        std::memcpy(host.data() + psz * i,
-                    b->dtype == SIGSDP_F64 ? (const void*)&solvers[i]->p64 : (const void*)&solvers[i]->p32, psz);
+    for (int i = 0; i < count; ++i) {
+        const unsigned long long id = ids ? (unsigned long long)ids[i] : (unsigned long long)i;
+        if (b->dtype == SIGSDP_F64) {
+            Prob<double> p = solvers[i]->p64;
+            p.seed = id;
+            std::memcpy(host.data() + psz * i, &p, psz);
+        } else {
+            Prob<float> p = solvers[i]->p32;
+            p.seed = id;
+            std::memcpy(host.data() + psz * i, &p, psz);
+        }
+    }
     cudaError_t e = cudaMalloc(&b->d_probs, host.size());
     if (e == cudaSuccess) e = cudaMemcpy(b->d_probs, host.data(), host.size(), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {

@@ -89,6 +89,57 @@ class mmw(STATS_OBJECT, sdp_solver):
         lam_min = float(lam[0]) * n
         return np.array([e_max, lam_min, e_max - lam_min])
 
+    def _final_factor(self, solver, Z, nit, torch, dev, stream, seed_offset=0):
+        """X_half = U sqrt(|Lambda|) of the top-r |lambda| eigenpairs of X_avgd / nit
+        (mmw.py:202-216, where svds does it), rows in the caller's numbering."""
+        plan = solver.plan
+        K = plan.n
+        rank = int(min(K - 1, (Z - 1) * self.rank_radio))
+        solver.xavg_matrix(1.0 / nit, stream)
+        if self.omega == "numpy":
+            v0 = torch.from_numpy(np.random.standard_normal(K)).to(dev)   # svds' ARPACK start vector
+        else:
+            g = torch.Generator(device="cpu").manual_seed(int(self.seed) + 1 + seed_offset)
+            v0 = torch.randn(K, dtype=torch.float64, generator=g).to(dev)
+        perm = torch.from_numpy(plan.perm().astype(np.int64)).to(dev)
+        lam, V, info = thick_restart_lanczos(self._matmat(solver, torch, dev), K, rank, "LM", v0[perm], tol=self.eig_tol,
+                                            native_steps=self._native_steps(solver, torch))
+        self.last_eig_info = info
+        X_half_int = V * torch.sqrt(lam.abs())[None, :]
+        X_half = torch.empty_like(X_half_int)
+        X_half[perm] = X_half_int                              # internal -> caller numbering
+        self.last_singular_values = lam.abs().cpu().numpy()
+        return X_half.cpu().numpy()
+
+    def run_many_with_states(self, Zs, states):
+        """Monte-Carlo sweeps (the drivers' `for seed in range(REPEAT)` loops): every
+        (Z, state) pair solved in ONE batched launch, one thread block per instance, Omega
+        generated on device.  Returns the list of X_half factors (same as calling
+        run_with_state on each with omega="device")."""
+        import torch
+        from .batch import BatchSolver
+        if not torch.cuda.is_available():
+            raise _lib.SigSdpError("no CUDA device: sig_sdp_mmw_b200 has no CPU fallback")
+        tic = self._get_tic()
+        dev = torch.device("cuda", self.device)
+        nit = int(self.nit)
+        keep_omega = self.omega
+        self.omega = "device"
+        try:
+            with torch.cuda.device(dev):
+                stream = torch.cuda.current_stream().cuda_stream
+                bs = BatchSolver(states, Zs, self.eta, rank_radio=self.rank_radio, dtype=self.dtype,
+                                 device=self.device, order=self.plan_order)
+                bs.iterate(nit, seed=self.seed, stream=stream)
+                torch.cuda.current_stream().synchronize()
+                out = [self._final_factor(sol, Z, nit, torch, dev, stream, seed_offset=i)
+                       for i, (sol, Z) in enumerate(zip(bs.solvers, bs.Zs))]
+        finally:
+            self.omega = keep_omega
+        self.last_batch = bs
+        self._add_np_log("mmw_batch", 0, np.array([len(states), nit, self._get_tim(tic)]))
+        return out
+
     def _run(self, Z, state):
         import torch
         if not torch.cuda.is_available():
@@ -147,21 +198,6 @@ class mmw(STATS_OBJECT, sdp_solver):
 
             # final factor (mmw.py:202-216): top-r |lambda| eigenpairs of X_avgd / nit
             tic_xavg = self._get_tic()
-            rank = int(min(K - 1, (Z - 1) * self.rank_radio))
-            solver.xavg_matrix(1.0 / nit, stream)
-            if self.omega == "numpy":
-                v0 = torch.from_numpy(np.random.standard_normal(K)).to(dev)   # svds' ARPACK start vector
-            else:
-                g = torch.Generator(device="cpu").manual_seed(int(self.seed) + 1)
-                v0 = torch.randn(K, dtype=torch.float64, generator=g).to(dev)
-            perm = torch.from_numpy(plan.perm().astype(np.int64)).to(dev)
-            lam, V, info = thick_restart_lanczos(self._matmat(solver, torch, dev), K, rank, "LM", v0[perm], tol=self.eig_tol,
-                                                native_steps=self._native_steps(solver, torch))
-            self.last_eig_info = info
-            X_half_int = V * torch.sqrt(lam.abs())[None, :]
-            X_half = torch.empty_like(X_half_int)
-            X_half[perm] = X_half_int                              # internal -> caller numbering
-            X_half = X_half.cpu().numpy()
-            self.last_singular_values = lam.abs().cpu().numpy()
+            X_half = self._final_factor(solver, Z, nit, torch, dev, stream)
             self._add_np_log("mmw_xavg", 0, np.array([Z, K, self._get_tim(tic_xavg)]))
         return True, X_half

@@ -265,3 +265,33 @@ def test_example_driver_runs(tmp_path):
     assert "cell  5 seed 0" in out.stdout
     rows = open(tmp_path / "log" / "mmw150-time-5-75").read().strip().split(",")
     assert len(rows) == 8 and float(rows[2]) > 0
+
+
+@pytest.mark.gpu
+def test_run_many_with_states_equals_single_runs():
+    """The batched drop-in call gives, instance by instance, the factor a standalone solver
+    produces for the same device Omega stream (Gram of X_half; column signs are arbitrary)."""
+    import torch
+    from sig_sdp_mmw_b200 import _lib, mmw
+    from sig_sdp_mmw_b200.topology import sparse_env
+    states = [sparse_env(cell_size=5 + (i % 2), sta_density_per_1m2=75e-4, seed=10 + i).generate_S_Q_hmax() for i in range(4)]
+    Zs = [8, 9, 8, 10]
+    alg = mmw(nit=20, eta=0.04, seed=3)
+    outs = alg.run_many_with_states(Zs, states)
+    assert alg.LOGGED_NP_DATA["mmw_batch"].shape == (1, 6)
+    for i, (st, Z, Xh) in enumerate(zip(states, Zs, outs)):
+        K = st[0].shape[0]
+        assert Xh.shape == (K, min(K - 1, (Z - 1) * 2))
+        plan = _lib.Plan(st, device=0, order=1)
+        sol = _lib.Solver(plan, Z, 2 * Z, 0.04)
+        sol.iterate(20, None, instance_seed(3, i), None)
+        torch.cuda.synchronize()
+        Xd, Xg, Xa = sol.X(True)
+        bd, bg, ba = alg.last_batch.solvers[i].X(True)
+        np.testing.assert_allclose(bd, Xd, rtol=1e-10)
+        np.testing.assert_allclose(bg, Xg, rtol=1e-9, atol=1e-12)
+        # the factor reproduces the top-r part of X_avgd / nit: compare with a dense eig of it
+        from oracle import mmw_oracle as orc
+        p = orc.build_problem(Z, st)
+        ref_half, _ = orc.final_factor(p, Xd, Xg, Xa, 20, 2)
+        np.testing.assert_allclose(Xh @ Xh.T, ref_half @ ref_half.T, atol=1e-8)
