@@ -38,6 +38,9 @@ CASES = [
          Z=4, nit=150, eta=0.04, rank_radio=2, log_gap=False, seed=0, trace=False),
     dict(name="n500_z13", env=dict(cell_size=10, sta_density_per_1m2=125e-4, seed=0),
          Z=13, nit=60, eta=0.04, rank_radio=2, log_gap=False, seed=2, trace=False),
+    # the instance size of BASELINE configs[4] (1,000-node Monte-Carlo instances)
+    dict(name="n1000_z8", env=dict(cell_size=20, sta_density_per_1m2=6.25e-3, seed=4),
+         Z=8, nit=40, eta=0.04, rank_radio=2, log_gap=False, seed=9, trace=False),
 ]
 
 

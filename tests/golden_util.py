@@ -7,7 +7,7 @@ import scipy.sparse as sp
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = os.path.join(ROOT, "tests", "golden")
-CASES = ["n75_z8", "n75_z6_rr3", "n300_z10", "n500_z4_cfg1", "n500_z13"]
+CASES = ["n75_z8", "n75_z6_rr3", "n300_z10", "n500_z4_cfg1", "n500_z13", "n1000_z8"]
 
 
 def load_case(name):
