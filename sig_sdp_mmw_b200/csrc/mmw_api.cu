@@ -809,7 +809,7 @@ static int solver_alloc(sigsdp_solver* s) {
     CK(s->mem.alloc(&P.hist_nt, HIST));
     CK(s->mem.alloc(&P.hist_a1, HIST));
     CK(s->mem.alloc(&P.hist_mu, HIST));
-    CK(s->mem.alloc(&P.hist_t, (size_t)HIST * 3));
+    CK(s->mem.alloc(&P.hist_t, (size_t)HIST * 3 + 8));
     P.omega = nullptr;
     P.seed = 0;
     tm.lap("solver alloc");
@@ -911,7 +911,7 @@ static int solver_reset_impl(sigsdp_solver* s, cudaStream_t st) {
     CK(cudaMemsetAsync(P.hist_nt, 0, HIST * sizeof(int), st));
     CK(cudaMemsetAsync(P.hist_a1, 0, HIST * sizeof(double), st));
     CK(cudaMemsetAsync(P.hist_mu, 0, HIST * sizeof(double), st));
-    CK(cudaMemsetAsync(P.hist_t, 0, (size_t)HIST * 3 * sizeof(double), st));
+    CK(cudaMemsetAsync(P.hist_t, 0, ((size_t)HIST * 3 + 8) * sizeof(double), st));
     k_fill<double><<<64, 256, 0, st>>>(P.Y, (size_t)s->C, 1.0 / (double)s->C);  // Y = 1/C (mmw.py:62)
     k_set_diag<<<64, 256, 0, st>>>(P.Xv, P.g.dpos, (int)n, 1.0);                // X = I   (mmw.py:67)
     CK(cudaGetLastError());
@@ -1253,7 +1253,7 @@ int sigsdp_solver_debug_term_profile(sigsdp_solver* s, double out6[6]) {
     CK(cudaSetDevice(s->plan->device));
     CK(cudaDeviceSynchronize());
     const double* ht = s->dtype == SIGSDP_F64 ? s->p64.hist_t : s->p32.hist_t;
-    CK(cudaMemcpy(out6, ht + (size_t)(HIST - 1) * 3 - 6, 6 * sizeof(double), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(out6, ht + (size_t)HIST * 3, 6 * sizeof(double), cudaMemcpyDeviceToHost));
     return SIGSDP_OK;
 }
 

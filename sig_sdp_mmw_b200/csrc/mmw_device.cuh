@@ -1145,7 +1145,7 @@ __device__ void phase_term_staged2(const Prob<T>& P, const Team& team, const T* 
         ctrl->dbg[0] += wait_c;
         ctrl->dbg[1] += clock64() - tph0 - wait_c;
         if (P.hist_t) {   // diagnostics: cumulative cycle split of block 0 / thread 0 in the last HIST slot
-            double* d = P.hist_t + (size_t)(HIST - 1) * 3 - 6;
+            double* d = P.hist_t + (size_t)HIST * 3;   // 8 diagnostic slots behind the ring
             for (int i = 0; i < 6; ++i) d[i] += (double)prof[i];
         }
     }
