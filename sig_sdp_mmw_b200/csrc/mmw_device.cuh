@@ -478,18 +478,34 @@ __device__ void phase_dual(const Prob<T>& P, const Team& team, double* sh) {
     for (int t = team.rank(); t < ntiles; t += team.size()) {
         const int k = t * R + grp;
         if (k < K) {
+            // every load of the row is issued before the first use: the phase is bound by
+            // memory latency, not bytes, so what counts is the number of loads in flight
+            const int pa = g.rowptr[k], p1 = g.rowptr[k + 1];
+            double hm = 0.0, ssum = 0.0, nh = 1.0, xd = 0.0, ea = 0.0, eb = 0.0;
+            if (lane == 0) {
+                hm = g.h_max[k];
+                ssum = g.S_sum[k];
+                nh = P.nH[k];
+                xd = P.Xv[g.dpos[k]];
+                ea = P.e_acc[k];
+                eb = P.e_acc[K + g.E_a + k];
+            }
             double acc = 0.0;
-            const int p1 = g.rowptr[k + 1];
-            for (int p = g.rowptr[k] + lane; p < p1; p += G) {
-                double tf = g.tfwd[p];
-                if (tf != 0.0) acc += tf * P.r[g.col[p]];
+            for (int p = pa + lane; p < p1; p += 2 * G) {
+                const bool hb = p + G < p1;
+                const int pb = hb ? p + G : p;
+                const double tf0 = g.tfwd[p], tf1 = g.tfwd[pb];
+                const int c0 = g.col[p], c1 = g.col[pb];
+                const double r0 = P.r[c0], r1 = P.r[c1];
+                if (tf0 != 0.0) acc += tf0 * r0;
+                if (hb && tf1 != 0.0) acc += tf1 * r1;
             }
             acc = group_sum<G>(tile, acc);
             if (lane == 0) {
-                double eH = (acc * zr - (g.h_max[k] - g.S_sum[k] / Z)) / P.nH[k];
-                double eD = (P.Xv[g.dpos[k]] - 1.0) * invD;
-                double a = P.e_acc[k] + P.eta * eD;
-                double b = P.e_acc[K + g.E_a + k] + P.eta * eH;
+                double eH = (acc * zr - (hm - ssum / Z)) / nh;
+                double eD = (xd - 1.0) * invD;
+                double a = ea + P.eta * eD;
+                double b = eb + P.eta * eH;
                 P.e_acc[k] = a;
                 P.e_acc[K + g.E_a + k] = b;
                 emax = fmax(emax, fmax(a, b));
@@ -606,23 +622,52 @@ __device__ void phase_loss(const Prob<T>& P, const Team& team, int it_local, dou
             const double wk = P.q[k] * invS;
             double rowabs = 0.0;
             const int p1 = g.rowptr[k + 1];
-            for (int p = g.rowptr[k] + lane; p < p1; p += G) {
-                const int e = g.eid[p];
-                double l, shift = 0.0;
-                if (e < 0) {
-                    l = (P.u[k] * invS - sumYD / K) * invD + cLF - cLH;
-                    shift = mu;
-                } else if (e < g.E_g) {
-                    const double wc = P.q[g.col[p]] * invS;
-                    l = gcoef * (g.tfwd[p] * wc + g.tbwd[p] * wk);
-                } else {
-                    l = P.u[K + (e - g.E_g)] * aF;
+            const double ldiag = (P.u[k] * invS - sumYD / K) * invD + cLF - cLH;
+            // two non-zeros per lane and trip, all their loads issued before the first use
+            // (latency-bound phase: loads in flight are what counts)
+            for (int p = g.rowptr[k] + lane; p < p1; p += 2 * G) {
+                const bool hb = p + G < p1;
+                const int pb = hb ? p + G : p;
+                const int e0 = g.eid[p], e1 = g.eid[pb];
+                const int c0 = g.col[p], c1 = g.col[pb];
+                const double tf0 = g.tfwd[p], tf1 = g.tfwd[pb];
+                const double tb0 = g.tbwd[p], tb1 = g.tbwd[pb];
+                const double lv0 = P.Lval[p], lv1 = P.Lval[pb];
+                const double q0 = P.q[c0], q1 = P.q[c1];
+                const double ua0 = e0 >= g.E_g ? P.u[K + (e0 - g.E_g)] : 0.0;
+                const double ua1 = e1 >= g.E_g ? P.u[K + (e1 - g.E_g)] : 0.0;
+                {
+                    double l, shift = 0.0;
+                    if (e0 < 0) {
+                        l = ldiag;
+                        shift = mu;
+                    } else if (e0 < g.E_g) {
+                        l = gcoef * (tf0 * (q0 * invS) + tb0 * wk);
+                    } else {
+                        l = ua0 * aF;
+                    }
+                    const double v = lv0 - eta * l;
+                    P.Lval[p] = v;
+                    const double a = 0.5 * v - shift;
+                    P.Aval[p] = (T)a;
+                    rowabs += fabs(a);
                 }
-                const double v = P.Lval[p] - eta * l;
-                P.Lval[p] = v;
-                const double a = 0.5 * v - shift;
-                P.Aval[p] = (T)a;
-                rowabs += fabs(a);
+                if (hb) {
+                    double l, shift = 0.0;
+                    if (e1 < 0) {
+                        l = ldiag;
+                        shift = mu;
+                    } else if (e1 < g.E_g) {
+                        l = gcoef * (tf1 * (q1 * invS) + tb1 * wk);
+                    } else {
+                        l = ua1 * aF;
+                    }
+                    const double v = lv1 - eta * l;
+                    P.Lval[pb] = v;
+                    const double a = 0.5 * v - shift;
+                    P.Aval[pb] = (T)a;
+                    rowabs += fabs(a);
+                }
             }
             rowabs = group_sum<G>(tile, rowabs);
             a1 = fmax(a1, rowabs);
@@ -656,6 +701,10 @@ __device__ void phase_loss(const Prob<T>& P, const Team& team, int it_local, dou
 #pragma unroll
                     for (int v = 0; v < VEC; ++v) ss += (double)raw[v] * (double)raw[v];
                 }
+            const bool one = Dp == G * VEC;
+            V w0;
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) w0.v[v] = (T)0;
             for (int c0 = lane * VEC; c0 < Dp; c0 += G * VEC) {
                 T raw[VEC];
                 if (P.omega) {
@@ -669,17 +718,16 @@ __device__ void phase_loss(const Prob<T>& P, const Team& team, int it_local, dou
                 }
 #pragma unroll
                 for (int v = 0; v < VEC; ++v) ss += (double)raw[v] * (double)raw[v];
-                V w;
 #pragma unroll
-                for (int v = 0; v < VEC; ++v) w.v[v] = raw[v];
-                w.store(P.B0 + (size_t)k * Dp + c0);  // unnormalised for now
+                for (int v = 0; v < VEC; ++v) w0.v[v] = raw[v];
+                if (!one) w0.store(P.B0 + (size_t)k * Dp + c0);  // unnormalised for now
             }
             ss = group_sum<G>(tile, ss);
             const double nrm = sqrt(ss);
             double rs = 0.0, dd = 0.0;
             for (int c0 = lane * VEC; c0 < Dp; c0 += G * VEC) {
-                V w;
-                w.load(P.B0 + (size_t)k * Dp + c0);
+                V w = w0;   // one chunk per lane: the row never leaves the registers
+                if (!one) w.load(P.B0 + (size_t)k * Dp + c0);
 #pragma unroll
                 for (int v = 0; v < VEC; ++v) {
                     w.v[v] = (T)((double)w.v[v] / nrm);
