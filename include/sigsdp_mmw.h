@@ -167,6 +167,10 @@ int sigsdp_solver_debug_term_profile(sigsdp_solver* s, double out6[6]);
 /* total Taylor terms (SpMM passes) executed since create/reset */
 int sigsdp_solver_total_terms(sigsdp_solver* s, int64_t* out);
 
+/* Row-tile statistics of a plan for given caps (host only, no device needed): tiles, bulk-copy
+ * runs, staged rows (incl. gap rows), max staged rows / non-zeros of a tile, nnz. */
+int sigsdp_plan_tile_stats(sigsdp_plan* p, int max_rows, int ucap, int nnzcap, int64_t out6[6]);
+
 /* Standard normals of the throughput-mode generator (Philox4x32-10 + Box-Muller),
  * n x D row-major, for testing its moments.  Synchronising. */
 int sigsdp_debug_normals(uint64_t seed, int64_t iter, int n, int D, int dtype, double* out_host);

@@ -66,6 +66,7 @@ def load():
         "sigsdp_solver_get_matrix": [vp, f64p],
         "sigsdp_solver_lanczos_steps": [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp],
         "sigsdp_plan_pattern": [vp, i32p, i32p],
+        "sigsdp_plan_tile_stats": [vp, C.c_int, C.c_int, C.c_int, i64p],
         "sigsdp_debug_normals": [C.c_uint64, C.c_int64, C.c_int, C.c_int, C.c_int, f64p],
         "sigsdp_batch_create": [C.POINTER(vp), C.c_int, C.POINTER(vp)],
         "sigsdp_batch_create_ids": [C.POINTER(vp), i64p, C.c_int, C.POINTER(vp)],
@@ -150,6 +151,13 @@ class Plan:
         p = np.empty(self.n, np.int32)
         check(load().sigsdp_plan_perm(self.handle, _p(p, C.c_int32)))
         return p
+
+    def tile_stats(self, max_rows, ucap, nnzcap):
+        """Row-tile statistics for the given caps (host only): dict of tiles, runs (bulk copies),
+        staged rows, the largest tile's staged rows / non-zeros, nnz."""
+        out = np.zeros(6, np.int64)
+        check(load().sigsdp_plan_tile_stats(self.handle, max_rows, ucap, nnzcap, _p(out, C.c_int64)))
+        return dict(zip(["tiles", "runs", "staged_rows", "umax", "nnzmax", "nnz"], out.tolist()))
 
     def pattern(self):
         rp = np.empty(self.n + 1, np.int32); col = np.empty(self.nnz, np.int32)

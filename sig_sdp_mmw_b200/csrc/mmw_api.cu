@@ -1267,6 +1267,22 @@ int sigsdp_solver_total_terms(sigsdp_solver* s, int64_t* out) {
     return SIGSDP_OK;
 }
 
+int sigsdp_plan_tile_stats(sigsdp_plan* p, int max_rows, int ucap, int nnzcap, int64_t out6[6]) {
+    if (!p || !out6 || max_rows <= 0 || ucap <= 0 || nnzcap <= 0) return fail(SIGSDP_EINVAL, "bad argument");
+    HostTiles t;
+    build_tiles(p->h, max_rows, ucap, nnzcap, t);
+    if (!t.ok) return fail(SIGSDP_EINVAL, "a row exceeds the tile caps");
+    int64_t copied = 0;
+    for (int32_t u : t.ucnt) copied += u;
+    out6[0] = t.ntiles;
+    out6[1] = (int64_t)t.runs.size() / 4;
+    out6[2] = copied;
+    out6[3] = t.umax;
+    out6[4] = t.nnzmax;
+    out6[5] = p->h.nnz;
+    return SIGSDP_OK;
+}
+
 int sigsdp_debug_normals(uint64_t seed, int64_t iter, int n, int D, int dtype, double* out_host) {
     if (!out_host || n <= 0 || D <= 0) return fail(SIGSDP_EINVAL, "bad argument");
     double* d = nullptr;

@@ -696,7 +696,7 @@ __device__ void phase_loss(const Prob<T>& P, const Team& team, int it_local, dou
                     } else {
                         philox_normals(P.seed, iter, ko, c0 / VEC, raw);
 #pragma unroll
-                        for (int v = 0; v < VEC; ++v) raw[v] = (c0 + v < Dtot) ? (T)((double)raw[v] / sqrtD) : (T)0;
+                        for (int v = 0; v < VEC; ++v) raw[v] = (c0 + v < Dtot) ? raw[v] : (T)0;   // 1/sqrt(D) cancels below
                     }
 #pragma unroll
                     for (int v = 0; v < VEC; ++v) ss += (double)raw[v] * (double)raw[v];
@@ -714,7 +714,7 @@ __device__ void phase_loss(const Prob<T>& P, const Team& team, int it_local, dou
                 } else {
                     philox_normals(P.seed, iter, ko, (col0 + c0) / VEC, raw);
 #pragma unroll
-                    for (int v = 0; v < VEC; ++v) raw[v] = (c0 + v < D) ? (T)((double)raw[v] / sqrtD) : (T)0;
+                    for (int v = 0; v < VEC; ++v) raw[v] = (c0 + v < D) ? raw[v] : (T)0;
                 }
 #pragma unroll
                 for (int v = 0; v < VEC; ++v) ss += (double)raw[v] * (double)raw[v];
@@ -723,14 +723,18 @@ __device__ void phase_loss(const Prob<T>& P, const Team& team, int it_local, dou
                 if (!one) w0.store(P.B0 + (size_t)k * Dp + c0);  // unnormalised for now
             }
             ss = group_sum<G>(tile, ss);
-            const double nrm = sqrt(ss);
+            // Omega from the caller: the reference's arithmetic (randn / sqrt(D), row / its norm).
+            // Device generator: the 1/sqrt(D) cancels and one reciprocal square root scales the row.
+            const bool host_omega = P.omega != nullptr;
+            const double nrm = host_omega ? sqrt(ss) : 1.0;
+            const double inrm = host_omega ? 1.0 : rsqrt(ss);
             double rs = 0.0, dd = 0.0;
             for (int c0 = lane * VEC; c0 < Dp; c0 += G * VEC) {
                 V w = w0;   // one chunk per lane: the row never leaves the registers
                 if (!one) w.load(P.B0 + (size_t)k * Dp + c0);
 #pragma unroll
                 for (int v = 0; v < VEC; ++v) {
-                    w.v[v] = (T)((double)w.v[v] / nrm);
+                    w.v[v] = host_omega ? (T)((double)w.v[v] / nrm) : (T)((double)w.v[v] * inrm);
                     rs += fabs((double)w.v[v]);
                     dd += (double)w.v[v] * (double)w.v[v];
                 }

@@ -79,6 +79,23 @@ def test_plan_locality_order_is_a_relabelling(order):
     assert abs(P @ U0 @ P.T - U1).nnz == 0
 
 
+def test_tile_stats_respect_the_caps():
+    """Row tiles (HostTiles, plan_host.h): every row lands in exactly one tile, the staged rows
+    cover at least the distinct columns and no tile exceeds the caps."""
+    g = load_case("n1000_z8")
+    pl = _lib.Plan(g["state"], device=-1, order=1)
+    rp, col = pl.pattern()
+    st = pl.tile_stats(32, 200, 1024)
+    assert st["nnz"] == pl.nnz == rp[-1]
+    assert st["tiles"] >= -(-pl.n // 32)
+    assert st["umax"] <= 200 and st["nnzmax"] <= 1024
+    assert 0 < st["runs"] <= st["staged_rows"]
+    one_row = pl.tile_stats(1, 200, 1024)
+    assert one_row["tiles"] == pl.n and one_row["nnzmax"] == int(np.diff(rp).max())
+    with pytest.raises(RuntimeError):
+        pl.tile_stats(32, 4, 1024)      # a single row has more neighbours than the cap
+
+
 def test_plan_rejects_bad_input():
     g = load_case("n75_z8")
     S, Q, h = g["state"]
