@@ -67,8 +67,8 @@ struct DevArena {
         *p = (U*)q;
         return e;
     }
-    template <typename U>
-    cudaError_t upload(U** p, const std::vector<U>& v) {
+    template <typename U, typename A>
+    cudaError_t upload(U** p, const std::vector<U, A>& v) {
         cudaError_t e = alloc(p, v.size());
         if (e != cudaSuccess) return e;
         if (!v.empty()) e = cudaMemcpy(*p, v.data(), v.size() * sizeof(U), cudaMemcpyHostToDevice);
@@ -389,16 +389,20 @@ __global__ void k_lz_dot(const double* Q, int n, int nrows, const double* w, dou
         }
         acc = warp_sum(acc);
         acc2 = warp_sum(acc2);
-        if (lane == 0) {
-            part[(size_t)blockIdx.x * ldp + r] = acc;
-            if (r2 < nrows) part[(size_t)blockIdx.x * ldp + r2] = acc2;
+        if (lane == 0) {   // partials of one basis row are contiguous: the reduction reads them coalesced
+            part[(size_t)r * ldp + blockIdx.x] = acc;
+            if (r2 < nrows) part[(size_t)r2 * ldp + blockIdx.x] = acc2;
         }
     }
 }
+// one warp per basis row; lanes stride over the slices, fixed order
 __global__ void k_lz_reduce(const double* part, int nblk, int ldp, int nrows, double* h, double* alpha, int j, int second) {
-    for (int r = threadIdx.x; r < nrows; r += blockDim.x) {
-        double acc = 0.0;
-        for (int b = 0; b < nblk; ++b) acc += part[(size_t)b * ldp + r];
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (r >= nrows) return;
+    double acc = 0.0;
+    for (int b = lane; b < nblk; b += 32) acc += part[(size_t)r * ldp + b];
+    acc = warp_sum(acc);
+    if (lane == 0) {
         h[r] = acc;
         if (r == j) *alpha = second ? *alpha + acc : acc;
     }
@@ -1379,14 +1383,14 @@ int sigsdp_solver_lanczos_steps(sigsdp_solver* s, double* Q_dev, int m, int j0, 
         s->lz_rows = m + 1;
     }
     double* alpha = s->lz_h + s->lz_rows;
-    const int ldp = s->lz_rows;
+    const int ldp = nb_dot;
     auto enqueue = [&](cudaStream_t q) {
         for (int j = j0; j < j1; ++j) {
             const int nrows = j + 1;
             k_symv<<<s->plan->num_sms * 8, 256, 0, q>>>(s->plan->d, s->Mval, Q_dev + (size_t)j * n, s->lz_w, 1);
             for (int pass = 0; pass < 2; ++pass) {
                 k_lz_dot<<<nb_dot, 256, 0, q>>>(Q_dev, n, nrows, s->lz_w, s->lz_part, ldp);
-                k_lz_reduce<<<1, 128, 0, q>>>(s->lz_part, nb_dot, ldp, nrows, s->lz_h, alpha, j, pass);
+                k_lz_reduce<<<(nrows + 7) / 8, 256, 0, q>>>(s->lz_part, nb_dot, ldp, nrows, s->lz_h, alpha, j, pass);
                 k_lz_sub<<<nb_sub, 256, nrows * sizeof(double), q>>>(Q_dev, n, nrows, s->lz_h, s->lz_w,
                                                                       pass ? s->lz_partn : nullptr);
             }

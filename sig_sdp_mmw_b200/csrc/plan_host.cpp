@@ -5,6 +5,7 @@
 #include "plan_host.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <chrono>
@@ -18,28 +19,16 @@
 namespace sigsdp {
 namespace {
 
-bool check_csr(int64_t n, const int32_t* p, const int32_t* idx, const char* name, std::string& err) {
-    if (p[0] != 0) {
-        err = std::string(name) + ": indptr[0] != 0";
-        return false;
-    }
-    for (int64_t r = 0; r < n; ++r) {
-        if (p[r + 1] < p[r]) {
-            err = std::string(name) + ": indptr not monotone";
-            return false;
-        }
+// first problem of rows [r0, r1) of a CSR structure, or nullptr
+const char* check_csr_rows(int64_t n, const int32_t* p, const int32_t* idx, int64_t r0, int64_t r1) {
+    for (int64_t r = r0; r < r1; ++r) {
+        if (p[r + 1] < p[r]) return "indptr not monotone";
         for (int32_t q = p[r]; q < p[r + 1]; ++q) {
-            if (idx[q] < 0 || idx[q] >= n) {
-                err = std::string(name) + ": column index out of range";
-                return false;
-            }
-            if (q > p[r] && idx[q] <= idx[q - 1]) {
-                err = std::string(name) + ": indices must be sorted and duplicate-free per row";
-                return false;
-            }
+            if (idx[q] < 0 || idx[q] >= n) return "column index out of range";
+            if (q > p[r] && idx[q] <= idx[q - 1]) return "indices must be sorted and duplicate-free per row";
         }
     }
-    return true;
+    return nullptr;
 }
 
 // value of the CSR entry (r, c) or 0
@@ -145,74 +134,138 @@ int build_host_plan(int64_t n, const int32_t* Sp, const int32_t* Si, const doubl
         err = "null input array";
         return SIGSDP_EINVAL;
     }
-    if (!check_csr(n, Sp, Si, "S_gain", err) || !check_csr(n, Qp, Qi, "Q_asso", err)) return SIGSDP_EINVAL;
+    if (Sp[0] != 0 || Qp[0] != 0) {
+        err = std::string(Sp[0] != 0 ? "S_gain" : "Q_asso") + ": indptr[0] != 0";
+        return SIGSDP_EINVAL;
+    }
+    // Structure checks on all host cores; every chunk keeps its first problem and the one in
+    // the lowest chunk is reported (the same message a sequential scan would give, up to which
+    // of two broken matrices is named first: S_gain wins).  Q_asso must be symmetric with an
+    // empty diagonal (the reference counts E_asso = nnz(Q)/2 and indexes triu(Q,1), mmw.py:57-59).
+    {
+        struct Issue { int64_t row = -1; std::string msg; };
+        std::vector<Issue> issues(64);
+        // the monotone check must hold everywhere before any row content is dereferenced
+        for (int64_t r = 0; r < n; ++r)
+            if (Sp[r + 1] < Sp[r] || Qp[r + 1] < Qp[r]) {
+                err = std::string(Sp[r + 1] < Sp[r] ? "S_gain" : "Q_asso") + ": indptr not monotone";
+                return SIGSDP_EINVAL;
+            }
+        std::atomic<int> slot{0};
+        auto note = [&](int64_t row, std::string msg) {
+            const int k = slot.fetch_add(1);
+            if (k < (int)issues.size()) {
+                issues[k].row = row;
+                issues[k].msg = std::move(msg);
+            }
+        };
+        for (int pass = 0; pass < 3; ++pass) {
+            parallel_rows(n, [&](int64_t r0, int64_t r1) {
+                if (pass == 0) {
+                    if (const char* m = check_csr_rows(n, Sp, Si, r0, r1)) note(r0, std::string("S_gain: ") + m);
+                } else if (pass == 1) {
+                    if (const char* m = check_csr_rows(n, Qp, Qi, r0, r1)) note(r0, std::string("Q_asso: ") + m);
+                } else {
+                    for (int64_t i = r0; i < r1; ++i)
+                        for (int32_t q = Qp[i]; q < Qp[i + 1]; ++q) {
+                            if (Qx[q] == 0.0) continue;
+                            const int32_t j = Qi[q];
+                            if (j == i) {
+                                note(r0, "Q_asso has a non-zero diagonal entry");
+                                return;
+                            }
+                            if (csr_at(Qp, Qi, Qx, j, (int32_t)i) == 0.0) {
+                                note(r0, "Q_asso is not structurally symmetric");
+                                return;
+                            }
+                        }
+                }
+            });
+            const int cnt = std::min<int>(slot.load(), (int)issues.size());
+            if (cnt > 0) {
+                int best = 0;
+                for (int k = 1; k < cnt; ++k)
+                    if (issues[k].row < issues[best].row) best = k;
+                err = issues[best].msg;
+                return SIGSDP_EINVAL;
+            }
+        }
+    }
     P = HostPlan();
     P.n = n;
     P.order = order;
 
-    // Q_asso must be symmetric with an empty diagonal (the reference counts
-    // E_asso = nnz(Q)/2 and indexes triu(Q,1), mmw.py:57-59)
-    for (int64_t i = 0; i < n; ++i)
-        for (int32_t q = Qp[i]; q < Qp[i + 1]; ++q) {
-            if (Qx[q] == 0.0) continue;
-            int32_t j = Qi[q];
-            if (j == i) {
-                err = "Q_asso has a non-zero diagonal entry";
-                return SIGSDP_EINVAL;
-            }
-            if (csr_at(Qp, Qi, Qx, j, (int32_t)i) == 0.0) {
-                err = "Q_asso is not structurally symmetric";
-                return SIGSDP_EINVAL;
-            }
-        }
-
     tm.lap("validate");
     // ---- T = S^T with association pairs and the diagonal zeroed (mmw.py:28-33)
-    std::vector<int32_t> Tp(n + 1, 0), Ti;
-    std::vector<double> Tx;
+    std::vector<int32_t> Tp(n + 1, 0);
+    hvec<int32_t> Ti;
+    hvec<double> Tx;
     std::vector<uint8_t> keep(Sp[n], 0);   // S entries that survive into T (= T^T entries of their own row)
     {
         // S entry (j, i) becomes T[i][j] unless i == j, the value is zero, or Q[i][j] != 0.
         // Q is symmetric (checked above), so Q[i][j] != 0 <=> Q[j][i] != 0: merge S row j with
         // Q row j (both sorted) instead of searching Q row i.
-        for (int64_t j = 0; j < n; ++j) {
-            int32_t qq = Qp[j];
-            const int32_t qe = Qp[j + 1];
-            for (int32_t q = Sp[j]; q < Sp[j + 1]; ++q) {
-                const int32_t i = Si[q];
-                if (Sx[q] == 0.0 || i == j) continue;
-                while (qq < qe && Qi[qq] < i) ++qq;
-                if (qq < qe && Qi[qq] == i && Qx[qq] != 0.0) continue;
-                keep[q] = 1;
-                Tp[i + 1]++;
+        parallel_rows(n, [&](int64_t j0, int64_t j1) {
+            for (int64_t j = j0; j < j1; ++j) {
+                int32_t qq = Qp[j];
+                const int32_t qe = Qp[j + 1];
+                for (int32_t q = Sp[j]; q < Sp[j + 1]; ++q) {
+                    const int32_t i = Si[q];
+                    if (Sx[q] == 0.0 || i == j) continue;
+                    while (qq < qe && Qi[qq] < i) ++qq;
+                    if (qq < qe && Qi[qq] == i && Qx[qq] != 0.0) continue;
+                    keep[q] = 1;
+                }
             }
+        });
+        // Transpose without scattered writes from one thread: each thread owns a range of T rows
+        // [i0, i1) and walks every S row j (ascending, so T rows come out sorted), binary-searching
+        // the part of the row that falls into its range.  Pass 0 counts, pass 1 fills.
+        for (int pass = 0; pass < 2; ++pass) {
+            if (pass == 1) {
+                for (int64_t i = 0; i < n; ++i) Tp[i + 1] += Tp[i];
+                Ti.resize(Tp[n]);
+                Tx.resize(Tp[n]);
+            }
+            parallel_rows(n, [&](int64_t i0, int64_t i1) {
+                std::vector<int32_t> fill;
+                if (pass == 1) fill.assign(Tp.begin() + i0, Tp.begin() + i1);
+                for (int64_t j = 0; j < n; ++j) {
+                    const int32_t* b = Si + Sp[j];
+                    const int32_t* e = Si + Sp[j + 1];
+                    if (b == e || e[-1] < i0 || b[0] >= i1) continue;
+                    for (const int32_t* it = std::lower_bound(b, e, (int32_t)i0); it != e && *it < i1; ++it) {
+                        const int32_t q = (int32_t)(it - Si);
+                        if (!keep[q]) continue;
+                        if (pass == 0) {
+                            Tp[*it + 1]++;
+                        } else {
+                            int32_t& f = fill[*it - i0];
+                            Ti[f] = (int32_t)j;
+                            Tx[f] = Sx[q];
+                            ++f;
+                        }
+                    }
+                }
+            });
         }
-        for (int64_t i = 0; i < n; ++i) Tp[i + 1] += Tp[i];
-        Ti.resize(Tp[n]);
-        Tx.resize(Tp[n]);
-        std::vector<int32_t> fill(Tp.begin(), Tp.end() - 1);
-        for (int64_t j = 0; j < n; ++j)
-            for (int32_t q = Sp[j]; q < Sp[j + 1]; ++q) {
-                if (!keep[q]) continue;
-                const int32_t i = Si[q];
-                Ti[fill[i]] = (int32_t)j;
-                Tx[fill[i]] = Sx[q];
-                fill[i]++;
-            }
     }
     P.nnzT = Tp[n];
+    tm.lap("  T = S^T filtered");
     // T^T needs no second transpose: row i of T^T is row i of S restricted to the kept entries
     // ---- S_sum = T 1 and sqrt((T o T) 1) (mmw.py:34-39)
     std::vector<double> S_sum(n), tnorm(n);
-    for (int64_t i = 0; i < n; ++i) {
-        double s = 0.0, s2 = 0.0;
-        for (int32_t q = Tp[i]; q < Tp[i + 1]; ++q) {
-            s += Tx[q];
-            s2 += Tx[q] * Tx[q];
+    parallel_rows(n, [&](int64_t i0, int64_t i1) {
+        for (int64_t i = i0; i < i1; ++i) {
+            double s = 0.0, s2 = 0.0;
+            for (int32_t q = Tp[i]; q < Tp[i + 1]; ++q) {
+                s += Tx[q];
+                s2 += Tx[q] * Tx[q];
+            }
+            S_sum[i] = s;
+            tnorm[i] = std::sqrt(s2);
         }
-        S_sum[i] = s;
-        tnorm[i] = std::sqrt(s2);
-    }
+    });
 
     // ---- union pattern: diag + gain (T + T^T != 0) + asso, per row, columns ascending.
     // Each row is a 3-way merge of sorted lists; rows are independent, so they are built on
@@ -243,6 +296,7 @@ int build_host_plan(int64_t n, const int32_t* Sp, const int32_t* Si, const doubl
         }
         return true;
     };
+    tm.lap("  row sums");
     std::vector<int32_t> rowptr(n + 1, 0);
     std::vector<int64_t> g_ut(n + 1, 0), a_ut(n + 1, 0);
     std::vector<int> bad(1, 0);
@@ -285,8 +339,8 @@ int build_host_plan(int64_t n, const int32_t* Sp, const int32_t* Si, const doubl
     tm.lap("union pattern");
 
     // ---- edge ids in the reference's order (row-major upper triangle, mmw.py:56-57)
-    std::vector<int32_t> col(P.nnz), eid(P.nnz);
-    std::vector<double> tfwd(P.nnz), tbwd(P.nnz);
+    hvec<int32_t> col(P.nnz), eid(P.nnz);
+    hvec<double> tfwd(P.nnz), tbwd(P.nnz);
     P.gi.resize(P.E_g); P.gj.resize(P.E_g); P.tij.resize(P.E_g); P.tji.resize(P.E_g);
     P.ai.resize(P.E_a); P.aj.resize(P.E_a);
     parallel_rows(n, [&](int64_t r0, int64_t r1) {
@@ -313,22 +367,29 @@ int build_host_plan(int64_t n, const int32_t* Sp, const int32_t* Si, const doubl
             }
         }
     });
+    tm.lap("  fill rows");
     {
-        // the pattern is symmetric: scanning the upper entries (j, i), j ascending, visits every
-        // row i's lower entries in ascending column order, so a cursor per row finds the mirror
-        std::vector<int32_t> cursor(rowptr.begin(), rowptr.end() - 1);
-        for (int64_t j = 0; j < n; ++j)
-            for (int32_t q = rowptr[j]; q < rowptr[j + 1]; ++q) {
-                const int32_t i = col[q];
-                if (i <= j) continue;
-                int32_t& c = cursor[i];
-                if (c >= rowptr[i + 1] || col[c] != j) {
-                    err = "internal: asymmetric union pattern";
-                    return SIGSDP_EINVAL;
+        // the pattern is symmetric: a lower entry (i, j < i) takes the id of its mirror (j, i),
+        // found by binary search in row j (rows are independent: all host cores)
+        std::atomic<int> asym{0};
+        parallel_rows(n, [&](int64_t r0, int64_t r1) {
+            for (int64_t i = r0; i < r1; ++i)
+                for (int32_t q = rowptr[i]; q < rowptr[i + 1] && col[q] < i; ++q) {
+                    const int32_t j = col[q];
+                    const int32_t* b = col.data() + rowptr[j];
+                    const int32_t* e = col.data() + rowptr[j + 1];
+                    const int32_t* it = std::lower_bound(b, e, (int32_t)i);
+                    if (it == e || *it != i) {
+                        asym.store(1);
+                        return;
+                    }
+                    eid[q] = eid[it - col.data()];
                 }
-                eid[c] = eid[q];
-                ++c;
-            }
+        });
+        if (asym.load()) {
+            err = "internal: asymmetric union pattern";
+            return SIGSDP_EINVAL;
+        }
     }
 
     P.rowptr.swap(rowptr);
@@ -349,10 +410,12 @@ int build_host_plan(int64_t n, const int32_t* Sp, const int32_t* Si, const doubl
         // renumber nodes for locality; edge ids and edge lists keep the caller's order
         std::vector<int32_t> perm;
         locality_order(P, order > 1 ? order : 64, perm);
+        tm.lap("  clustered BFS");
         std::vector<int32_t> iperm(n);
         for (int64_t k = 0; k < n; ++k) iperm[perm[k]] = (int32_t)k;
-        std::vector<int32_t> rp(n + 1, 0), c2(P.nnz), e2(P.nnz);
-        std::vector<double> f2(P.nnz), b2(P.nnz);
+        std::vector<int32_t> rp(n + 1, 0);
+        hvec<int32_t> c2(P.nnz), e2(P.nnz);
+        hvec<double> f2(P.nnz), b2(P.nnz);
         for (int64_t k = 0; k < n; ++k) rp[k + 1] = rp[k] + (P.rowptr[perm[k] + 1] - P.rowptr[perm[k]]);
         parallel_rows(n, [&](int64_t k0, int64_t k1) {
             std::vector<uint64_t> ord;
@@ -392,32 +455,33 @@ int build_host_plan(int64_t n, const int32_t* Sp, const int32_t* Si, const doubl
     tm.lap("locality renumbering");
     P.dpos.assign(n, -1);
     P.apos.assign(P.E_a, -1);
-    for (int64_t k = 0; k < n; ++k)
-        for (int32_t q = P.rowptr[k]; q < P.rowptr[k + 1]; ++q) {
-            if (P.eid[q] < 0) P.dpos[k] = q;
-            else if (P.eid[q] >= P.E_g && k < P.col[q]) P.apos[P.eid[q] - P.E_g] = q;
-        }
+    parallel_rows(n, [&](int64_t k0, int64_t k1) {   // every slot has exactly one writer
+        for (int64_t k = k0; k < k1; ++k)
+            for (int32_t q = P.rowptr[k]; q < P.rowptr[k + 1]; ++q) {
+                if (P.eid[q] < 0) P.dpos[k] = q;
+                else if (P.eid[q] >= P.E_g && k < P.col[q]) P.apos[P.eid[q] - P.E_g] = q;
+            }
+    });
+    tm.lap("diag / asso positions");
     return SIGSDP_OK;
 }
 
-void build_tiles(const HostPlan& P, int max_rows, int ucap, int nnzcap, HostTiles& T) {
-    int run_gap = 2;
-    if (const char* e = getenv("SIGSDP_RUN_GAP")) run_gap = std::max(0, atoi(e));
-    const int64_t n = P.n;
-    T = HostTiles();
-    T.max_rows = max_rows;
-    T.ucap = std::min(ucap, 65535);
-    T.nnzcap = nnzcap;
-    T.lcol.resize(P.nnz);
-    T.trow.push_back(0);
-    T.rptr.push_back(0);
-    std::vector<int32_t> stamp(n, -1), local(n, 0), cols, fresh;
-    int64_t r0 = 0;
+namespace {
+// tiles of the rows [ra, rb), tile-local numbering of runs; lcol is written in place
+struct TilePart {
+    std::vector<int32_t> trow_end, ucnt, rend, runs;
+    int umax = 0, nnzmax = 0;
+    bool ok = true;
+};
+void build_tiles_range(const HostPlan& P, int64_t ra, int64_t rb, int max_rows, int ucap, int nnzcap, int run_gap,
+                       uint16_t* lcol, TilePart& out) {
+    std::vector<int32_t> stamp(P.n, -1), local(P.n, 0), cols, fresh;
+    int64_t r0 = ra;
     int t = 0;
-    while (r0 < n) {
+    while (r0 < rb) {
         cols.clear();
         int64_t r1 = r0;
-        while (r1 < n && r1 - r0 < max_rows) {
+        while (r1 < rb && r1 - r0 < max_rows) {
             // distinct columns row r1 would add
             fresh.clear();
             for (int32_t q = P.rowptr[r1]; q < P.rowptr[r1 + 1]; ++q) {
@@ -427,8 +491,7 @@ void build_tiles(const HostPlan& P, int max_rows, int ucap, int nnzcap, HostTile
                     fresh.push_back(c);
                 }
             }
-            const bool fits = (int)(cols.size() + fresh.size()) <= T.ucap &&
-                              P.rowptr[r1 + 1] - P.rowptr[r0] <= nnzcap;
+            const bool fits = (int)(cols.size() + fresh.size()) <= ucap && P.rowptr[r1 + 1] - P.rowptr[r0] <= nnzcap;
             if (!fits) {
                 for (int32_t c : fresh) stamp[c] = -1;
                 break;
@@ -436,7 +499,10 @@ void build_tiles(const HostPlan& P, int max_rows, int ucap, int nnzcap, HostTile
             cols.insert(cols.end(), fresh.begin(), fresh.end());
             ++r1;
         }
-        if (r1 == r0) return;  // a single row exceeds the caps: T.ok stays false
+        if (r1 == r0) {   // a single row exceeds the caps
+            out.ok = false;
+            return;
+        }
         std::sort(cols.begin(), cols.end());
         // runs of (nearly) consecutive columns, one bulk copy each: columns separated by at most
         // `gap` unneeded rows share a run (fewer, larger copies at the price of a few extra rows);
@@ -451,7 +517,7 @@ void build_tiles(const HostPlan& P, int max_rows, int ucap, int nnzcap, HostTile
                 copied += cols[j - 1] - cols[i] + 1;
                 i = j;
             }
-            if (copied <= T.ucap || gap == 0) break;
+            if (copied <= ucap || gap == 0) break;
         }
         int slot = 0;
         for (size_t i = 0; i < cols.size();) {
@@ -459,22 +525,67 @@ void build_tiles(const HostPlan& P, int max_rows, int ucap, int nnzcap, HostTile
             while (j < cols.size() && cols[j] - cols[j - 1] <= gap + 1) ++j;
             const int len = cols[j - 1] - cols[i] + 1;
             for (size_t k = i; k < j; ++k) local[cols[k]] = slot + (cols[k] - cols[i]);
-            T.runs.push_back(cols[i]);
-            T.runs.push_back(slot);
-            T.runs.push_back(len);
-            T.runs.push_back(0);
+            out.runs.push_back(cols[i]);
+            out.runs.push_back(slot);
+            out.runs.push_back(len);
+            out.runs.push_back(0);
             slot += len;
             i = j;
         }
-        for (int32_t q = P.rowptr[r0]; q < P.rowptr[r1]; ++q) T.lcol[q] = (uint16_t)local[P.col[q]];
-        T.rptr.push_back((int32_t)(T.runs.size() / 4));
-        T.ucnt.push_back((int32_t)copied);
-        T.trow.push_back((int32_t)r1);
-        T.umax = std::max<int>(T.umax, copied);
-        T.nnzmax = std::max<int>(T.nnzmax, P.rowptr[r1] - P.rowptr[r0]);
+        for (int32_t q = P.rowptr[r0]; q < P.rowptr[r1]; ++q) lcol[q] = (uint16_t)local[P.col[q]];
+        out.rend.push_back((int32_t)(out.runs.size() / 4));
+        out.ucnt.push_back((int32_t)copied);
+        out.trow_end.push_back((int32_t)r1);
+        out.umax = std::max<int>(out.umax, copied);
+        out.nnzmax = std::max<int>(out.nnzmax, P.rowptr[r1] - P.rowptr[r0]);
         r0 = r1;
         ++t;
     }
+}
+}  // namespace
+
+void build_tiles(const HostPlan& P, int max_rows, int ucap, int nnzcap, HostTiles& T) {
+    int run_gap = 2;
+    if (const char* e = getenv("SIGSDP_RUN_GAP")) run_gap = std::max(0, atoi(e));
+    const int64_t n = P.n;
+    T = HostTiles();
+    T.max_rows = max_rows;
+    T.ucap = std::min(ucap, 65535);
+    T.nnzcap = nnzcap;
+    T.lcol.resize(P.nnz);
+    // Large graphs are cut into a FIXED number of row ranges tiled independently on the host
+    // cores (fixed, not the core count: the tiling, and with it the order of the per-block
+    // partial sums, is the same on every machine); a range boundary only ends a tile early.
+    const int nchunks = n >= 32768 ? 16 : 1;
+    std::vector<TilePart> parts(nchunks);
+    {
+        std::atomic<int> next{0};
+        auto work = [&] {
+            for (int c = next.fetch_add(1); c < nchunks; c = next.fetch_add(1))
+                build_tiles_range(P, n * c / nchunks, n * (c + 1) / nchunks, max_rows, T.ucap, nnzcap, run_gap,
+                                  T.lcol.data(), parts[c]);
+        };
+        unsigned nt = std::thread::hardware_concurrency();
+        if (const char* e = getenv("SIGSDP_HOST_THREADS")) nt = (unsigned)std::max(1, atoi(e));
+        nt = std::max(1u, std::min<unsigned>(nt, (unsigned)nchunks));
+        std::vector<std::thread> th;
+        for (unsigned i = 1; i < nt; ++i) th.emplace_back(work);
+        work();
+        for (auto& x : th) x.join();
+    }
+    T.trow.push_back(0);
+    T.rptr.push_back(0);
+    for (const TilePart& pt : parts) {
+        if (!pt.ok) return;   // T.ok stays false: the caller falls back to the gather kernels
+        const int32_t run0 = (int32_t)(T.runs.size() / 4);
+        T.runs.insert(T.runs.end(), pt.runs.begin(), pt.runs.end());
+        for (int32_t e : pt.rend) T.rptr.push_back(run0 + e);
+        T.ucnt.insert(T.ucnt.end(), pt.ucnt.begin(), pt.ucnt.end());
+        T.trow.insert(T.trow.end(), pt.trow_end.begin(), pt.trow_end.end());
+        T.umax = std::max(T.umax, pt.umax);
+        T.nnzmax = std::max(T.nnzmax, pt.nnzmax);
+    }
+    const int t = (int)T.ucnt.size();
     T.ntiles = t;
     T.trec.resize((size_t)t * 8);
     for (int i = 0; i < t; ++i) {

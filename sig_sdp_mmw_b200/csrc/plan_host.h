@@ -2,10 +2,29 @@
 // edge-list set-up (mmw.py:52-57) produce, in the flat layout the kernels walk.
 #pragma once
 #include <cstdint>
+#include <memory>
 #include <string>
+#include <type_traits>
+#include <utility>
 #include <vector>
 
 namespace sigsdp {
+
+// std::vector that leaves trivially constructible elements uninitialised on resize: the
+// big per-non-zero arrays are written once, in parallel, by the threads that build them,
+// so the pages are first touched there instead of being zero-filled by one thread.
+template <class T>
+struct DefaultInitAllocator : std::allocator<T> {
+    template <class U> struct rebind { using other = DefaultInitAllocator<U>; };
+    using std::allocator<T>::allocator;
+    template <class U> void construct(U* p) noexcept(std::is_nothrow_default_constructible<U>::value) {
+        ::new (static_cast<void*>(p)) U;
+    }
+    template <class U, class... A> void construct(U* p, A&&... a) {
+        ::new (static_cast<void*>(p)) U(std::forward<A>(a)...);
+    }
+};
+template <class T> using hvec = std::vector<T, DefaultInitAllocator<T>>;
 
 struct HostPlan {
     int64_t n = 0;
@@ -14,11 +33,12 @@ struct HostPlan {
     int64_t nnzT = 0;           // stored entries of T
     int max_row = 0;
     // union pattern in INTERNAL numbering, columns ascending inside a row
-    std::vector<int32_t> rowptr, col, eid;   // eid: -1 diag, [0,E_g) gain, E_g + a asso
-    std::vector<double> tfwd, tbwd;          // T[row,col], T[col,row] (0 off the gain pattern)
+    std::vector<int32_t> rowptr;
+    hvec<int32_t> col, eid;                  // eid: -1 diag, [0,E_g) gain, E_g + a asso
+    hvec<double> tfwd, tbwd;                 // T[row,col], T[col,row] (0 off the gain pattern)
     // edge lists in the CALLER's numbering and the reference's order
-    std::vector<int32_t> gi, gj, ai, aj;
-    std::vector<double> tij, tji;
+    hvec<int32_t> gi, gj, ai, aj;
+    hvec<double> tij, tji;
     // node vectors, INTERNAL numbering
     std::vector<double> S_sum, tnorm, h_max;
     // perm[new] = old, iperm[old] = new
