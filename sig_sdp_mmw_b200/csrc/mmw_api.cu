@@ -160,7 +160,7 @@ struct sigsdp_batch {
 template <typename T, int G>
 __global__ void __launch_bounds__(NT, 2) k_fused(Prob<T> P, int n_iters, int do_finish) {
     extern __shared__ __align__(16) unsigned char dyn_smem[];
-    GridTeam team;
+    GridTeam team(&P.ctrl->bar);
     run_iterations<T, G>(P, team, n_iters, dyn_smem, do_finish);
 }
 template <typename T, int G>
@@ -827,8 +827,20 @@ static int solver_alloc(sigsdp_solver* s) {
     if (s->tiling != 0) {
         const size_t rowbytes = (size_t)s->Dp * sizeof(T);
         const size_t budget = 106 * 1024;
-        const int max_rows = s->tiling > 0 ? s->tiling : std::max(R, 64);
+        int max_rows = s->tiling > 0 ? s->tiling : std::max(R, 64);
         const int nnzcap = (std::max(2048, std::min(8192, 4 * h.max_row)) + 7) & ~7;
+        if (s->tiling < 0) {
+            // Tiles are dealt round-robin to the persistent grid (2 blocks per SM), so the staged
+            // phases take ceil(tiles / grid) tile times: when the row count is what ends a tile
+            // (not the shared-memory caps), shrink the tiles until the last wave is full too.
+            // cfg4: 1585 tiles of 64 rows = 5.35 waves -> 1730 tiles of 58 rows = 5.85 waves.
+            const double grid_est = 2.0 * pl->num_sms, n_rows = (double)h.n;
+            const double avg_nnz = (double)h.nnz / n_rows;
+            if (avg_nnz * max_rows <= 0.95 * nnzcap && n_rows > grid_est * max_rows) {
+                const double waves = std::ceil(1.015 * n_rows / max_rows / grid_est);
+                max_rows = std::min(max_rows, std::max(16, (int)std::ceil(1.02 * n_rows / (grid_est * waves))));
+            }
+        }
         const size_t fixed = 16 + (size_t)(nnzcap + 4) * sizeof(T) + (size_t)(nnzcap + 8) * 2 + 48;
         const int ucap = budget > fixed ? (int)std::min<size_t>((budget - fixed) / rowbytes, 65535) : 0;
         if (ucap >= h.max_row && h.max_row <= nnzcap) {

@@ -71,6 +71,10 @@ struct Ctrl {
     // block-0 cycle counters (clock64): [0] term staging wait, [1] term compute, [2] gram staging
     // wait, [3] gram compute, [4] grid-barrier wait, [5] dual, [6] exp, [7] loss
     long long dbg[8];
+    // arrivals at the fused kernel's grid barrier, counted up for ever (GridTeam); on a line
+    // of its own so the polling does not collide with the keys above
+    alignas(128) unsigned long long bar;
+    unsigned long long bar_pad[15];
 };
 
 template <typename T>
@@ -117,10 +121,38 @@ struct Prob {
 
 // ---------------------------------------------------------------------------
 // teams
+// The fused kernel's grid barrier (cooperative launch: all blocks are resident).  One
+// arrival counter that only counts up: barrier number b is complete when it reaches
+// b * gridDim.x, so there is no reset and no second round trip; every block derives the
+// number it starts at from the counter itself (arrivals of the first barrier of a launch
+// cannot complete it before this block has arrived too, so rounding down is exact).
+// Thread 0 arrives with a release and polls with an acquire at GPU scope; the block
+// barriers on either side extend that to the whole block.  Measured against
+// cooperative_groups' grid.sync(): the same at 296 blocks (cfg4, where the wait is
+// imbalance), 2-7 % per iteration on the smaller configurations.
 struct GridTeam {
+    unsigned long long* ctr;
+    mutable unsigned long long next;
+    __device__ explicit GridTeam(unsigned long long* c) : ctr(c) {
+        unsigned long long v;
+        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(c) : "memory");
+        next = (v / gridDim.x + 1ull) * gridDim.x;
+    }
     __device__ int rank() const { return blockIdx.x; }
     __device__ int size() const { return gridDim.x; }
-    __device__ void sync() const { cg::this_grid().sync(); }
+    __device__ void sync() const {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(ctr) : "memory");
+            unsigned long long v;
+            do {
+                asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(ctr) : "memory");
+            } while (v < next);
+        }
+        next += gridDim.x;
+        __syncthreads();
+    }
 };
 struct StepTeam {  // stepwise: the kernel boundary is the barrier
     __device__ int rank() const { return blockIdx.x; }
@@ -1232,12 +1264,34 @@ __device__ void phase_gram_staged(const Prob<T>& P, const Team& team, double* sh
     for (int t = team.rank(); t < tl.ntiles; t += team.size()) {
         const int4 trc = tl.trec[2 * t];
         const int r0 = trc.x, r1 = trc.y;
+        // Row pointers / diagonal positions of this warp's rows (lane i: its i-th row of the
+        // tile) are requested before the stage and handed out by shuffle: one global latency per
+        // tile, hidden behind the stage, instead of one per row.
+        int mp0 = 0, mp1 = 0, mpd = 0;
+        {
+            const int kk = r0 + wrp + NWARP * lane;
+            if (kk < r1) {
+                mp0 = g.rowptr[kk];
+                mp1 = g.rowptr[kk + 1];
+                mpd = g.dpos[kk];
+            }
+        }
         stage_tile(P, (const T*)P.F, (const T*)nullptr, t, st, timed ? &wait_c : nullptr);
-        for (int kb = r0; kb < r1; kb += NWARP) {   // block-uniform trip count
+        int pass = 0;
+        for (int kb = r0; kb < r1; kb += NWARP, ++pass) {   // block-uniform trip count
             const int k = kb + wrp;
             double rsum = 0.0;
+            int p0, p1, pd;
+            if (pass < 32) {
+                p0 = __shfl_sync(0xffffffffu, mp0, pass);
+                p1 = __shfl_sync(0xffffffffu, mp1, pass);
+                pd = __shfl_sync(0xffffffffu, mpd, pass);
+            } else {   // tiles of more than 32 * NWARP rows do not exist today
+                p0 = k < r1 ? g.rowptr[k] : 0;
+                p1 = k < r1 ? g.rowptr[k + 1] : 0;
+                pd = k < r1 ? g.dpos[k] : 0;
+            }
             if (k < r1) {
-                const int p0 = g.rowptr[k], p1 = g.rowptr[k + 1], pd = g.dpos[k];
                 const unsigned abase = st.rows_a + lds_u16(st.la + 2u * (unsigned)pd) * rowb;
                 for (int p = p0 + lane; p < p1; p += 32) {
                     double xold = 0.0, xbar = 0.0;
