@@ -9,6 +9,24 @@ import numpy as np
 import torch
 
 
+_blas_ctl = None
+
+
+def _small_eigh(Tm):
+    """Projected (ncv x ncv) eigenproblem on the host, on ONE BLAS thread: at this size the
+    threaded LAPACK is no faster, and its worker threads keep spinning after the call, which
+    slows whatever the host does next on its cores (e.g. the next plan build, measured 2x)."""
+    global _blas_ctl
+    try:
+        if _blas_ctl is None:
+            from threadpoolctl import ThreadpoolController
+            _blas_ctl = ThreadpoolController()
+        with _blas_ctl.limit(limits=1, user_api="blas"):
+            return np.linalg.eigh(Tm)
+    except ImportError:
+        return np.linalg.eigh(Tm)
+
+
 def _dense_from_matvec(matmat, n, device):
     eye = torch.eye(n, dtype=torch.float64, device=device)
     M = matmat(eye)          # rows of the result are M e_i = columns of M (symmetric)
@@ -91,7 +109,7 @@ def thick_restart_lanczos(matmat, n, k, which, v0, ncv=None, tol=1e-12, max_rest
             Tm[j, j] = al_h[j]
             if j + 1 < m:
                 Tm[j, j + 1] = Tm[j + 1, j] = be_h[j]
-        theta, S = np.linalg.eigh(Tm)
+        theta, S = _small_eigh(Tm)
         order = np.argsort(-np.abs(theta)) if which == "LM" else np.arange(m)
         want = order[:k]
         beta_m = be_h[m - 1]
