@@ -204,7 +204,10 @@ __global__ void __launch_bounds__(NT, 2) k_gram(Prob<T> P) {
     if (P.tl.enabled) {
         Stage<T> st;
         stage_setup(P, dyn_smem, st);
-        phase_gram_staged<T, G>(P, StepTeam(), sh, st);
+        if (G >= 8 && P.Dp == G * Vec<T>::N)
+            phase_gram_staged2<T, G>(P, StepTeam(), sh, st);
+        else
+            phase_gram_staged<T, G>(P, StepTeam(), sh, st);
     } else {
         phase_gram<T, G>(P, StepTeam(), sh);
     }

@@ -1364,6 +1364,124 @@ __device__ void phase_gram_staged(const Prob<T>& P, const Team& team, double* sh
 }
 
 
+// Variant of phase_gram_staged for rows that fill the lane group exactly (Dp == G * VEC,
+// G >= 8), same thread mapping as phase_term_staged2: G/2 lanes per row, each lane keeps ITS
+// two 16-byte chunks of F_k in registers for the whole row and reads the same two chunks of
+// every neighbour row F_c, i.e. 2 shared-memory wavefronts per non-zero instead of the 4-5 of
+// the lane-per-non-zero kernel (which re-reads F_k per non-zero).  The G/2 partial dot
+// products of a non-zero are combined eight non-zeros at a time by a transposing butterfly
+// (xor 4, 2, 1: 7 shuffles for 8 sums, lane l ends up owning non-zero l of the chunk) and
+// that lane finishes the entry (X, X_avgd, row sum).  Fixed summation tree: bit-reproducible.
+template <typename T, int G, class Team>
+__device__ void phase_gram_staged2(const Prob<T>& P, const Team& team, double* sh, Stage<T>& st) {
+    using V = Vec<T>;
+    using LD = SmemLd<T>;
+    constexpr int VEC = V::N;
+    constexpr int W = (int)sizeof(T);
+    constexpr int GH = G / 2;
+    constexpr int R = NT / GH;
+    const PlanDev& g = P.g;
+    const TileDev& tl = P.tl;
+    const int K = g.n, Dp = P.Dp;
+    const unsigned rowb = (unsigned)(Dp * W);
+    const int lane = threadIdx.x & (GH - 1);
+    const int grp = threadIdx.x / GH;
+    const bool raw = P.split != 0;
+    const double tr = raw ? 1.0 : team_sum(P.ptr, 1, team.size(), sh) / K;
+    const double inv_tr = 1.0 / tr;
+    const bool timed = team.rank() == 0 && threadIdx.x == 0;
+    long long wait_c = 0;
+    const long long tph0 = timed ? clock64() : 0;
+    const unsigned ca = (unsigned)(lane * VEC * W), cb2 = (unsigned)((lane + GH) * VEC * W);
+    fence_proxy_async();
+    for (int t = team.rank(); t < tl.ntiles; t += team.size()) {
+        const int4 trc = tl.trec[2 * t];
+        const int r0 = trc.x, r1 = trc.y;
+        stage_tile(P, (const T*)P.F, (const T*)nullptr, t, st, timed ? &wait_c : nullptr);
+        for (int kb = r0; kb < r1; kb += R) {   // block-uniform trip count
+            const int k = kb + grp;
+            const bool valid = k < r1;
+            int p0 = 0, len = 0, pd = 0;
+            if (valid) {
+                p0 = g.rowptr[k];
+                len = g.rowptr[k + 1] - p0;
+                pd = g.dpos[k];
+            }
+            // F_k: this lane's two chunks (an idle group reads slot 0 of the tile and discards)
+            V fka, fkb;
+            {
+                const unsigned abase = st.rows_a + (valid ? lds_u16(st.la + 2u * (unsigned)pd) * rowb : 0u);
+                LD::vec(fka, abase + ca);
+                LD::vec(fkb, abase + cb2);
+            }
+            const double xdiag = (valid && !raw) ? P.dsq[k] * inv_tr : 0.0;
+            const unsigned la = st.la + 2u * (unsigned)p0;
+            // the shuffles below are warp-wide instructions: every group of the warp runs the
+            // trip count of the warp's longest row (shorter rows repeat their last entry)
+            const int nch = __reduce_max_sync(0xffffffffu, (len + GH - 1) / GH);
+            double rsum = 0.0;
+            for (int c = 0; c < nch; ++c) {
+                const int jmine = c * GH + lane;           // the entry this lane will finish
+                const bool mine = jmine < len;
+                double xold = 0.0, xbar = 0.0;
+                if (mine && !raw) {   // in flight during the dot products
+                    xold = P.Xv[p0 + jmine];
+                    xbar = P.Xbarv[p0 + jmine];
+                }
+                T v[GH];
+#pragma unroll
+                for (int i = 0; i < GH; ++i) {
+                    const int j = min(c * GH + i, len - 1);
+                    const unsigned bbase = st.rows_a + (j >= 0 ? lds_u16(la + 2u * (unsigned)j) * rowb : 0u);
+                    V fa, fb;
+                    LD::vec(fa, bbase + ca);
+                    LD::vec(fb, bbase + cb2);
+                    T d = (T)0;
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q) d = fma(fka.v[q], fa.v[q], d);
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q) d = fma(fkb.v[q], fb.v[q], d);
+                    v[i] = d;
+                }
+                // transposing butterfly: after the stage with distance h a lane holds h sums
+#pragma unroll
+                for (int h = GH / 2; h >= 1; h >>= 1) {
+                    const bool up = (lane & h) != 0;
+#pragma unroll
+                    for (int i = 0; i < h; ++i) {
+                        const T send = up ? v[i] : v[i + h];
+                        const T keep = up ? v[i + h] : v[i];
+                        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+                    }
+                }
+                if (mine) {
+                    const int p = p0 + jmine;
+                    double x;
+                    if (p == pd) {
+                        x = xdiag;
+                    } else {
+                        x = (double)v[0] * inv_tr;
+                        rsum += x;
+                    }
+                    if (raw) {
+                        P.graw[p] = x;
+                    } else {
+                        P.Xbarv[p] = xbar + xold;
+                        P.Xv[p] = x;
+                    }
+                }
+            }
+#pragma unroll
+            for (int o = GH / 2; o > 0; o >>= 1) rsum += __shfl_xor_sync(0xffffffffu, rsum, o);
+            if (valid && lane == 0 && !raw) P.r[k] = rsum;
+        }
+    }
+    if (timed) {
+        P.ctrl->dbg[2] += wait_c;
+        P.ctrl->dbg[3] += clock64() - tph0 - wait_c;
+    }
+}
+
 // ===========================================================================
 // Sketch-column sharding: after the ranks all-reduced [graw | dsq] (partial dot products and
 // partial ||F_k||^2 over each rank's columns), every rank completes the Gram phase the same
@@ -1520,7 +1638,10 @@ __device__ void run_iterations(const Prob<T>& P, const Team& team, int n_iters, 
         }
         terms += tcount;
         if (staged)
-            phase_gram_staged<T, G>(P, team, sh, st);
+            if (G >= 8 && P.Dp == G * Vec<T>::N)
+                phase_gram_staged2<T, G>(P, team, sh, st);
+            else
+                phase_gram_staged<T, G>(P, team, sh, st);
         else
             phase_gram<T, G>(P, team, sh);
         TIMED_SYNC();
