@@ -1430,18 +1430,22 @@ __device__ void phase_gram_staged2(const Prob<T>& P, const Team& team, double* s
                 }
                 T v[GH];
 #pragma unroll
-                for (int i = 0; i < GH; ++i) {
-                    const int j = min(c * GH + i, len - 1);
-                    const unsigned bbase = st.rows_a + (j >= 0 ? lds_u16(la + 2u * (unsigned)j) * rowb : 0u);
-                    V fa, fb;
-                    LD::vec(fa, bbase + ca);
-                    LD::vec(fb, bbase + cb2);
-                    T d = (T)0;
+                for (int i = 0; i < GH; ++i) v[i] = (T)0;
+                if (c * GH < len) {   // a group whose row is finished only takes part in the shuffles
 #pragma unroll
-                    for (int q = 0; q < VEC; ++q) d = fma(fka.v[q], fa.v[q], d);
+                    for (int i = 0; i < GH; ++i) {
+                        const int j = min(c * GH + i, len - 1);
+                        const unsigned bbase = st.rows_a + lds_u16(la + 2u * (unsigned)j) * rowb;
+                        V fa, fb;
+                        LD::vec(fa, bbase + ca);
+                        LD::vec(fb, bbase + cb2);
+                        T d = (T)0;
 #pragma unroll
-                    for (int q = 0; q < VEC; ++q) d = fma(fkb.v[q], fb.v[q], d);
-                    v[i] = d;
+                        for (int q = 0; q < VEC; ++q) d = fma(fka.v[q], fa.v[q], d);
+#pragma unroll
+                        for (int q = 0; q < VEC; ++q) d = fma(fkb.v[q], fb.v[q], d);
+                        v[i] = d;
+                    }
                 }
                 // transposing butterfly: after the stage with distance h a lane holds h sums
 #pragma unroll
