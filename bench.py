@@ -32,7 +32,7 @@ WORKLOADS = {
     "cfg1_500": (dict(cell_size=10, sta_density_per_1m2=125e-4), 4, 2, "float64"),
 }
 ETA = 0.04
-NCU_TRAFFIC_RATIO = 10.902 / 8.453   # measured DRAM bytes / algorithmic bytes of k_fused (see roofline.traffic_source)
+NCU_TRAFFIC_RATIO = 10.846 / 8.453   # measured DRAM bytes / algorithmic bytes of k_fused (see roofline.traffic_source)
 METRIC = "mmw_iters_per_s"
 UNIT = "iterations/s"
 
@@ -418,7 +418,7 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": tot_bytes * NCU_TRAFFIC_RATIO if args.workload == "cfg4_100k" else None,
                          "traffic_source": "ncu --set full dram__bytes_read+write of k_fused on this workload "
-                                           "(profiles/r1b_ncu_fused_cfg4_full.txt: 10.90 GB for a 12-iteration launch "
+                                           "(profiles/r1c_ncu_fused_cfg4_full.txt: 10.85 GB for a 12-iteration launch "
                                            "whose algorithmic bytes are 8.45 GB), scaled to this launch's algorithmic bytes",
                          "kernel": "k_fused (whole iteration)", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": tot_bytes, "spmm_term_bytes": spmm_b,
