@@ -96,6 +96,48 @@ def test_tile_stats_respect_the_caps():
         pl.tile_stats(32, 4, 1024)      # a single row has more neighbours than the cap
 
 
+def _ring_state(n, hops=(1, 2, 5), seed=0):
+    """Circulant interference graph with an association matching: cheap to build at any n."""
+    rng = np.random.default_rng(seed)
+    rows, cols = [], []
+    for hp in hops:
+        i = np.arange(n)
+        rows += [i, (i + hp) % n]
+        cols += [(i + hp) % n, i]
+    rows, cols = np.concatenate(rows), np.concatenate(cols)
+    S = sp.csr_matrix((rng.uniform(0.1, 1.0, rows.size), (rows, cols)), shape=(n, n))
+    S.sum_duplicates()
+    a = np.arange(0, n - 1, 2)
+    Q = sp.csr_matrix((np.ones(2 * a.size), (np.r_[a, a + 1], np.r_[a + 1, a])), shape=(n, n))
+    S = S - S.multiply(Q)          # a pair is either a gain edge or an association edge
+    S.eliminate_zeros()
+    S.sort_indices()
+    Q.sort_indices()
+    return sp.csr_matrix(S), Q, rng.uniform(1.0, 2.0, n)
+
+
+def test_plan_and_tiles_do_not_depend_on_host_thread_count(monkeypatch):
+    """The plan stages and the tile builder run on all host cores (plan_host.cpp); their output
+    must be the same whatever the thread count, including the 16 fixed row ranges large graphs
+    are tiled in."""
+    state = _ring_state(40000)
+    out = []
+    for threads in ("1", "3", None):
+        if threads is None:
+            monkeypatch.delenv("SIGSDP_HOST_THREADS", raising=False)
+        else:
+            monkeypatch.setenv("SIGSDP_HOST_THREADS", threads)
+        pl = _lib.Plan(state, device=-1, order=1)
+        out.append((pl.pattern(), pl.edges(), pl.vectors(), pl.perm(), pl.tile_stats(64, 300, 2048)))
+    for other in out[1:]:
+        for a, b in zip(out[0][0] + out[0][1] + out[0][2], other[0] + other[1] + other[2]):
+            np.testing.assert_array_equal(a, b)
+        np.testing.assert_array_equal(out[0][3], other[3])
+        assert out[0][4] == other[4]
+    st = out[0][4]
+    assert st["tiles"] >= 40000 // 64 and st["umax"] <= 300
+
+
 def test_plan_rejects_bad_input():
     g = load_case("n75_z8")
     S, Q, h = g["state"]
