@@ -1,5 +1,6 @@
 // C ABI of libsigsdp_mmw.so: handles, device workspace, kernel launches, host fetches.
 // See include/sigsdp_mmw.h for the contract and the reference lines each entry replaces.
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -900,6 +901,60 @@ static int solver_alloc(sigsdp_solver* s) {
     if (blocks > maxblk) blocks = maxblk;
     if (blocks < 1) blocks = 1;
     s->grid = (int)blocks;
+    // Slot table of the two-chunk term kernel (phase_term_staged2: G/2 lanes per row, NT / (G/2)
+    // groups per block): a tile has fewer rows than the block has groups (58 of 64 at cfg4, far
+    // fewer when the caps end a tile early), and the multiply lasts as long as the tile's longest
+    // row.  The spare groups take the second halves of the longest rows.
+    P.tl.slots = nullptr;
+    P.tl.slot_r = 0;
+    if (P.tl.enabled && s->G >= 8 && s->Dp == s->G * (int)(16 / sizeof(T)) && getenv("SIGSDP_NO_SPLIT") == nullptr) {
+        const HostTiles& ht = pl->tiles.at(std::make_tuple(s->RT, P.tl.ucap, P.tl.nnzcap)).h;
+        const int Rs = NT / (s->G / 2), nt = ht.ntiles;
+        bool fits = true;
+        for (int t = 0; t < nt && fits; ++t) fits = ht.trow[t + 1] - ht.trow[t] <= Rs;
+        if (fits) {
+            std::vector<int32_t> slots((size_t)nt * Rs * 4);
+            std::vector<int> idx;
+            std::vector<uint8_t> split;
+            for (int t = 0; t < nt; ++t) {
+                const int r0 = ht.trow[t], r1 = ht.trow[t + 1], nr = r1 - r0;
+                int32_t* sl = slots.data() + (size_t)t * Rs * 4;
+                for (int g2 = 0; g2 < Rs; ++g2) {
+                    sl[g2 * 4 + 0] = -1;
+                    sl[g2 * 4 + 1] = sl[g2 * 4 + 2] = sl[g2 * 4 + 3] = 0;
+                }
+                idx.resize(nr);
+                for (int i = 0; i < nr; ++i) idx[i] = r0 + i;
+                std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) {
+                    return h.rowptr[a + 1] - h.rowptr[a] > h.rowptr[b + 1] - h.rowptr[b];
+                });
+                split.assign(nr, 0);
+                int nsplit = 0;
+                while (nsplit < Rs - nr && nsplit < nr && h.rowptr[idx[nsplit] + 1] - h.rowptr[idx[nsplit]] >= 16) {
+                    split[idx[nsplit] - r0] = 1;
+                    ++nsplit;
+                }
+                int pos = 0;
+                for (int i = 0; i < nsplit; ++i) {   // pairs first: they start at even slots, i.e. inside a warp
+                    const int k = idx[i], p0 = h.rowptr[k], len = h.rowptr[k + 1] - p0, half = (len + 1) / 2;
+                    int32_t* a = sl + (size_t)pos * 4;
+                    a[0] = k; a[1] = p0; a[2] = half; a[3] = 1;
+                    a[4] = k; a[5] = p0 + half; a[6] = len - half; a[7] = 2;
+                    pos += 2;
+                }
+                for (int k = r0; k < r1; ++k) {
+                    if (split[k - r0]) continue;
+                    int32_t* a = sl + (size_t)pos * 4;
+                    a[0] = k; a[1] = h.rowptr[k]; a[2] = h.rowptr[k + 1] - h.rowptr[k]; a[3] = 0;
+                    ++pos;
+                }
+            }
+            int32_t* d_slots = nullptr;
+            CK(s->mem.upload(&d_slots, slots));
+            P.tl.slots = reinterpret_cast<const int4*>(d_slots);
+            P.tl.slot_r = Rs;
+        }
+    }
     return SIGSDP_OK;
 }
 }  // extern "C++"

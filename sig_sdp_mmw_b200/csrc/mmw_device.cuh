@@ -50,6 +50,13 @@ struct TileDev {
     const int4* runs;            // {first column, first shared-memory slot, length, 0}
     const unsigned short* lcol;  // nnz (+ padding)
     const int4* trec;            // 2 per tile: {r0, r1, p0, p1}, {run0, run1, distinct columns, 0}
+    // phase_term_staged2 only (per solver, nullptr otherwise): what each of the slot_r lane
+    // groups of a block does in a tile, {row or -1, first non-zero, non-zeros, role}.  A tile has
+    // fewer rows than groups; the spare groups take the second halves of its longest rows
+    // (role 1 = first half, adds the partial sums of the group to its right; 2 = second half, no
+    // epilogue; 0 = whole row), so the multiply ends with the longest HALF row.
+    const int4* slots;
+    int slot_r;
 };
 
 // device-resident controller: reductions that must be order independent use
@@ -1128,26 +1135,42 @@ __device__ void phase_term_staged2(const Prob<T>& P, const Team& team, const T* 
     const long long tph0 = timed ? clock64() : 0;
     const int ca = lane * VEC, cb2 = (lane + GH) * VEC;
     long long prof[6] = {0, 0, 0, 0, 0, 0};
+    const bool use_slots = tl.slots != nullptr && tl.slot_r == R;
     fence_proxy_async();
     for (int t = team.rank(); t < tl.ntiles; t += team.size()) {
         const int4 trc = tl.trec[2 * t];
         const int r0 = trc.x, r1 = trc.y;
         stage_tile(P, Bin, (const T*)P.Aval, t, st, timed ? &wait_c : nullptr, timed ? prof : nullptr);
-        for (int kb = r0; kb < r1; kb += R) {   // block-uniform trip count
+        for (int kb = r0; kb < r1; kb += R) {   // block-uniform trip count (one trip with a slot table)
             const long long tq0 = timed ? clock64() : 0;
-            const int k = kb + grp;
-            const bool valid = k < r1;
-            const int p0 = valid ? g.rowptr[k] : 0, len = valid ? g.rowptr[k + 1] - p0 : 0;
+            int k, p0, len, role = 0;
+            bool valid;
+            if (use_slots) {
+                const int4 sr = tl.slots[(size_t)t * R + grp];
+                k = sr.x;
+                valid = k >= 0;
+                p0 = sr.y;
+                len = sr.z;
+                role = sr.w;
+            } else {
+                k = kb + grp;
+                valid = k < r1;
+                p0 = valid ? g.rowptr[k] : 0;
+                len = valid ? g.rowptr[k + 1] - p0 : 0;
+            }
+            const bool owner = valid && role != 2;
             if (timed) prof[3] += clock64() - tq0 + (long long)(len & 0);   // row pointer loads
             const long long tq1 = timed ? clock64() : 0;
             double rsb = 0.0, rsf = 0.0, dd = 0.0;
-            if (valid) {
-                V fa, fb;
+            V fa, fb;
+            T acca[VEC], accb[VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) acca[v] = accb[v] = fa.v[v] = fb.v[v] = (T)0;
+            if (owner) {
                 fa.load(P.F + (size_t)k * Dp + ca);   // consumed in the epilogue
                 fb.load(P.F + (size_t)k * Dp + cb2);
-                T acca[VEC], accb[VEC];
-#pragma unroll
-                for (int v = 0; v < VEC; ++v) acca[v] = accb[v] = (T)0;
+            }
+            if (valid) {
                 const unsigned la = st.la + 2u * (unsigned)p0, va = st.va + (unsigned)(W * p0);
                 const unsigned rba = st.rows_a + (unsigned)(ca * W), rbb = st.rows_a + (unsigned)(cb2 * W);
                 int j = 0;
@@ -1186,6 +1209,21 @@ __device__ void phase_term_staged2(const Prob<T>& P, const Team& team, const T* 
                     }
                 }
                 if (timed) prof[4] += clock64() - tq1 + (long long)(acca[0] == (T)12345.678 ? 1 : 0);   // multiply loop
+            }
+            // second halves hand their partial sums to the group on their left (same warp: pairs
+            // start at even slots); a warp without split rows skips the shuffles
+            if (__any_sync(0xffffffffu, role == 1)) {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) {
+                    const T ra = __shfl_down_sync(0xffffffffu, acca[v], GH);
+                    const T rb = __shfl_down_sync(0xffffffffu, accb[v], GH);
+                    if (role == 1) {
+                        acca[v] += ra;
+                        accb[v] += rb;
+                    }
+                }
+            }
+            if (owner) {
                 V bna, bnb;
 #pragma unroll
                 for (int v = 0; v < VEC; ++v) {
@@ -1211,7 +1249,7 @@ __device__ void phase_term_staged2(const Prob<T>& P, const Team& team, const T* 
             }
             bmax = fmax(bmax, rsb);
             fmaxv = fmax(fmaxv, rsf);
-            if (valid && lane == 0) {
+            if (owner && lane == 0) {
                 P.dsq[k] = dd;
                 trp += dd;
             }
