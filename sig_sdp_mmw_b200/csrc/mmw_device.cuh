@@ -1431,19 +1431,33 @@ __device__ void phase_gram_staged2(const Prob<T>& P, const Team& team, double* s
     long long wait_c = 0;
     const long long tph0 = timed ? clock64() : 0;
     const unsigned ca = (unsigned)(lane * VEC * W), cb2 = (unsigned)((lane + GH) * VEC * W);
+    const bool use_slots = tl.slots != nullptr && tl.slot_r == R;
     fence_proxy_async();
     for (int t = team.rank(); t < tl.ntiles; t += team.size()) {
         const int4 trc = tl.trec[2 * t];
         const int r0 = trc.x, r1 = trc.y;
         stage_tile(P, (const T*)P.F, (const T*)nullptr, t, st, timed ? &wait_c : nullptr);
-        for (int kb = r0; kb < r1; kb += R) {   // block-uniform trip count
-            const int k = kb + grp;
-            const bool valid = k < r1;
-            int p0 = 0, len = 0, pd = 0;
-            if (valid) {
-                p0 = g.rowptr[k];
-                len = g.rowptr[k + 1] - p0;
-                pd = g.dpos[k];
+        for (int kb = r0; kb < r1; kb += R) {   // block-uniform trip count (one trip with a slot table)
+            // the term kernel's slot table balances this kernel too: the two halves of a split
+            // row finish their own entries independently, only the row sum is combined
+            int k, p0 = 0, len = 0, pd = 0, role = 0;
+            bool valid;
+            if (use_slots) {
+                const int4 sr = tl.slots[(size_t)t * R + grp];
+                k = sr.x;
+                valid = k >= 0;
+                p0 = sr.y;
+                len = sr.z;
+                role = sr.w;
+                if (valid) pd = g.dpos[k];
+            } else {
+                k = kb + grp;
+                valid = k < r1;
+                if (valid) {
+                    p0 = g.rowptr[k];
+                    len = g.rowptr[k + 1] - p0;
+                    pd = g.dpos[k];
+                }
             }
             // F_k: this lane's two chunks (an idle group reads slot 0 of the tile and discards)
             V fka, fkb;
@@ -1515,7 +1529,11 @@ __device__ void phase_gram_staged2(const Prob<T>& P, const Team& team, double* s
             }
 #pragma unroll
             for (int o = GH / 2; o > 0; o >>= 1) rsum += __shfl_xor_sync(0xffffffffu, rsum, o);
-            if (valid && lane == 0 && !raw) P.r[k] = rsum;
+            {
+                const double right = __shfl_down_sync(0xffffffffu, rsum, GH);
+                if (role == 1) rsum += right;
+            }
+            if (valid && role != 2 && lane == 0 && !raw) P.r[k] = rsum;
         }
     }
     if (timed) {
