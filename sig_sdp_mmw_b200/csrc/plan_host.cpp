@@ -48,11 +48,18 @@ struct Ent {
 
 // fn(begin, end) over [0, n) on the host's cores (contiguous chunks; fn must only touch
 // its own rows' outputs)
+// host threads for the builders: all cores, shared fairly when several ranks of one launch
+// (torchrun's LOCAL_WORLD_SIZE) build their plans on the same box at the same time
+unsigned host_threads() {
+    unsigned nt = std::thread::hardware_concurrency();
+    if (const char* e = getenv("LOCAL_WORLD_SIZE")) nt /= (unsigned)std::max(1, atoi(e));
+    if (const char* e = getenv("SIGSDP_HOST_THREADS")) nt = (unsigned)std::max(1, atoi(e));
+    return std::max(1u, std::min(nt, 32u));
+}
+
 template <class F>
 void parallel_rows(int64_t n, F fn) {
-    unsigned nt = std::thread::hardware_concurrency();
-    if (const char* e = getenv("SIGSDP_HOST_THREADS")) nt = (unsigned)std::max(1, atoi(e));
-    nt = std::max(1u, std::min(nt, 32u));
+    const unsigned nt = host_threads();
     if (n < 4096 || nt == 1) {
         fn(0, n);
         return;
@@ -565,9 +572,7 @@ void build_tiles(const HostPlan& P, int max_rows, int ucap, int nnzcap, HostTile
                 build_tiles_range(P, n * c / nchunks, n * (c + 1) / nchunks, max_rows, T.ucap, nnzcap, run_gap,
                                   T.lcol.data(), parts[c]);
         };
-        unsigned nt = std::thread::hardware_concurrency();
-        if (const char* e = getenv("SIGSDP_HOST_THREADS")) nt = (unsigned)std::max(1, atoi(e));
-        nt = std::max(1u, std::min<unsigned>(nt, (unsigned)nchunks));
+        const unsigned nt = std::min<unsigned>(host_threads(), (unsigned)nchunks);
         std::vector<std::thread> th;
         for (unsigned i = 1; i < nt; ++i) th.emplace_back(work);
         work();
