@@ -41,6 +41,13 @@ CASES = [
     # the instance size of BASELINE configs[4] (1,000-node Monte-Carlo instances)
     dict(name="n1000_z8", env=dict(cell_size=20, sta_density_per_1m2=6.25e-3, seed=4),
          Z=8, nit=40, eta=0.04, rank_radio=2, log_gap=False, seed=9, trace=False),
+    # the sketch widths of the benchmarked kernels: D = 32 (BASELINE cfg3 / cfg4: Z = 16,
+    # rank_radio = 2; the two-chunk fp64 kernels with 16 lanes per row) and D = 64 (cfg2: Z = 8,
+    # rank_radio = 8; the fp32 two-chunk kernels, and the 32-lane fp64 ones)
+    dict(name="n300_z16_d32", env=dict(cell_size=10, sta_density_per_1m2=75e-4, seed=2),
+         Z=16, nit=60, eta=0.04, rank_radio=2, log_gap=False, seed=13, trace=False),
+    dict(name="n500_z8_d64", env=dict(cell_size=10, sta_density_per_1m2=125e-4, seed=1),
+         Z=8, nit=40, eta=0.04, rank_radio=8, log_gap=False, seed=17, trace=False),
 ]
 
 
@@ -202,12 +209,48 @@ def run_evaluate_case(ref):
     np.savez_compressed(os.path.join(GOLD, "evaluate_n75_n300.npz"), **out)
 
 
+def run_r2_pins(ref):
+    """rounding.py:56-66 of the unmodified reference (rand_rounding.get_interference /
+    get_violation_pct) on fixed colourings of three topologies: H = S_gain^T with an empty
+    diagonal (interference received by user k from same-slot users), I_max = h_max.  Pins
+    oracle.conflict_counts and the device counter (sigsdp_round_conflicts)."""
+    rr = ref.rand_rounding
+    out = {}
+    for tag, kw, Z in [("a", dict(cell_size=5, sta_density_per_1m2=75e-4, seed=0), 6),
+                       ("b", dict(cell_size=10, sta_density_per_1m2=75e-4, seed=1), 9),
+                       ("c", dict(cell_size=10, sta_density_per_1m2=125e-4, seed=0), 13)]:
+        e = ref.env(**kw)
+        S, Q, h = e.generate_S_Q_hmax()
+        H = np.asarray(sp.csr_matrix(S).transpose().todense(), dtype=np.float64)
+        np.fill_diagonal(H, 0.)
+        H = np.asarray(H)
+        rs = np.random.RandomState(21)
+        for j in range(3):
+            z = rs.randint(Z, size=S.shape[0])
+            I = np.asarray(rr.get_interference(H, z)).ravel()
+            pct = rr.get_violation_pct(I, np.asarray(h, dtype=np.float64))
+            out["%s%d_z" % (tag, j)] = z.astype(np.int64)
+            out["%s%d_I" % (tag, j)] = I
+            out["%s%d_pct" % (tag, j)] = np.array(pct)
+        out[tag + "_kw"] = np.array([kw["cell_size"], kw["sta_density_per_1m2"], kw["seed"]])
+        out[tag + "_Z"] = np.array(Z)
+    np.savez_compressed(os.path.join(GOLD, "r2_pins.npz"), **out)
+    print("r2_pins: %d colourings" % (len([k for k in out if k.endswith("_z")])))
+
+
 def main():
     ref = load_reference()
     os.makedirs(GOLD, exist_ok=True)
-    run_binary_search_case(ref)
-    run_evaluate_case(ref)
+    only = set(sys.argv[1:])          # optional: names of the cases to (re)generate
+    if not only or "bs_n75" in only:
+        run_binary_search_case(ref)
+    if not only or "evaluate" in only:
+        run_evaluate_case(ref)
+    if not only or "r2_pins" in only:
+        run_r2_pins(ref)
     for c in CASES:
+        if only and c["name"] not in only:
+            continue
         out = run_case(ref, c)
         path = os.path.join(GOLD, c["name"] + ".npz")
         np.savez_compressed(path, **out)

@@ -59,6 +59,7 @@ def load_reference():
     from sim_src.env.env import env
     from sim_src.alg.binary_search_relaxation import binary_search_relaxation
     from sim_src.alg.sdp_solver import sdp_solver
-    ns = types.SimpleNamespace(mmw=mmw, env=env, sdp_solver=sdp_solver,
+    from sim_src.alg.rounding import rand_rounding
+    ns = types.SimpleNamespace(mmw=mmw, env=env, sdp_solver=sdp_solver, rand_rounding=rand_rounding,
                                binary_search_relaxation=binary_search_relaxation)
     return ns

@@ -5,7 +5,7 @@ import pytest
 import scipy.sparse as sp
 
 from oracle import mmw_oracle as orc
-from tests.golden_util import CASES, load_case, omega_stream
+from tests.golden_util import CASES, load_case, load_r2_pins, omega_stream
 
 
 @pytest.fixture(scope="module", params=CASES)
@@ -84,3 +84,16 @@ def test_rounding(name):
                                          lambda n: rs.randint(g["Z"], size=n))
     assert rem == int(g["round1_rem"])
     np.testing.assert_array_equal(z, g["round1_z"])
+
+
+def test_conflict_counts_match_reference_rounding_py():
+    """R2: oracle.conflict_counts against the unmodified reference's
+    rand_rounding.get_interference / get_violation_pct (rounding.py:56-66)."""
+    from sig_sdp_mmw_b200.topology import sparse_env
+    for kw, Z, z, I_ref, pct in load_r2_pins():
+        state = sparse_env(**kw).generate_S_Q_hmax()
+        I, n_vio, n_asso = orc.conflict_counts(z, state)
+        np.testing.assert_allclose(I, I_ref, rtol=1e-13, atol=1e-13)
+        assert n_vio == int(round(pct * z.size))
+        Q = sp.triu(sp.csr_matrix(state[1]), k=1).tocoo()
+        assert n_asso == int(np.sum(z[Q.row] == z[Q.col]))
