@@ -341,8 +341,7 @@ def run_ours(args):
             print(json.dumps({"profiling_run": True, "mode": args.mode, "workload": args.workload, "steps": args.steps,
                               "ms": ms, "taylor_terms": terms, "phase_us": phase.tolist(), "grid": sol.grid,
                               "tile_rows": sol.tile_rows, "smem": sol.smem,
-                              "block0_Mcycles": {k: round(v / 1e6, 3) for k, v in sol.debug_cycles().items()},
-                              "term_profile_Mcycles": sol.debug_term_profile()}))
+                              "barrier_wait_ms": sol.sync_wait_ns() / 1e6}))
         return
 
     # ---- time-to-epsilon (second half of the BASELINE metric): e_max of the running mean X_avgd/i

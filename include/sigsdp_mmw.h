@@ -112,6 +112,48 @@ int sigsdp_solver_create_sharded(const sigsdp_plan* plan, int Z, int D_total, in
                                  int tiling, sigsdp_solver** out);
 int sigsdp_solver_split_step(sigsdp_solver* s, int do_iter, const double* omega_dev, uint64_t seed, void* stream);
 int sigsdp_solver_exchange_buffer(sigsdp_solver* s, void** dev_ptr, int64_t* count);
+
+/* ------------------------------------------------------------ row sharding ----
+ * ONE graph across the GPUs of a box, one process (rank) per GPU -- BASELINE configs[3].
+ * Rank r of `nranks` (<= 8) owns a contiguous range of rows of the locality-ordered pattern
+ * (whole row tiles, balanced by non-zeros) and with them their part of everything:
+ * L_accu / X / X_avgd entries, dual weights (own rows' D and H constraints, the association
+ * edges whose smaller endpoint it owns), sketch rows.  Per Taylor term (scipy
+ * _expm_multiply.py:291-303) the only rows of the sketch block another rank reads are those
+ * of its boundary ("halo"): the SpMM epilogue stores them straight into the neighbour's copy
+ * of the block through peer-mapped memory (NVLink), the row sums r (mmw.py:133) and the
+ * loss weights q (mmw.py:160-163) travel the same way once per iteration, and the grid
+ * barrier that separates the phases is extended across the GPUs: it carries the packed
+ * scalars every rank must agree on (max e_accu and the soft-max sums mmw.py:139, ||A||_1
+ * and the ||.||_inf of the Taylor terms _expm_multiply.py:259-303, the trace mmw.py:183),
+ * reduced in rank order so all ranks continue with identical bits.  No host involvement and
+ * no NCCL call inside sigsdp_solver_iterate.
+ *
+ * Set-up on every rank (same plan arguments, same Z / D / eta / dtype / tiling):
+ *   sigsdp_solver_create_rows(plan, ..., rank, nranks, max_blocks, &s)
+ *   sigsdp_solver_shard_ipc_handle(s, h64)       64-byte CUDA IPC handle of the exchange arena
+ *   (exchange the handles between the processes: e.g. torch.distributed.all_gather)
+ *   sigsdp_solver_shard_attach_ipc(s, handles)   nranks x 64 bytes, in rank order
+ * or, for several shards driven by ONE process (tests; shards on one GPU or on P2P-capable
+ * GPUs): sigsdp_solver_shard_attach_local(all the shards in rank order).
+ * Then every rank calls sigsdp_solver_iterate with the same arguments; the kernels of the
+ * ranks synchronise among themselves (a barrier that does not complete within
+ * SIGSDP_SHARD_TIMEOUT_S seconds, default 20, traps -- e.g. a rank that never launched).
+ * sigsdp_solver_reset on a shard must be followed by a barrier between the ranks (host
+ * side) before any of them iterates again.  max_blocks > 0 caps the grid (shards sharing one
+ * GPU must be co-resident: use blocks-per-GPU / nranks); 0 = fill the GPU.
+ * The sigsdp_solver_get_* fetches of a shard return the entries the rank owns and zeros
+ * elsewhere, so the sum over the ranks is the whole vector.
+ * info[0..11] = rank, nranks, first row, end row, first tile, end tile, halo rows pushed per
+ * Taylor term (x 2 blocks x Dp x word bytes = bytes sent), halo rows read, arena bytes,
+ * incident association edges, owned association edges, attached. */
+int sigsdp_solver_create_rows(const sigsdp_plan* plan, int Z, int D, double eta, int dtype, int tiling, int rank,
+                              int nranks, int max_blocks, sigsdp_solver** out);
+int sigsdp_solver_shard_info(const sigsdp_solver* s, int64_t info[12]);
+int sigsdp_solver_shard_arena(sigsdp_solver* s, void** dev_ptr, int64_t* bytes);
+int sigsdp_solver_shard_ipc_handle(sigsdp_solver* s, void* handle64_host);
+int sigsdp_solver_shard_attach_ipc(sigsdp_solver* s, const void* handles64_host);
+int sigsdp_solver_shard_attach_local(sigsdp_solver* const* ranks, int count);
 void sigsdp_solver_destroy(sigsdp_solver* s);
 int sigsdp_solver_reset(sigsdp_solver* s, void* stream);
 int sigsdp_solver_set_mode(sigsdp_solver* s, int mode);
@@ -147,6 +189,10 @@ int sigsdp_solver_get_dual(sigsdp_solver* s, double* Y_host, double* e_accu_host
 int sigsdp_solver_get_X(sigsdp_solver* s, int averaged, double* diag_host, double* gain_host, double* asso_host);
 int sigsdp_solver_get_L(sigsdp_solver* s, double* diag_host, double* gain_host, double* asso_host);
 int sigsdp_solver_get_sketch(sigsdp_solver* s, double* Yh_host);
+/* Inverse of sigsdp_solver_get_X: load X (or the running sum X_avgd) from edge-list form,
+ * every entry -- e.g. the sum of the row shards' fetches, before the final factor. */
+int sigsdp_solver_set_X(sigsdp_solver* s, int averaged, const double* diag_host, const double* gain_host,
+                        const double* asso_host);
 /* Per-iteration Taylor controller history of the last `count` iterations
  * (scipy _expm_multiply.py:259-303, _fragment_3_1 :503-558): m_star, s, executed
  * terms (int32 each) and ||A - mu I||_1, mu (fp64 each).  Any pointer may be NULL. */
@@ -156,14 +202,10 @@ int sigsdp_solver_get_history(sigsdp_solver* s, int count, int32_t* m_star_host,
  * dual (mmw.py:124-142) | loss (:144-170) | sketch + Gram (:172-197) -- what the
  * reference logs as mmw_dual / mmw_loss / mmw_expm.  Fused mode only (zeros otherwise). */
 int sigsdp_solver_get_phase_times(sigsdp_solver* s, int count, double* us_host);
-/* Block-0 cycle counters of the fused kernel since create/reset (SM clock cycles):
- * [0] Taylor-term staging wait, [1] Taylor-term compute, [2] Gram staging wait,
- * [3] Gram compute, [4] grid-barrier wait, [5] dual, [6] exp, [7] loss.  Diagnostics. */
+/* Diagnostics since create/reset: out8[4] = nanoseconds the fused kernel's leader thread spent
+ * in team barriers (grid barriers; for a row shard this includes the cross-GPU wait), the other
+ * entries are reserved (0). */
 int sigsdp_solver_debug_cycles(sigsdp_solver* s, int64_t out8[8]);
-/* Diagnostics: cumulative SM cycles of block 0 / thread 0 inside the staged Taylor term since
- * reset: [0] tile barrier, [1] metadata + copy issue, [2] copy wait, [3] row pointer loads,
- * [4] multiply loop, [5] unused. */
-int sigsdp_solver_debug_term_profile(sigsdp_solver* s, double out6[6]);
 /* total Taylor terms (SpMM passes) executed since create/reset */
 int sigsdp_solver_total_terms(sigsdp_solver* s, int64_t* out);
 

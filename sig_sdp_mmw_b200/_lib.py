@@ -47,6 +47,13 @@ def load():
         "sigsdp_solver_create_sharded": [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.POINTER(vp)],
         "sigsdp_solver_split_step": [vp, C.c_int, vp, C.c_uint64, vp],
         "sigsdp_solver_exchange_buffer": [vp, C.POINTER(vp), i64p],
+        "sigsdp_solver_create_rows": [vp, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)],
+        "sigsdp_solver_shard_info": [vp, i64p],
+        "sigsdp_solver_shard_arena": [vp, C.POINTER(vp), i64p],
+        "sigsdp_solver_shard_ipc_handle": [vp, vp],
+        "sigsdp_solver_shard_attach_ipc": [vp, vp],
+        "sigsdp_solver_shard_attach_local": [C.POINTER(vp), C.c_int],
+        "sigsdp_solver_set_X": [vp, C.c_int, f64p, f64p, f64p],
         "sigsdp_solver_reset": [vp, vp],
         "sigsdp_solver_set_mode": [vp, C.c_int],
         "sigsdp_solver_info": [vp, i64p],
@@ -58,7 +65,6 @@ def load():
         "sigsdp_solver_get_history": [vp, C.c_int, i32p, i32p, i32p, f64p, f64p],
         "sigsdp_solver_total_terms": [vp, i64p],
         "sigsdp_solver_debug_cycles": [vp, i64p],
-        "sigsdp_solver_debug_term_profile": [vp, f64p],
         "sigsdp_solver_get_phase_times": [vp, C.c_int, f64p],
         "sigsdp_solver_xavg_matrix": [vp, C.c_double, vp],
         "sigsdp_solver_gap_prepare": [vp, f64p, vp],
@@ -168,14 +174,22 @@ class Plan:
 class Solver:
     """MMW state for one (plan, Z, D, eta, dtype), see sigsdp_solver_create."""
 
-    def __init__(self, plan, Z, D, eta, dtype=F64, mode=MODE_FUSED, tiling=-1, D_total=None, col0=0):
+    def __init__(self, plan, Z, D, eta, dtype=F64, mode=MODE_FUSED, tiling=-1, D_total=None, col0=0,
+                 rows=None, max_blocks=0):
+        """rows=(rank, nranks): a row shard (sigsdp_solver_create_rows); attach its peers before
+        iterating (attach_local / ipc_handle + attach_ipc)."""
         lib = load()
         self.plan = plan
         self.handle = C.c_void_p()
         if D_total is None:
             D_total = D
-        check(lib.sigsdp_solver_create_sharded(plan.handle, int(Z), int(D_total), int(col0), int(D), float(eta),
-                                               int(dtype), int(tiling), C.byref(self.handle)))
+        self.rows = tuple(int(x) for x in rows) if rows is not None else None
+        if self.rows is not None:
+            check(lib.sigsdp_solver_create_rows(plan.handle, int(Z), int(D), float(eta), int(dtype), int(tiling),
+                                                self.rows[0], self.rows[1], int(max_blocks), C.byref(self.handle)))
+        else:
+            check(lib.sigsdp_solver_create_sharded(plan.handle, int(Z), int(D_total), int(col0), int(D), float(eta),
+                                                   int(dtype), int(tiling), C.byref(self.handle)))
         self.D_total, self.col0 = int(D_total), int(col0)
         if mode != MODE_FUSED:
             check(lib.sigsdp_solver_set_mode(self.handle, mode))
@@ -206,6 +220,37 @@ class Solver:
 
     def split_step(self, do_iter=True, omega_dev_ptr=None, seed=0, stream=None):
         check(load().sigsdp_solver_split_step(self.handle, int(bool(do_iter)), omega_dev_ptr, int(seed), stream))
+
+    # ---- row shards
+    def shard_info(self):
+        a = (C.c_int64 * 12)()
+        check(load().sigsdp_solver_shard_info(self.handle, a))
+        keys = ["rank", "nranks", "row_lo", "row_hi", "tile_lo", "tile_hi", "halo_send_rows", "halo_recv_rows",
+                "arena_bytes", "n_inc", "n_inc_owned", "attached"]
+        return dict(zip(keys, [int(x) for x in a]))
+
+    def ipc_handle(self):
+        buf = (C.c_ubyte * 64)()
+        check(load().sigsdp_solver_shard_ipc_handle(self.handle, buf))
+        return bytes(buf)
+
+    def attach_ipc(self, handles):
+        """handles: the ranks' 64-byte IPC handles in rank order (this rank's own entry is ignored)."""
+        blob = b"".join(handles)
+        assert len(blob) == 64 * self.rows[1]
+        buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        check(load().sigsdp_solver_shard_attach_ipc(self.handle, buf))
+
+    @staticmethod
+    def attach_local(shards):
+        arr = (C.c_void_p * len(shards))(*[s.handle for s in shards])
+        check(load().sigsdp_solver_shard_attach_local(arr, len(shards)))
+
+    def set_X(self, averaged, diag, gain, asso):
+        d = np.ascontiguousarray(diag, dtype=np.float64); g = np.ascontiguousarray(gain, dtype=np.float64)
+        a = np.ascontiguousarray(asso, dtype=np.float64)
+        assert d.size == self.plan.n and g.size == self.plan.E_g and a.size == self.plan.E_a
+        check(load().sigsdp_solver_set_X(self.handle, int(averaged), _p(d, C.c_double), _p(g, C.c_double), _p(a, C.c_double)))
 
     def exchange_buffer(self):
         """(device pointer, number of doubles) of the per-iteration all-reduce buffer."""
@@ -267,16 +312,11 @@ class Solver:
         check(load().sigsdp_solver_get_matrix(self.handle, _p(v, C.c_double)))
         return v
 
-    def debug_cycles(self):
+    def sync_wait_ns(self):
+        """Nanoseconds the fused kernel's leader thread spent in team barriers since reset."""
         a = (C.c_int64 * 8)()
         check(load().sigsdp_solver_debug_cycles(self.handle, a))
-        keys = ["term_wait", "term_compute", "gram_wait", "gram_compute", "grid_sync", "dual", "exp", "loss"]
-        return dict(zip(keys, [int(x) for x in a]))
-
-    def debug_term_profile(self):
-        a = np.zeros(6)
-        check(load().sigsdp_solver_debug_term_profile(self.handle, _p(a, C.c_double)))
-        return dict(zip(["tile_barrier", "issue", "copy_wait", "rowptr", "multiply", "-"], (a / 1e6).round(3).tolist()))
+        return int(a[4])
 
     def total_terms(self):
         v = C.c_int64()

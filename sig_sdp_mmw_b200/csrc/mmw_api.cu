@@ -11,7 +11,7 @@
 #include <vector>
 
 #include "../../include/sigsdp_mmw.h"
-#include "mmw_device.cuh"
+#include "mmw_kernels.cuh"
 #include "plan_host.h"
 
 using namespace sigsdp;
@@ -131,6 +131,15 @@ struct sigsdp_solver {
     // sketch-column shard: columns [col0, col0 + D) of a Dtot-wide sketch (Dtot == D: unsharded)
     int Dtot = 0, col0 = 0;
     bool pending_finish = false;   // split mode: a raw Gram is waiting for its all-reduce + finish
+    // row shard: rank `rank` of `nranks` owns rows [row_lo, row_hi) (nranks == 1: unsharded)
+    int nranks = 1, rank = 0, max_blocks = 0;
+    int row_lo = 0, row_hi = 0, tile_lo = 0, tile_hi = 0, n_inc = 0, n_inc_owned = 0;
+    long long halo_send_rows = 0, halo_recv_rows = 0;   // per Taylor term: rows pushed to / read from peers
+    std::vector<int32_t> rank_row0;   // nranks + 1: first row of every rank
+    void* arena = nullptr;            // exchange arena (plain cudaMalloc: IPC-exportable)
+    size_t arena_bytes = 0;
+    bool attached = false;
+    std::vector<void*> ipc_mapped;    // peers' arenas opened through CUDA IPC
     // scratch of the eigen-solver building blocks (allocated on first use)
     double* Mval = nullptr;      // nnz: a symmetric matrix on the plan's pattern
     double* rtmp = nullptr;      // n
@@ -157,86 +166,13 @@ struct sigsdp_batch {
 };
 
 // ---------------------------------------------------------------------------
-// kernels
-template <typename T, int G>
-__global__ void __launch_bounds__(NT, 2) k_fused(Prob<T> P, int n_iters, int do_finish) {
-    extern __shared__ __align__(16) unsigned char dyn_smem[];
-    GridTeam team(&P.ctrl->bar);
-    run_iterations<T, G>(P, team, n_iters, dyn_smem, do_finish);
-}
-template <typename T, int G>
-__global__ void __launch_bounds__(NT, 2) k_dual(Prob<T> P) {
-    __shared__ double sh[NWARP + 2];
-    phase_dual<T, G>(P, StepTeam(), sh);
-}
-template <typename T, int G>
-__global__ void __launch_bounds__(NT, 2) k_exp(Prob<T> P) {
-    __shared__ double sh[NWARP + 2];
-    phase_exp<T, G>(P, StepTeam(), sh);
-}
-template <typename T, int G>
-__global__ void __launch_bounds__(NT, 2) k_loss(Prob<T> P, int it_local) {
-    __shared__ double sh[NWARP + 2];
-    phase_loss<T, G>(P, StepTeam(), it_local, sh);
-}
-template <typename T, int G>
-__global__ void __launch_bounds__(NT, 2) k_term(Prob<T> P, const T* bin, T* bout, double coeff, double mu, int slot) {
-    extern __shared__ __align__(16) unsigned char dyn_smem[];
-    __shared__ double sh[NWARP + 2];
-    if (P.tl.enabled) {
-        Stage<T> st;
-        stage_setup(P, dyn_smem, st);
-        if (G >= 8 && P.Dp == G * Vec<T>::N)
-            phase_term_staged2<T, G>(P, StepTeam(), bin, bout, coeff, slot, sh, st);
-        else
-            phase_term_staged<T, G>(P, StepTeam(), bin, bout, coeff, slot, sh, st);
-    } else {
-        phase_term<T, G>(P, StepTeam(), bin, bout, coeff, mu, slot, sh);
-    }
-}
-template <typename T, int G>
-__global__ void __launch_bounds__(NT, 2) k_copy(Prob<T> P, T* dst) {
-    phase_copy<T, G>(P, StepTeam(), dst);
-}
-template <typename T, int G>
-__global__ void __launch_bounds__(NT, 2) k_gram(Prob<T> P) {
-    extern __shared__ __align__(16) unsigned char dyn_smem[];
-    __shared__ double sh[NWARP + 2];
-    if (P.tl.enabled) {
-        Stage<T> st;
-        stage_setup(P, dyn_smem, st);
-        if (G >= 8 && P.Dp == G * Vec<T>::N)
-            phase_gram_staged2<T, G>(P, StepTeam(), sh, st);
-        else
-            phase_gram_staged<T, G>(P, StepTeam(), sh, st);
-    } else {
-        phase_gram<T, G>(P, StepTeam(), sh);
-    }
-}
-// batch: one thread block per independent instance, __syncthreads as the team barrier
-template <typename T, int G>
-__global__ void __launch_bounds__(NT, 2) k_batch(const Prob<T>* probs, int n_iters, unsigned long long seed) {
-    extern __shared__ __align__(16) unsigned char dyn_smem[];
-    __shared__ Prob<T> Ps;
-    {
-        const int* src = reinterpret_cast<const int*>(probs + blockIdx.x);
-        int* dst = reinterpret_cast<int*>(&Ps);
-        for (int i = threadIdx.x; i < (int)(sizeof(Prob<T>) / sizeof(int)); i += NT) dst[i] = src[i];
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            Ps.omega = nullptr;   // (the uploaded descriptor carries the instance id in its seed field)
-            Ps.seed = seed + 0x9E3779B97F4A7C15ull * (Ps.seed + 1ull);
-        }
-        __syncthreads();
-    }
-    CtaTeam team;
-    run_iterations<T, G>(Ps, team, n_iters, dyn_smem);
-}
-
 // stepwise controller: single-thread kernels that publish decisions for the host
 __global__ void k_begin(Ctrl* ctrl) {
     TaylorState ts;
-    taylor_begin(ctrl, ts);
+    ts.a1 = dkey_pos_inv(ld_u64(&ctrl->a1_key));
+    ts.c1 = dkey_pos_inv(ld_u64(&ctrl->c1_key));
+    ts.mu = ctrl->mu;
+    taylor_select(ts.a1, ts.m_star, ts.s);
     ctrl->m_star = ts.m_star;
     ctrl->s = ts.s;
     ctrl->c1 = ts.c1;
@@ -249,17 +185,6 @@ __global__ void k_decide(Ctrl* ctrl, int slot, double c1, double tol) {
     ctrl->done = (c1 + c2 <= tol * fn) ? 1 : 0;
     ctrl->c1 = c2;
     ctrl->a1 = fn;
-}
-template <typename T>
-__global__ void k_record(Prob<T> P, int it_local, int m_star, long long s, double a1, double mu, int nterms) {
-    TaylorState ts;
-    ts.m_star = m_star;
-    ts.s = s;
-    ts.a1 = a1;
-    ts.mu = mu;
-    ts.c1 = 0.0;
-    record_history(P, P.ctrl->iter + it_local, ts, nterms);
-    P.ctrl->total_terms += nterms;
 }
 __global__ void k_advance(Ctrl* ctrl, int n_iters) { ctrl->iter += n_iters; }
 
@@ -546,42 +471,31 @@ template <typename T> static Prob<T>& prob_of(sigsdp_solver* s);
 template <> Prob<double>& prob_of<double>(sigsdp_solver* s) { return s->p64; }
 template <> Prob<float>& prob_of<float>(sigsdp_solver* s) { return s->p32; }
 
-#define FOR_G(Gv, BODY)                                   \
-    switch (Gv) {                                         \
-        case 4: { constexpr int G = 4; BODY; } break;     \
-        case 8: { constexpr int G = 8; BODY; } break;     \
-        case 16: { constexpr int G = 16; BODY; } break;   \
-        default: { constexpr int G = 32; BODY; } break;   \
-    }
-
-template <typename T, int G>
-static int occupancy_fused(int* occ, size_t smem) {
-    if (smem > 48 * 1024) {
-        CK(cudaFuncSetAttribute(k_fused<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CK(cudaFuncSetAttribute(k_term<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CK(cudaFuncSetAttribute(k_gram<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    }
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_fused<T, G>, NT, smem));
-    return SIGSDP_OK;
+static const KernelSet& kset_of(int dtype, int G) {
+    if (dtype == SIGSDP_F64) return G == 4 ? ks_f64_g4 : G == 8 ? ks_f64_g8 : G == 16 ? ks_f64_g16 : ks_f64_g32;
+    return G == 4 ? ks_f32_g4 : G == 8 ? ks_f32_g8 : G == 16 ? ks_f32_g16 : ks_f32_g32;
 }
+static const void* prob_ptr(const sigsdp_solver* s) {
+    return s->dtype == SIGSDP_F64 ? (const void*)&s->p64 : (const void*)&s->p32;
+}
+static Ctrl* ctrl_of(const sigsdp_solver* s) { return s->dtype == SIGSDP_F64 ? s->p64.ctrl : s->p32.ctrl; }
 
-template <typename T, int G>
 static int launch_fused(sigsdp_solver* s, int n_iters, cudaStream_t st, int do_finish = 0) {
-    Prob<T> P = prob_of<T>(s);
-    void* args[] = {(void*)&P, (void*)&n_iters, (void*)&do_finish};
-    CK(cudaLaunchCooperativeKernel((void*)k_fused<T, G>, dim3(s->grid), dim3(NT), args, s->smem, st));
+    CK(kset_of(s->dtype, s->G).fused(prob_ptr(s), s->grid, s->smem, n_iters, do_finish, s->nranks > 1, st));
     return SIGSDP_OK;
 }
 
-template <typename T, int G>
+template <typename T>
 static int run_stepwise(sigsdp_solver* s, int n_iters, cudaStream_t st) {
-    Prob<T> P = prob_of<T>(s);
-    const dim3 grid(s->grid), blk(NT);
+    const Prob<T>& P = prob_of<T>(s);
+    const KernelSet& ks = kset_of(s->dtype, s->G);
+    const void* pp = &P;
+    const int grid = s->grid;
     Ctrl hc;
     for (int it = 0; it < n_iters; ++it) {
-        k_dual<T, G><<<grid, blk, 0, st>>>(P);
-        k_exp<T, G><<<grid, blk, 0, st>>>(P);
-        k_loss<T, G><<<grid, blk, 0, st>>>(P, it);
+        ks.dual(pp, grid, st);
+        ks.exp(pp, grid, st);
+        ks.loss(pp, grid, it, st);
         k_begin<<<1, 1, 0, st>>>(P.ctrl);
         CK(cudaMemcpyAsync(&hc, P.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
@@ -594,12 +508,12 @@ static int run_stepwise(sigsdp_solver* s, int n_iters, cudaStream_t st) {
         int tcount = 0;
         for (long long si = 0; si < ss; ++si) {
             if (si > 0) {
-                k_copy<T, G><<<grid, blk, 0, st>>>(P, bin);
+                ks.copy(pp, grid, bin, st);
                 c1 = fn_last;
             }
             for (int j = 0; j < m_star; ++j) {
                 const int slot = tcount % 3;
-                k_term<T, G><<<grid, blk, s->smem, st>>>(P, bin, bout, 1.0 / ((double)ss * (double)(j + 1)), mu, slot);
+                ks.term(pp, grid, s->smem, bin, bout, 1.0 / ((double)ss * (double)(j + 1)), mu, slot, st);
                 k_decide<<<1, 1, 0, st>>>(P.ctrl, slot, c1, P.tol);
                 CK(cudaMemcpyAsync(&hc, P.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
                 CK(cudaStreamSynchronize(st));
@@ -612,8 +526,8 @@ static int run_stepwise(sigsdp_solver* s, int n_iters, cudaStream_t st) {
                 if (hc.done) break;
             }
         }
-        k_record<T><<<1, 1, 0, st>>>(P, it, m_star, ss, a1, mu, tcount);
-        k_gram<T, G><<<grid, blk, s->smem, st>>>(P);
+        ks.record(pp, it, m_star, ss, a1, mu, tcount, st);
+        ks.gram(pp, grid, s->smem, st);
         CK(cudaGetLastError());
     }
     k_advance<<<1, 1, 0, st>>>(P.ctrl, n_iters);
@@ -793,18 +707,40 @@ static int solver_alloc(sigsdp_solver* s) {
     CK(s->mem.alloc(&P.u, s->C));
     CK(s->mem.alloc(&P.Y, s->C));
     CK(s->mem.alloc(&P.Ybar, s->C));
-    CK(s->mem.alloc(&P.q, n));
     CK(s->mem.alloc(&P.Xv, h.nnz));
     CK(s->mem.alloc(&P.Xbarv, h.nnz));
-    CK(s->mem.alloc(&P.r, n));
     CK(s->mem.alloc(&P.graw, h.nnz + n));   // [graw | dsq]: one buffer, so one all-reduce in split mode
     P.dsq = P.graw + h.nnz;
     P.Dtot = s->Dtot;
     P.col0 = s->col0;
     P.split = s->Dtot != s->D ? 1 : 0;
-    CK(s->mem.alloc(&P.B0, (size_t)n * s->Dp));
-    CK(s->mem.alloc(&P.B1, (size_t)n * s->Dp));
-    CK(s->mem.alloc(&P.F, (size_t)n * s->Dp));
+    P.sh = ShardDev{};
+    P.sh.nranks = 1;
+    if (s->nranks > 1) {
+        // Exchange arena: what the peers write into -- barrier flags and scalar inbox, the three
+        // sketch blocks and the two n-vectors whose halo entries neighbours push -- in ONE plain
+        // cudaMalloc block with the same layout on every rank, so a peer's copy of an element
+        // is this rank's address plus a constant, and one IPC handle per rank maps everything.
+        const size_t blk = (((size_t)n * s->Dp * sizeof(T)) + 255) & ~(size_t)255;
+        const size_t vec = (((size_t)n * sizeof(double)) + 255) & ~(size_t)255;
+        s->arena_bytes = 4096 + 3 * blk + 2 * vec;
+        CK(cudaMalloc(&s->arena, s->arena_bytes));
+        CK(cudaMemset(s->arena, 0, s->arena_bytes));
+        char* base = static_cast<char*>(s->arena);
+        P.sh.flags = reinterpret_cast<unsigned long long*>(base);
+        P.sh.inbox = reinterpret_cast<unsigned long long*>(base + 256);
+        P.B0 = reinterpret_cast<T*>(base + 4096);
+        P.B1 = reinterpret_cast<T*>(base + 4096 + blk);
+        P.F = reinterpret_cast<T*>(base + 4096 + 2 * blk);
+        P.r = reinterpret_cast<double*>(base + 4096 + 3 * blk);
+        P.q = reinterpret_cast<double*>(base + 4096 + 3 * blk + vec);
+    } else {
+        CK(s->mem.alloc(&P.q, n));
+        CK(s->mem.alloc(&P.r, n));
+        CK(s->mem.alloc(&P.B0, (size_t)n * s->Dp));
+        CK(s->mem.alloc(&P.B1, (size_t)n * s->Dp));
+        CK(s->mem.alloc(&P.F, (size_t)n * s->Dp));
+    }
     s->B0 = P.B0;
     s->B1 = P.B1;
     s->F = P.F;
@@ -838,8 +774,10 @@ static int solver_alloc(sigsdp_solver* s) {
             // phases take ceil(tiles / grid) tile times: when the row count is what ends a tile
             // (not the shared-memory caps), shrink the tiles until the last wave is full too.
             // cfg4: 1585 tiles of 64 rows = 5.35 waves -> 1730 tiles of 58 rows = 5.85 waves.
-            const double grid_est = 2.0 * pl->num_sms, n_rows = (double)h.n;
-            const double avg_nnz = (double)h.nnz / n_rows;
+            // (a row-sharded rank deals only its own 1/nranks of the rows)
+            const double grid_est = s->max_blocks > 0 ? (double)s->max_blocks : 2.0 * pl->num_sms;
+            const double n_rows = (double)h.n / s->nranks;
+            const double avg_nnz = (double)h.nnz / (double)h.n;
             if (avg_nnz * max_rows <= 0.95 * nnzcap && n_rows > grid_est * max_rows) {
                 const double waves = std::ceil(1.015 * n_rows / max_rows / grid_est);
                 max_rows = std::min(max_rows, std::max(16, (int)std::ceil(1.02 * n_rows / (grid_est * waves))));
@@ -890,13 +828,98 @@ static int solver_alloc(sigsdp_solver* s) {
         }
     }
     tm.lap("tiles build + upload");
+    // ---- row shard: this rank's rows (whole tiles), halo masks, incident association edges
+    const HostTiles* htiles = s->RT > 0 ? &pl->tiles.at(std::make_tuple(s->RT, P.tl.ucap, P.tl.nnzcap)).h : nullptr;
+    {
+        const int nr = s->nranks;
+        // cut points: the boundary (tile start, or row when untiled) closest to r/nranks of the non-zeros
+        s->rank_row0.assign(nr + 1, 0);
+        std::vector<int32_t> cut_tile(nr + 1, 0);
+        const int nb = htiles ? htiles->ntiles : (int)n;
+        auto brow = [&](int b) { return htiles ? htiles->trow[b] : b; };
+        for (int r = 1; r < nr; ++r) {
+            const double target = (double)h.nnz * r / nr;
+            int lo = cut_tile[r - 1], hi = nb;
+            while (lo < hi) {   // first boundary whose cumulative non-zeros reach the target
+                const int mid = (lo + hi) / 2;
+                if ((double)h.rowptr[brow(mid)] < target) lo = mid + 1; else hi = mid;
+            }
+            cut_tile[r] = std::max(lo, cut_tile[r - 1]);
+            s->rank_row0[r] = brow(cut_tile[r]);
+        }
+        cut_tile[nr] = nb;
+        s->rank_row0[nr] = (int32_t)n;
+        s->row_lo = s->rank_row0[s->rank];
+        s->row_hi = s->rank_row0[s->rank + 1];
+        s->tile_lo = htiles ? cut_tile[s->rank] : 0;
+        s->tile_hi = htiles ? cut_tile[s->rank + 1] : 0;
+        s->n_inc = s->n_inc_owned = (int)h.E_a;
+        P.sh.rank = s->rank;
+        P.sh.nranks = nr;
+        P.sh.row_lo = s->row_lo;
+        P.sh.row_hi = s->row_hi;
+        P.sh.tile_lo = s->tile_lo;
+        P.sh.tile_hi = s->tile_hi;
+        P.sh.timeout_ns = 20000000000ull;
+        if (const char* e = getenv("SIGSDP_SHARD_TIMEOUT_S")) P.sh.timeout_ns = (unsigned long long)(atof(e) * 1e9);
+        if (nr > 1) {
+            if (s->row_hi <= s->row_lo) return fail(SIGSDP_EINVAL, "more ranks than row tiles: a rank would own no rows");
+            auto owner = [&](int32_t row) {
+                return (int)(std::upper_bound(s->rank_row0.begin() + 1, s->rank_row0.end(), row) - (s->rank_row0.begin() + 1));
+            };
+            std::vector<uint8_t> pmask(n, 0), seen(n, 0);
+            std::vector<int32_t> own_e, own_p, for_e, for_p;
+            long long send = 0, recv = 0;
+            for (int32_t k = s->row_lo; k < s->row_hi; ++k) {
+                unsigned m = 0;
+                for (int32_t p = h.rowptr[k]; p < h.rowptr[k + 1]; ++p) {
+                    const int32_t c = h.col[p];
+                    const bool own_c = c >= s->row_lo && c < s->row_hi;
+                    if (!own_c) {
+                        m |= 1u << owner(c);
+                        if (!seen[c]) {
+                            seen[c] = 1;
+                            ++recv;
+                        }
+                    }
+                    if (h.eid[p] >= h.E_g) {
+                        if (k < c) {
+                            own_e.push_back(h.eid[p] - (int32_t)h.E_g);
+                            own_p.push_back(p);
+                        } else if (!own_c) {
+                            for_e.push_back(h.eid[p] - (int32_t)h.E_g);
+                            for_p.push_back(p);
+                        }
+                    }
+                }
+                pmask[k] = (uint8_t)m;
+                send += __builtin_popcount(m);
+            }
+            s->halo_send_rows = send;
+            s->halo_recv_rows = recv;
+            s->n_inc_owned = (int)own_e.size();
+            own_e.insert(own_e.end(), for_e.begin(), for_e.end());
+            own_p.insert(own_p.end(), for_p.begin(), for_p.end());
+            s->n_inc = (int)own_e.size();
+            uint8_t* d_pm;
+            int32_t *d_ie, *d_ip;
+            CK(s->mem.upload(&d_pm, pmask));
+            CK(s->mem.upload(&d_ie, own_e));
+            CK(s->mem.upload(&d_ip, own_p));
+            P.sh.pmask = d_pm;
+            P.sh.inc_e = d_ie;
+            P.sh.inc_pos = d_ip;
+        }
+        P.sh.n_inc = s->n_inc;
+        P.sh.n_inc_owned = s->n_inc_owned;
+    }
     // launch geometry: persistent grid, one tile per block iteration
-    int occ = 0, rc = SIGSDP_OK;
-    FOR_G(s->G, rc = (occupancy_fused<T, G>(&occ, s->smem)));
-    if (rc != SIGSDP_OK) return rc;
+    int occ = 0;
+    CK(kset_of(s->dtype, s->G).prepare(s->smem, s->nranks > 1, &occ));
     if (occ < 1) return fail(SIGSDP_ECUDA, "fused kernel does not fit on an SM");
-    int64_t tiles = s->RT > 0 ? s->ntiles : (n + R - 1) / R;
+    int64_t tiles = s->RT > 0 ? (s->tile_hi - s->tile_lo) : (s->row_hi - s->row_lo + R - 1) / R;
     int64_t blocks = (int64_t)pl->num_sms * occ;
+    if (s->max_blocks > 0 && blocks > s->max_blocks) blocks = s->max_blocks;
     if (blocks > tiles) blocks = tiles;
     if (blocks > maxblk) blocks = maxblk;
     if (blocks < 1) blocks = 1;
@@ -908,7 +931,7 @@ static int solver_alloc(sigsdp_solver* s) {
     P.tl.slots = nullptr;
     P.tl.slot_r = 0;
     if (P.tl.enabled && s->G >= 8 && s->Dp == s->G * (int)(16 / sizeof(T)) && getenv("SIGSDP_NO_SPLIT") == nullptr) {
-        const HostTiles& ht = pl->tiles.at(std::make_tuple(s->RT, P.tl.ucap, P.tl.nnzcap)).h;
+        const HostTiles& ht = *htiles;
         const int Rs = NT / (s->G / 2), nt = ht.ntiles;
         bool fits = true;
         for (int t = 0; t < nt && fits; ++t) fits = ht.trow[t + 1] - ht.trow[t] <= Rs;
@@ -980,6 +1003,7 @@ static int solver_reset_impl(sigsdp_solver* s, cudaStream_t st) {
     CK(cudaMemsetAsync(P.B1, 0, (size_t)n * s->Dp * sizeof(T), st));
     CK(cudaMemsetAsync(P.F, 0, (size_t)n * s->Dp * sizeof(T), st));
     CK(cudaMemsetAsync(P.ctrl, 0, sizeof(Ctrl), st));
+    if (s->arena) CK(cudaMemsetAsync(s->arena, 0, 4096, st));   // barrier epochs and scalar inbox (see sigsdp_solver_reset)
     CK(cudaMemsetAsync(P.hist_m, 0, HIST * sizeof(int), st));
     CK(cudaMemsetAsync(P.hist_s, 0, HIST * sizeof(int), st));
     CK(cudaMemsetAsync(P.hist_nt, 0, HIST * sizeof(int), st));
@@ -1003,8 +1027,23 @@ int sigsdp_solver_create_tiled(const sigsdp_plan* plan, int Z, int D, double eta
     return sigsdp_solver_create_sharded(plan, Z, D, 0, D, eta, dtype, tiling, out);
 }
 
+static int solver_create_common(const sigsdp_plan* plan, int Z, int D_total, int col0, int D, double eta, int dtype,
+                                int tiling, int rank, int nranks, int max_blocks, sigsdp_solver** out);
+
 int sigsdp_solver_create_sharded(const sigsdp_plan* plan, int Z, int D_total, int col0, int D, double eta, int dtype,
                                  int tiling, sigsdp_solver** out) {
+    return solver_create_common(plan, Z, D_total, col0, D, eta, dtype, tiling, 0, 1, 0, out);
+}
+
+int sigsdp_solver_create_rows(const sigsdp_plan* plan, int Z, int D, double eta, int dtype, int tiling, int rank,
+                              int nranks, int max_blocks, sigsdp_solver** out) {
+    if (nranks < 1 || nranks > MAXR || rank < 0 || rank >= nranks)
+        return fail(SIGSDP_EINVAL, "row shard: need 0 <= rank < nranks <= 8");
+    return solver_create_common(plan, Z, D, 0, D, eta, dtype, tiling, rank, nranks, max_blocks, out);
+}
+
+static int solver_create_common(const sigsdp_plan* plan, int Z, int D_total, int col0, int D, double eta, int dtype,
+                                int tiling, int rank, int nranks, int max_blocks, sigsdp_solver** out) {
     if (!out) return fail(SIGSDP_EINVAL, "out is null");
     *out = nullptr;
     if (!plan) return fail(SIGSDP_EINVAL, "null plan");
@@ -1022,6 +1061,9 @@ int sigsdp_solver_create_sharded(const sigsdp_plan* plan, int Z, int D_total, in
     sigsdp_solver* s = new sigsdp_solver();
     s->Dtot = D_total;
     s->col0 = col0;
+    s->rank = rank;
+    s->nranks = nranks;
+    s->max_blocks = max_blocks;
     s->plan = plan;
     s->Z = Z;
     s->D = D;
@@ -1039,6 +1081,7 @@ int sigsdp_solver_create_sharded(const sigsdp_plan* plan, int Z, int D_total, in
     if (rc != SIGSDP_OK) {
         std::string keep = g_err;
         s->mem.release();
+        if (s->arena) cudaFree(s->arena);
         delete s;
         g_err = keep;
         return rc;
@@ -1058,7 +1101,102 @@ void sigsdp_solver_destroy(sigsdp_solver* s) {
         cudaEventDestroy(s->lz_ev_out);
     }
     s->mem.release();
+    for (void* p : s->ipc_mapped) cudaIpcCloseMemHandle(p);
+    if (s->arena) {
+        cudaDeviceSynchronize();
+        cudaFree(s->arena);
+    }
     delete s;
+}
+
+// ---- row shard: exchange arena, peers ------------------------------------------
+int sigsdp_solver_shard_info(const sigsdp_solver* s, int64_t info[12]) {
+    if (!s || !info) return fail(SIGSDP_EINVAL, "null argument");
+    info[0] = s->rank;
+    info[1] = s->nranks;
+    info[2] = s->row_lo;
+    info[3] = s->row_hi;
+    info[4] = s->tile_lo;
+    info[5] = s->tile_hi;
+    info[6] = s->halo_send_rows;
+    info[7] = s->halo_recv_rows;
+    info[8] = (int64_t)s->arena_bytes;
+    info[9] = s->n_inc;
+    info[10] = s->n_inc_owned;
+    info[11] = s->attached ? 1 : 0;
+    return SIGSDP_OK;
+}
+
+int sigsdp_solver_shard_arena(sigsdp_solver* s, void** dev_ptr, int64_t* bytes) {
+    if (!s || !dev_ptr || !bytes) return fail(SIGSDP_EINVAL, "null argument");
+    if (!s->arena) return fail(SIGSDP_ESTATE, "not a row shard");
+    *dev_ptr = s->arena;
+    *bytes = (int64_t)s->arena_bytes;
+    return SIGSDP_OK;
+}
+
+int sigsdp_solver_shard_ipc_handle(sigsdp_solver* s, void* handle64) {
+    if (!s || !handle64) return fail(SIGSDP_EINVAL, "null argument");
+    if (!s->arena) return fail(SIGSDP_ESTATE, "not a row shard");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CK(cudaSetDevice(s->plan->device));
+    cudaIpcMemHandle_t hnd;
+    CK(cudaIpcGetMemHandle(&hnd, s->arena));
+    std::memcpy(handle64, &hnd, 64);
+    return SIGSDP_OK;
+}
+
+static int shard_set_peers(sigsdp_solver* s, void* const* bases) {
+    ShardDev& sh = s->dtype == SIGSDP_F64 ? s->p64.sh : s->p32.sh;
+    for (int p = 0; p < MAXR; ++p) sh.delta[p] = 0;
+    for (int p = 0; p < s->nranks; ++p)
+        sh.delta[p] = (long long)(static_cast<const char*>(bases[p]) - static_cast<const char*>(s->arena));
+    s->attached = true;
+    return SIGSDP_OK;
+}
+
+int sigsdp_solver_shard_attach_local(sigsdp_solver* const* ranks, int count) {
+    if (!ranks || count < 1) return fail(SIGSDP_EINVAL, "bad argument");
+    void* bases[MAXR];
+    for (int r = 0; r < count; ++r) {
+        const sigsdp_solver* s = ranks[r];
+        if (!s || !s->arena || s->nranks != count || s->rank != r)
+            return fail(SIGSDP_EINVAL, "attach_local: ranks[r] must be row shard r of `count`");
+        if (s->arena_bytes != ranks[0]->arena_bytes) return fail(SIGSDP_EINVAL, "attach_local: arenas differ (different plans?)");
+        bases[r] = s->arena;
+    }
+    for (int r = 0; r < count; ++r) {
+        for (int q = 0; q < count; ++q) {
+            const int da = ranks[r]->plan->device, db = ranks[q]->plan->device;
+            if (da == db) continue;
+            CK(cudaSetDevice(da));
+            cudaError_t e = cudaDeviceEnablePeerAccess(db, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+            else if (e != cudaSuccess) return fail(SIGSDP_ECUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+        }
+        shard_set_peers(ranks[r], bases);
+    }
+    return SIGSDP_OK;
+}
+
+int sigsdp_solver_shard_attach_ipc(sigsdp_solver* s, const void* handles64) {
+    if (!s || !handles64) return fail(SIGSDP_EINVAL, "null argument");
+    if (!s->arena) return fail(SIGSDP_ESTATE, "not a row shard");
+    CK(cudaSetDevice(s->plan->device));
+    void* bases[MAXR];
+    for (int p = 0; p < s->nranks; ++p) {
+        if (p == s->rank) {
+            bases[p] = s->arena;
+            continue;
+        }
+        cudaIpcMemHandle_t hnd;
+        std::memcpy(&hnd, static_cast<const char*>(handles64) + (size_t)p * 64, 64);
+        void* q = nullptr;
+        CK(cudaIpcOpenMemHandle(&q, hnd, cudaIpcMemLazyEnablePeerAccess));
+        s->ipc_mapped.push_back(q);
+        bases[p] = q;
+    }
+    return shard_set_peers(s, bases);
 }
 
 int sigsdp_solver_reset(sigsdp_solver* s, void* stream) {
@@ -1100,9 +1238,9 @@ static int iterate_impl(sigsdp_solver* s, int n_iters, const double* omega_dev, 
     P.seed = seed;
     int rc = SIGSDP_OK;
     if (s->mode == SIGSDP_MODE_FUSED) {
-        FOR_G(s->G, rc = (launch_fused<T, G>(s, n_iters, st)));
+        rc = launch_fused(s, n_iters, st);
     } else {
-        FOR_G(s->G, rc = (run_stepwise<T, G>(s, n_iters, st)));
+        rc = run_stepwise<T>(s, n_iters, st);
     }
     if (rc == SIGSDP_OK) s->iters_done += n_iters;
     return rc;
@@ -1124,7 +1262,7 @@ static int split_step_impl(sigsdp_solver* s, int do_iter, const double* omega_de
     P.seed = seed;
     const int do_finish = s->pending_finish ? 1 : 0;
     int rc = SIGSDP_OK;
-    FOR_G(s->G, rc = (launch_fused<T, G>(s, do_iter ? 1 : 0, st, do_finish)));
+    rc = launch_fused(s, do_iter ? 1 : 0, st, do_finish);
     return rc;
 }
 }
@@ -1148,6 +1286,8 @@ int sigsdp_solver_iterate(sigsdp_solver* s, int n_iters, const double* omega_dev
     if (s->Dtot != s->D) return fail(SIGSDP_ESTATE, "column shard: drive it with sigsdp_solver_split_step");
     if (n_iters < 0) return fail(SIGSDP_EINVAL, "n_iters < 0");
     if (n_iters == 0) return SIGSDP_OK;
+    if (s->nranks > 1 && !s->attached) return fail(SIGSDP_ESTATE, "row shard: attach the peers' arenas first");
+    if (s->nranks > 1 && s->mode != SIGSDP_MODE_FUSED) return fail(SIGSDP_ESTATE, "row shards run the fused kernel only");
     CK(cudaSetDevice(s->plan->device));
     return s->dtype == SIGSDP_F64 ? iterate_impl<double>(s, n_iters, omega_dev, seed, (cudaStream_t)stream)
                                   : iterate_impl<float>(s, n_iters, omega_dev, seed, (cudaStream_t)stream);
@@ -1170,7 +1310,18 @@ static void unpermute_dual(const HostPlan& h, const std::vector<double>& in, dou
     for (int64_t e = 0; e < Ea; ++e) out[n + e] = in[n + e];
 }
 
-#define COMMON(s) (s->dtype == SIGSDP_F64 ? (void*)&s->p64 : (void*)&s->p32)
+// row shards return the entries they own and zeros elsewhere, so the ranks' fetches add up
+// to the whole vector (the host language sums them: all-reduce)
+static inline bool owns_row(const sigsdp_solver* s, int64_t k) { return s->nranks == 1 || (k >= s->row_lo && k < s->row_hi); }
+static void zero_foreign_dual(const sigsdp_solver* s, double* out) {
+    if (s->nranks == 1) return;
+    const HostPlan& h = s->plan->h;
+    const int64_t n = h.n, Ea = h.E_a;
+    for (int64_t k = 0; k < n; ++k)
+        if (!owns_row(s, k)) out[h.perm[k]] = out[n + Ea + h.perm[k]] = 0.0;
+    for (int64_t e = 0; e < Ea; ++e)
+        if (!owns_row(s, std::min(h.iperm[h.ai[e]], h.iperm[h.aj[e]]))) out[n + e] = 0.0;
+}
 
 int sigsdp_solver_get_dual(sigsdp_solver* s, double* Y, double* e_accu, double* Y_avgd) {
     if (!s) return fail(SIGSDP_EINVAL, "null solver");
@@ -1185,14 +1336,17 @@ int sigsdp_solver_get_dual(sigsdp_solver* s, double* Y, double* e_accu, double* 
     if (Y) {
         if ((rc = fetch(tmp, dY, s->C)) != SIGSDP_OK) return rc;
         unpermute_dual(h, tmp, Y);
+        zero_foreign_dual(s, Y);
     }
     if (e_accu) {
         if ((rc = fetch(tmp, dE, s->C)) != SIGSDP_OK) return rc;
         unpermute_dual(h, tmp, e_accu);
+        zero_foreign_dual(s, e_accu);
     }
     if (Y_avgd) {
         if ((rc = fetch(tmp, dB, s->C)) != SIGSDP_OK) return rc;
         unpermute_dual(h, tmp, Y_avgd);
+        zero_foreign_dual(s, Y_avgd);
     }
     return SIGSDP_OK;
 }
@@ -1209,13 +1363,14 @@ int sigsdp_solver_get_X(sigsdp_solver* s, int averaged, double* diag, double* ga
     for (int64_t k = 0; k < h.n; ++k)
         for (int32_t p = h.rowptr[k]; p < h.rowptr[k + 1]; ++p) {
             const int32_t e = h.eid[p];
+            const double x = owns_row(s, k) ? X[p] : 0.0;
             if (e < 0) {
-                if (diag) diag[h.perm[k]] = X[p];
+                if (diag) diag[h.perm[k]] = x;
             } else if (k < h.col[p]) {
                 if (e < h.E_g) {
-                    if (gain) gain[e] = X[p];
+                    if (gain) gain[e] = x;
                 } else if (asso) {
-                    asso[e - h.E_g] = X[p];
+                    asso[e - h.E_g] = x;
                 }
             }
         }
@@ -1234,16 +1389,33 @@ int sigsdp_solver_get_L(sigsdp_solver* s, double* diag, double* gain, double* as
     for (int64_t k = 0; k < h.n; ++k)
         for (int32_t p = h.rowptr[k]; p < h.rowptr[k + 1]; ++p) {
             const int32_t e = h.eid[p];
+            const double x = owns_row(s, k) ? L[p] : 0.0;
             if (e < 0) {
-                if (diag) diag[h.perm[k]] = L[p];
+                if (diag) diag[h.perm[k]] = x;
             } else if (k < h.col[p]) {
                 if (e < h.E_g) {
-                    if (gain) gain[e] = L[p];
+                    if (gain) gain[e] = x;
                 } else if (asso) {
-                    asso[e - h.E_g] = L[p];
+                    asso[e - h.E_g] = x;
                 }
             }
         }
+    return SIGSDP_OK;
+}
+
+int sigsdp_solver_set_X(sigsdp_solver* s, int averaged, const double* diag, const double* gain, const double* asso) {
+    if (!s || !diag || !gain || !asso) return fail(SIGSDP_EINVAL, "null argument");
+    CK(cudaSetDevice(s->plan->device));
+    CK(cudaDeviceSynchronize());
+    const HostPlan& h = s->plan->h;
+    double* dv = s->dtype == SIGSDP_F64 ? (averaged ? s->p64.Xbarv : s->p64.Xv) : (averaged ? s->p32.Xbarv : s->p32.Xv);
+    std::vector<double> X(h.nnz);
+    for (int64_t k = 0; k < h.n; ++k)
+        for (int32_t p = h.rowptr[k]; p < h.rowptr[k + 1]; ++p) {
+            const int32_t e = h.eid[p];
+            X[p] = e < 0 ? diag[h.perm[k]] : e < h.E_g ? gain[e] : asso[e - h.E_g];
+        }
+    CK(cudaMemcpy(dv, X.data(), h.nnz * sizeof(double), cudaMemcpyHostToDevice));
     return SIGSDP_OK;
 }
 
@@ -1261,12 +1433,13 @@ int sigsdp_solver_get_sketch(sigsdp_solver* s, double* Yh) {
         std::vector<double> F(tot);
         CK(cudaMemcpy(F.data(), s->F, tot * sizeof(double), cudaMemcpyDeviceToHost));
         for (int64_t k = 0; k < h.n; ++k)
-            for (int c = 0; c < s->D; ++c) Yh[(size_t)h.perm[k] * s->D + c] = scale * F[(size_t)k * s->Dp + c];
+            for (int c = 0; c < s->D; ++c) Yh[(size_t)h.perm[k] * s->D + c] = owns_row(s, k) ? scale * F[(size_t)k * s->Dp + c] : 0.0;
     } else {
         std::vector<float> F(tot);
         CK(cudaMemcpy(F.data(), s->F, tot * sizeof(float), cudaMemcpyDeviceToHost));
         for (int64_t k = 0; k < h.n; ++k)
-            for (int c = 0; c < s->D; ++c) Yh[(size_t)h.perm[k] * s->D + c] = scale * (double)F[(size_t)k * s->Dp + c];
+            for (int c = 0; c < s->D; ++c)
+                Yh[(size_t)h.perm[k] * s->D + c] = owns_row(s, k) ? scale * (double)F[(size_t)k * s->Dp + c] : 0.0;
     }
     return SIGSDP_OK;
 }
@@ -1319,15 +1492,6 @@ int sigsdp_solver_debug_cycles(sigsdp_solver* s, int64_t out8[8]) {
     Ctrl hc;
     CK(cudaMemcpy(&hc, s->dtype == SIGSDP_F64 ? s->p64.ctrl : s->p32.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost));
     for (int i = 0; i < 8; ++i) out8[i] = hc.dbg[i];
-    return SIGSDP_OK;
-}
-
-int sigsdp_solver_debug_term_profile(sigsdp_solver* s, double out6[6]) {
-    if (!s || !out6) return fail(SIGSDP_EINVAL, "null argument");
-    CK(cudaSetDevice(s->plan->device));
-    CK(cudaDeviceSynchronize());
-    const double* ht = s->dtype == SIGSDP_F64 ? s->p64.hist_t : s->p32.hist_t;
-    CK(cudaMemcpy(out6, ht + (size_t)HIST * 3, 6 * sizeof(double), cudaMemcpyDeviceToHost));
     return SIGSDP_OK;
 }
 
@@ -1610,18 +1774,6 @@ int sigsdp_round_conflicts(const sigsdp_plan* plan, const int32_t* z_dev, double
 
 
 // ---- batch -------------------------------------------------------------------
-extern "C++" {
-template <typename T, int G>
-static int launch_batch(sigsdp_batch* b, int n_iters, unsigned long long seed, cudaStream_t st) {
-    if (b->smem > 48 * 1024)
-        CK(cudaFuncSetAttribute(k_batch<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem));
-    k_batch<T, G><<<dim3((unsigned)b->solvers.size()), dim3(NT), b->smem, st>>>(
-        reinterpret_cast<const Prob<T>*>(b->d_probs), n_iters, seed);
-    CK(cudaGetLastError());
-    return SIGSDP_OK;
-}
-}
-
 int sigsdp_batch_create(sigsdp_solver* const* solvers, int count, sigsdp_batch** out) {
     return sigsdp_batch_create_ids(solvers, nullptr, count, out);
 }
@@ -1682,15 +1834,12 @@ int sigsdp_batch_iterate(sigsdp_batch* b, int n_iters, uint64_t seed, void* stre
     if (n_iters == 0) return SIGSDP_OK;
     CK(cudaSetDevice(b->device));
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = SIGSDP_OK;
-    if (b->dtype == SIGSDP_F64) {
-        FOR_G(b->G, rc = (launch_batch<double, G>(b, n_iters, seed, st)));
-    } else {
-        FOR_G(b->G, rc = (launch_batch<float, G>(b, n_iters, seed, st)));
-    }
-    if (rc == SIGSDP_OK)
-        for (sigsdp_solver* s : b->solvers) s->iters_done += n_iters;
-    return rc;
+    const KernelSet& ks = kset_of(b->dtype, b->G);
+    int occ = 0;
+    CK(ks.prepare(b->smem, 0, &occ));
+    CK(ks.batch(b->d_probs, (int)b->solvers.size(), b->smem, n_iters, seed, st));
+    for (sigsdp_solver* s : b->solvers) s->iters_done += n_iters;
+    return SIGSDP_OK;
 }
 
 int sigsdp_round_greedy(int64_t n, int Z, const int32_t* Sp, const int32_t* Si, const double* Sx, const int32_t* Qp,

@@ -59,6 +59,32 @@ struct TileDev {
     int slot_r;
 };
 
+// Row sharding of ONE graph across the GPUs of a box (BASELINE configs[3]): rank r owns the
+// consecutive rows [row_lo, row_hi) (whole tiles) of the locality-ordered pattern -- their
+// L_accu / X entries, dual weights and sketch rows.  Every rank keeps full-length arrays in the
+// plan's global numbering and only walks its own part; the rows of B / F (per Taylor term),
+// r and q (per iteration) that a neighbouring rank's rows read are pushed into that rank's
+// copy of the array by the kernel that produces them, with plain stores through peer-mapped
+// memory (NVLink), and become visible at the next team barrier.  nranks == 1: everything is
+// "own" and none of this is touched.
+constexpr int MAXR = 8;          // ranks of a row-sharded solver
+struct ShardDev {
+    int nranks, rank;
+    int row_lo, row_hi;          // own rows
+    int tile_lo, tile_hi;        // own tiles of the staged kernels
+    // association edges with an entry in an own row: the first n_inc_owned are owned (their
+    // row < col entry is in an own row: this rank accounts for them in the soft-max sums), the
+    // rest belong to a neighbour and are kept up to date redundantly (L needs their weight)
+    int n_inc, n_inc_owned;
+    const int* inc_e;            // asso edge id (nullptr: edge i, position apos[i])
+    const int* inc_pos;          // position of that edge's entry in an own row
+    const unsigned char* pmask;  // n: bit p set = rank p reads row k of B / F / r / q (nullptr: unsharded)
+    long long delta[MAXR];       // bytes from this rank's exchange arena to rank p's
+    unsigned long long* flags;   // [MAXR] barrier epochs the peers have reached (in this rank's arena)
+    unsigned long long* inbox;   // [2][MAXR][8] packed scalars of the peers, by barrier parity
+    unsigned long long timeout_ns;
+};
+
 // device-resident controller: reductions that must be order independent use
 // atomicMax on the bit pattern of non-negative doubles
 struct Ctrl {
@@ -75,9 +101,9 @@ struct Ctrl {
     int m_star, done, nterms;
     long long s;
     double c1, a1;
-    // block-0 cycle counters (clock64): [0] term staging wait, [1] term compute, [2] gram staging
-    // wait, [3] gram compute, [4] grid-barrier wait, [5] dual, [6] exp, [7] loss
+    // diagnostics: [4] nanoseconds the leader thread spent in team barriers (the others are unused)
     long long dbg[8];
+    unsigned long long xepoch;     // cross-GPU barriers completed so far (row-sharded solvers)
     // arrivals at the fused kernel's grid barrier, counted up for ever (GridTeam); on a line
     // of its own so the polling does not collide with the keys above
     alignas(128) unsigned long long bar;
@@ -124,52 +150,7 @@ struct Prob {
     // the ranks all-reduce that buffer and phase_gram_finish completes X, X_avgd and r.
     int Dtot, col0, split;
     double* graw;          // nnz (+ n: dsq)
-};
-
-// ---------------------------------------------------------------------------
-// teams
-// The fused kernel's grid barrier (cooperative launch: all blocks are resident).  One
-// arrival counter that only counts up: barrier number b is complete when it reaches
-// b * gridDim.x, so there is no reset and no second round trip; every block derives the
-// number it starts at from the counter itself (arrivals of the first barrier of a launch
-// cannot complete it before this block has arrived too, so rounding down is exact).
-// Thread 0 arrives with a release and polls with an acquire at GPU scope; the block
-// barriers on either side extend that to the whole block.  Measured against
-// cooperative_groups' grid.sync(): the same at 296 blocks (cfg4, where the wait is
-// imbalance), 2-7 % per iteration on the smaller configurations.
-struct GridTeam {
-    unsigned long long* ctr;
-    mutable unsigned long long next;
-    __device__ explicit GridTeam(unsigned long long* c) : ctr(c) {
-        unsigned long long v;
-        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(c) : "memory");
-        next = (v / gridDim.x + 1ull) * gridDim.x;
-    }
-    __device__ int rank() const { return blockIdx.x; }
-    __device__ int size() const { return gridDim.x; }
-    __device__ void sync() const {
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            __threadfence();
-            asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(ctr) : "memory");
-            unsigned long long v;
-            do {
-                asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(ctr) : "memory");
-            } while (v < next);
-        }
-        next += gridDim.x;
-        __syncthreads();
-    }
-};
-struct StepTeam {  // stepwise: the kernel boundary is the barrier
-    __device__ int rank() const { return blockIdx.x; }
-    __device__ int size() const { return gridDim.x; }
-    __device__ void sync() const {}
-};
-struct CtaTeam {  // batch: one block owns the instance
-    __device__ int rank() const { return 0; }
-    __device__ int size() const { return 1; }
-    __device__ void sync() const { __syncthreads(); }
+    ShardDev sh;           // row sharding (nranks == 1: none)
 };
 
 // ---------------------------------------------------------------------------
@@ -254,6 +235,249 @@ __device__ __forceinline__ double group_sum(cg::thread_block_tile<G>& tile, doub
     return v;
 }
 
+// ---------------------------------------------------------------------------
+// teams: the set of thread blocks that runs one solver, its barrier, and how a phase reads
+// the scalars the previous phase reduced (max e_accu, soft-max sums, ||A||_1, ||.||_inf of
+// the Taylor terms, trace).  The phases are written against this interface:
+//   sync(P, what, slot)   barrier; `what` names the scalars the finished phase produced
+//   emax / exp_sums / a1 / c1 / trace_sum / term_norms   those scalars, valid after the sync
+enum SyncWhat { SY_PLAIN = 0, SY_DUAL = 1, SY_EXP = 2, SY_LOSS = 3, SY_TERM = 4 };
+
+// spin-wait helper: tight polls first, then back off; a barrier that does not complete
+// within `limit_ns` (a block died, a peer never launched) traps instead of hanging the GPU
+struct SpinGuard {
+    unsigned n = 0;
+    unsigned long long t0 = 0;
+    __device__ __forceinline__ void step(unsigned long long limit_ns) {
+        if (++n < 2048u) return;
+        if (t0 == 0) t0 = globaltimer_ns();
+        __nanosleep(64);
+        if ((n & 1023u) == 0u && limit_ns && globaltimer_ns() - t0 > limit_ns) __trap();
+    }
+};
+#ifndef SIGSDP_LOCAL_BARRIER_TIMEOUT_NS
+#define SIGSDP_LOCAL_BARRIER_TIMEOUT_NS 20000000000ull   // 20 s: far beyond any phase; 0 disables
+#endif
+
+// shared by the single-GPU teams: the scalars live in this solver's Ctrl / partial arrays
+struct LocalScalars {
+    template <typename T> __device__ double emax(const Prob<T>& P) const { return dkey_any_inv(ld_u64(&P.ctrl->emax_key)); }
+    template <typename T> __device__ void exp_sums(const Prob<T>& P, int nblk, double* sh, double s[4]) const {
+        s[0] = team_sum(P.psum + 0, PSTRIDE, nblk, sh);
+        s[1] = team_sum(P.psum + 1, PSTRIDE, nblk, sh);
+        s[2] = team_sum(P.psum + 2, PSTRIDE, nblk, sh);
+        s[3] = team_sum(P.psum + 3, PSTRIDE, nblk, sh);
+    }
+    template <typename T> __device__ double a1(const Prob<T>& P) const { return dkey_pos_inv(ld_u64(&P.ctrl->a1_key)); }
+    template <typename T> __device__ double c1(const Prob<T>& P) const { return dkey_pos_inv(ld_u64(&P.ctrl->c1_key)); }
+    template <typename T> __device__ void term_norms(const Prob<T>& P, int slot, double& c2, double& fn) const {
+        c2 = dkey_pos_inv(ld_u64(&P.ctrl->nrm_b[slot]));
+        fn = dkey_pos_inv(ld_u64(&P.ctrl->nrm_f[slot]));
+    }
+};
+
+// The fused kernel's grid barrier (cooperative launch: all blocks are resident).  One
+// arrival counter that only counts up: barrier number b is complete when it reaches
+// b * gridDim.x, so there is no reset and no second round trip; every block derives the
+// number it starts at from the counter itself (arrivals of the first barrier of a launch
+// cannot complete it before this block has arrived too, so rounding down is exact).
+// Thread 0 arrives with a release and polls with an acquire at GPU scope; the block
+// barriers on either side extend that to the whole block.
+struct GridTeam : LocalScalars {
+    unsigned long long* ctr;
+    mutable unsigned long long next;
+    __device__ explicit GridTeam(unsigned long long* c) : ctr(c) {
+        unsigned long long v;
+        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(c) : "memory");
+        next = (v / gridDim.x + 1ull) * gridDim.x;
+    }
+    __device__ int rank() const { return blockIdx.x; }
+    __device__ int size() const { return gridDim.x; }
+    template <typename T> __device__ void sync(const Prob<T>&, int = SY_PLAIN, int = 0) const {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(ctr) : "memory");
+            unsigned long long v;
+            SpinGuard g;
+            for (;;) {
+                asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(ctr) : "memory");
+                if (v >= next) break;
+                g.step(SIGSDP_LOCAL_BARRIER_TIMEOUT_NS);
+            }
+        }
+        next += gridDim.x;
+        __syncthreads();
+    }
+    template <typename T> __device__ double trace_sum(const Prob<T>& P, double* sh) const { return team_sum(P.ptr, 1, size(), sh); }
+    template <typename T> __device__ void exp_sums(const Prob<T>& P, double* sh, double s[4]) const { LocalScalars::exp_sums(P, size(), sh, s); }
+    template <typename T> __device__ void finish(const Prob<T>&) const {}
+};
+struct StepTeam : LocalScalars {  // stepwise: the kernel boundary is the barrier
+    __device__ int rank() const { return blockIdx.x; }
+    __device__ int size() const { return gridDim.x; }
+    template <typename T> __device__ void sync(const Prob<T>&, int = SY_PLAIN, int = 0) const {}
+    template <typename T> __device__ double trace_sum(const Prob<T>& P, double* sh) const { return team_sum(P.ptr, 1, size(), sh); }
+    template <typename T> __device__ void exp_sums(const Prob<T>& P, double* sh, double s[4]) const { LocalScalars::exp_sums(P, size(), sh, s); }
+    template <typename T> __device__ void finish(const Prob<T>&) const {}
+};
+struct CtaTeam : LocalScalars {  // batch: one block owns the instance
+    __device__ int rank() const { return 0; }
+    __device__ int size() const { return 1; }
+    template <typename T> __device__ void sync(const Prob<T>&, int = SY_PLAIN, int = 0) const { __syncthreads(); }
+    template <typename T> __device__ double trace_sum(const Prob<T>& P, double* sh) const { return team_sum(P.ptr, 1, 1, sh); }
+    template <typename T> __device__ void exp_sums(const Prob<T>& P, double* sh, double s[4]) const { LocalScalars::exp_sums(P, 1, sh, s); }
+    template <typename T> __device__ void finish(const Prob<T>&) const {}
+};
+
+// Row-sharded solver: the blocks of this GPU plus, through peer-mapped memory, the blocks of
+// the other ranks.  A barrier is (1) every block of this GPU arrives on the local counter with
+// a system-scope release (its halo pushes into the peers' arrays are ordered before it);
+// (2) block 0 waits for the local count, reduces this rank's partial scalars in a fixed order,
+// stores them into slot [parity][rank] of EVERY rank's inbox and then releases its epoch number
+// into every rank's flag array; (3) every block of every rank polls its own flag array until
+// all ranks have reached the epoch, then reduces the inbox over the ranks in rank order -- so
+// every block on every GPU continues with bit-identical scalars (same Taylor degree, same
+// early exit, same trace), which is what keeps the ranks' control flow in step without a host.
+// The inbox is double-buffered by barrier parity: a rank can be at most one barrier ahead.
+struct ShardTeam {
+    unsigned long long* ctr;
+    mutable unsigned long long next;
+    mutable unsigned long long epoch;
+    double* xr;   // shared memory, 8 doubles: [0..3] keys (as doubles' bit patterns), [4..7] sums
+    template <typename T>
+    __device__ ShardTeam(const Prob<T>& P, double* xr_) : ctr(&P.ctrl->bar), xr(xr_) {
+        unsigned long long v;
+        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(ctr) : "memory");
+        next = (v / gridDim.x + 1ull) * gridDim.x;
+        epoch = *reinterpret_cast<const volatile unsigned long long*>(&P.ctrl->xepoch);
+    }
+    __device__ int rank() const { return blockIdx.x; }
+    __device__ int size() const { return gridDim.x; }
+    template <typename T>
+    __device__ void sync(const Prob<T>& P, int what = SY_PLAIN, int slot = 0) const {
+        const ShardDev& S = P.sh;
+        Ctrl* ctrl = P.ctrl;
+        const unsigned long long ep = epoch + 1ull;
+        const unsigned par = (unsigned)(ep & 1ull);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            asm volatile("red.release.sys.global.add.u64 [%0], 1;" ::"l"(ctr) : "memory");
+        }
+        if (blockIdx.x == 0 && threadIdx.x < 32) {
+            const int lane = threadIdx.x;
+            if (lane == 0) {
+                unsigned long long v;
+                SpinGuard g;
+                for (;;) {
+                    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(ctr) : "memory");
+                    if (v >= next) break;
+                    g.step(S.timeout_ns);
+                }
+            }
+            __syncwarp();
+            // this rank's payload: 4 keys (max-reduced across ranks) and 4 sums
+            unsigned long long pk[4] = {0ull, 0ull, 0ull, 0ull};
+            double ps[4] = {0.0, 0.0, 0.0, 0.0};
+            const int nblk = gridDim.x;
+            if (what == SY_DUAL) {
+                pk[0] = ld_u64(&ctrl->emax_key);
+            } else if (what == SY_EXP) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    double t = 0.0;
+                    for (int b = lane; b < nblk; b += 32) t += P.psum[(size_t)b * PSTRIDE + i];
+                    ps[i] = warp_sum(t);
+                }
+            } else if (what == SY_LOSS || what == SY_TERM) {
+                pk[0] = what == SY_LOSS ? ld_u64(&ctrl->a1_key) : ld_u64(&ctrl->nrm_b[slot]);
+                pk[1] = what == SY_LOSS ? ld_u64(&ctrl->c1_key) : ld_u64(&ctrl->nrm_f[slot]);
+                double t = 0.0;
+                for (int b = lane; b < nblk; b += 32) t += P.ptr[b];
+                ps[0] = warp_sum(t);
+            }
+            if (lane < S.nranks) {
+                char* peer = reinterpret_cast<char*>(S.inbox) + S.delta[lane];
+                unsigned long long* dst = reinterpret_cast<unsigned long long*>(peer) + ((size_t)par * MAXR + S.rank) * 8;
+                if (what != SY_PLAIN) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        dst[i] = pk[i];
+                        dst[4 + i] = (unsigned long long)__double_as_longlong(ps[i]);
+                    }
+                    __threadfence_system();
+                }
+                unsigned long long* fl = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(S.flags) + S.delta[lane]) + S.rank;
+                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(fl), "l"(ep) : "memory");
+            }
+        }
+        if (threadIdx.x < S.nranks) {   // one poller per peer
+            unsigned long long v;
+            SpinGuard g;
+            for (;;) {
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(S.flags + threadIdx.x) : "memory");
+                if (v >= ep) break;
+                g.step(S.timeout_ns);
+            }
+        }
+        __syncthreads();
+        if (what != SY_PLAIN && threadIdx.x < 8) {
+            const unsigned long long* in = S.inbox + (size_t)par * MAXR * 8 + threadIdx.x;
+            if (threadIdx.x < 4) {
+                unsigned long long m = 0ull;
+                for (int r = 0; r < S.nranks; ++r) {
+                    unsigned long long v;
+                    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(in + (size_t)r * 8) : "memory");
+                    m = v > m ? v : m;
+                }
+                xr[threadIdx.x] = __longlong_as_double((long long)m);
+            } else {
+                double a = 0.0;
+                for (int r = 0; r < S.nranks; ++r) {
+                    unsigned long long v;
+                    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(in + (size_t)r * 8) : "memory");
+                    a += __longlong_as_double((long long)v);
+                }
+                xr[threadIdx.x] = a;
+            }
+        }
+        __syncthreads();
+        next += gridDim.x;
+        epoch = ep;
+    }
+    __device__ unsigned long long key(int i) const { return (unsigned long long)__double_as_longlong(xr[i]); }
+    template <typename T> __device__ double emax(const Prob<T>&) const { return dkey_any_inv(key(0)); }
+    template <typename T> __device__ void exp_sums(const Prob<T>&, double*, double s[4]) const {
+        s[0] = xr[4]; s[1] = xr[5]; s[2] = xr[6]; s[3] = xr[7];
+    }
+    template <typename T> __device__ double a1(const Prob<T>&) const { return dkey_pos_inv(key(0)); }
+    template <typename T> __device__ double c1(const Prob<T>&) const { return dkey_pos_inv(key(1)); }
+    template <typename T> __device__ void term_norms(const Prob<T>&, int, double& c2, double& fn) const {
+        c2 = dkey_pos_inv(key(0));
+        fn = dkey_pos_inv(key(1));
+    }
+    template <typename T> __device__ double trace_sum(const Prob<T>&, double*) const { return xr[4]; }
+    template <typename T> __device__ void finish(const Prob<T>& P) const { P.ctrl->xepoch = epoch; }
+};
+
+// halo pushes: the same element of every peer's copy of an exchange-arena array
+template <typename V, typename T>
+__device__ __forceinline__ void push_vec(const ShardDev& S, T* local, const V& v, unsigned mask) {
+    while (mask) {
+        const int r = __ffs((int)mask) - 1;
+        mask &= mask - 1u;
+        v.store(reinterpret_cast<T*>(reinterpret_cast<char*>(local) + S.delta[r]));
+    }
+}
+__device__ __forceinline__ void push_f64(const ShardDev& S, double* local, double v, unsigned mask) {
+    while (mask) {
+        const int r = __ffs((int)mask) - 1;
+        mask &= mask - 1u;
+        *reinterpret_cast<double*>(reinterpret_cast<char*>(local) + S.delta[r]) = v;
+    }
+}
+
 // vector of VEC sketch columns held by one lane
 template <typename T> struct Vec;
 template <> struct Vec<double> {
@@ -291,19 +515,6 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
                      smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
@@ -353,18 +564,27 @@ __device__ __forceinline__ void bulk_g2s_a(unsigned dst, const void* src, unsign
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
+// try_wait suspends the thread for a hardware-defined time before it reports "not yet", so this
+// loop is not a hot spin; debug builds (-DSIGSDP_DEBUG_SPIN) trap when a copy never lands
 __device__ __forceinline__ void mbar_wait_a(unsigned bar, unsigned parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}" ::"r"(bar),
-        "r"(parity)
-        : "memory");
+    unsigned done;
+#ifdef SIGSDP_DEBUG_SPIN
+    unsigned tries = 0;
+#endif
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred P1;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, P1;\n"
+            "}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+#ifdef SIGSDP_DEBUG_SPIN
+        if (!done && ++tries > (1u << 24)) __trap();
+#endif
+    } while (!done);
 }
 
 // Stage one tile with TMA bulk copies: the distinct rows of `src` (n x Dp, global) its
@@ -373,13 +593,10 @@ __device__ __forceinline__ void mbar_wait_a(unsigned bar, unsigned parity) {
 // column indices, each from a 16-byte aligned superset.  Completion is counted in bytes
 // on the mbarrier; the compute that follows reads shared memory only.
 template <typename T>
-__device__ __forceinline__ void stage_tile(const Prob<T>& P, const T* src, const T* vals_src, int t, Stage<T>& st,
-                                           long long* wait_cycles = nullptr, long long* prof = nullptr) {
-    const long long tc0 = wait_cycles ? clock64() : 0;
+__device__ __forceinline__ void stage_tile(const Prob<T>& P, const T* src, const T* vals_src, int t, Stage<T>& st) {
     const TileDev& tl = P.tl;
     constexpr int VA = 16 / (int)sizeof(T);   // values per 16 bytes
     __syncthreads();  // every reader of the previous tile is done with the buffers
-    const long long tc1 = prof ? clock64() : 0;
     const int4 ra = tl.trec[2 * t], rb = tl.trec[2 * t + 1];   // one load level instead of rowptr[trow[t]] chains
     const int p0 = ra.z, p1 = ra.w;
     const unsigned rowbytes = (unsigned)(P.Dp * sizeof(T));
@@ -393,25 +610,15 @@ __device__ __forceinline__ void stage_tile(const Prob<T>& P, const T* src, const
         bulk_g2s_a(st.lcol_a, tl.lcol + pl, lbytes, st.bar_a);
         if (vals_src) bulk_g2s_a(st.vals_a, vals_src + pv, vbytes, st.bar_a);
     }
-    // the row copies are spread over the warps (a bulk copy is a per-warp instruction with
-    // uniform operands, so this spreads them over the SM's four schedulers)
     // run i goes to warp i % NWARP, lane i / NWARP: a bulk copy is a per-warp instruction with
     // uniform operands (a warp issues its lanes' copies one after the other), so the runs
-    // are dealt across the warps first
+    // are dealt across the warps (and with them the SM's four schedulers) first
     for (int i = rb.x + (threadIdx.x >> 5) + NWARP * (threadIdx.x & 31); i < rb.y; i += NT) {
         const int4 r = tl.runs[i];
         bulk_g2s_a(st.rows_a + (unsigned)r.y * rowbytes, src + (size_t)r.x * P.Dp, (unsigned)r.z * rowbytes, st.bar_a);
     }
-    const long long tc2 = prof ? clock64() : 0;
     mbar_wait_a(st.bar_a, st.parity);
     st.parity ^= 1u;
-    if (wait_cycles) *wait_cycles += clock64() - tc0;
-    if (prof) {
-        const long long tc3 = clock64();
-        prof[0] += tc1 - tc0;   // barrier: waiting for the block's slowest warp
-        prof[1] += tc2 - tc1;   // metadata loads + issuing the copies
-        prof[2] += tc3 - tc2;   // waiting for the copies to land
-    }
 }
 
 // ---------------------------------------------------------------------------
@@ -496,6 +703,7 @@ __device__ __forceinline__ void taylor_select(double a1, int& m_star, long long&
 template <typename T, int G, class Team>
 __device__ void phase_dual(const Prob<T>& P, const Team& team, double* sh) {
     const PlanDev& g = P.g;
+    const ShardDev& S = P.sh;
     const int K = g.n, Z = P.Z;
     cg::thread_block_tile<G> tile = cg::tiled_partition<G>(cg::this_thread_block());
     const int lane = tile.thread_rank();
@@ -513,10 +721,10 @@ __device__ void phase_dual(const Prob<T>& P, const Team& team, double* sh) {
             P.ctrl->c1_key = 0ull;
         }
     }
-    const int ntiles = (K + R - 1) / R;
+    const int ntiles = (S.row_hi - S.row_lo + R - 1) / R;
     for (int t = team.rank(); t < ntiles; t += team.size()) {
-        const int k = t * R + grp;
-        if (k < K) {
+        const int k = S.row_lo + t * R + grp;
+        if (k < S.row_hi) {
             // every load of the row is issued before the first use: the phase is bound by
             // memory latency, not bytes, so what counts is the number of loads in flight
             const int pa = g.rowptr[k], p1 = g.rowptr[k + 1];
@@ -551,12 +759,16 @@ __device__ void phase_dual(const Prob<T>& P, const Team& team, double* sh) {
             }
         }
     }
+    // association edges with an entry in an own row (all of them when unsharded); a row-sharded
+    // rank also advances the edges a neighbour owns from its own (bit-identical) copy of X_e
     const double zf = 1.0 / (Z - 1);
-    for (int e = team.rank() * NT + threadIdx.x; e < g.E_a; e += team.size() * NT) {
-        double eF = (P.Xv[g.apos[e]] + zf) / cF;
+    for (int i = team.rank() * NT + threadIdx.x; i < S.n_inc; i += team.size() * NT) {
+        const int e = S.inc_e ? S.inc_e[i] : i;
+        const int pos = S.inc_e ? S.inc_pos[i] : g.apos[i];
+        double eF = (P.Xv[pos] + zf) / cF;
         double a = P.e_acc[K + e] + P.eta * eF;
         P.e_acc[K + e] = a;
-        emax = fmax(emax, a);
+        if (i < S.n_inc_owned) emax = fmax(emax, a);
     }
     emax = block_max(emax, sh);
     if (threadIdx.x == 0 && emax > -INFINITY) atomicMax(&P.ctrl->emax_key, dkey_any(emax));
@@ -569,20 +781,32 @@ __device__ void phase_dual(const Prob<T>& P, const Team& team, double* sh) {
 template <typename T, int G, class Team>
 __device__ void phase_exp(const Prob<T>& P, const Team& team, double* sh) {
     const PlanDev& g = P.g;
-    const int K = g.n, C = P.C;
-    const double emax = dkey_any_inv(ld_u64(&P.ctrl->emax_key));
+    const ShardDev& S = P.sh;
+    const int K = g.n;
+    const double emax = team.emax(P);
     double sD = 0.0, sF = 0.0, sH = 0.0, sHq = 0.0;
-    for (int c = team.rank() * NT + threadIdx.x; c < C; c += team.size() * NT) {
-        double v = exp(P.e_acc[c] - emax);
-        P.u[c] = v;
-        if (c < K) {
+    // this rank's part of the constraint vector [D | F | H]: own rows, incident asso edges, own rows
+    const int nr = S.row_hi - S.row_lo;
+    const int tot = 2 * nr + S.n_inc;
+    for (int i = team.rank() * NT + threadIdx.x; i < tot; i += team.size() * NT) {
+        if (i < nr) {
+            const int c = S.row_lo + i;
+            const double v = exp(P.e_acc[c] - emax);
+            P.u[c] = v;
             sD += v;
-        } else if (c < K + g.E_a) {
-            sF += v;
+        } else if (i < nr + S.n_inc) {
+            const int j = i - nr;
+            const int c = K + (S.inc_e ? S.inc_e[j] : j);
+            const double v = exp(P.e_acc[c] - emax);
+            P.u[c] = v;
+            if (j < S.n_inc_owned) sF += v;
         } else {
-            int k = c - K - g.E_a;
-            double qq = v / P.nH[k];
+            const int k = S.row_lo + (i - nr - S.n_inc);
+            const double v = exp(P.e_acc[K + g.E_a + k] - emax);
+            P.u[K + g.E_a + k] = v;
+            const double qq = v / P.nH[k];
             P.q[k] = qq;
+            if (S.pmask) push_f64(S, P.q + k, qq, S.pmask[k]);
             sH += v;
             sHq += P.hcoef[k] * qq;
         }
@@ -615,23 +839,23 @@ __device__ void phase_loss(const Prob<T>& P, const Team& team, int it_local, dou
     using V = Vec<T>;
     constexpr int VEC = V::N;
     const PlanDev& g = P.g;
-    const int K = g.n, Z = P.Z, C = P.C, Dp = P.Dp, D = P.D;
+    const ShardDev& S = P.sh;
+    const int K = g.n, Z = P.Z, Dp = P.Dp, D = P.D;
     cg::thread_block_tile<G> tile = cg::tiled_partition<G>(cg::this_thread_block());
     const int lane = tile.thread_rank();
     const int grp = threadIdx.x / G;
     constexpr int R = NT / G;
     Ctrl* ctrl = P.ctrl;
 
-    const double sD = team_sum(P.psum + 0, PSTRIDE, team.size(), sh);
-    const double sF = team_sum(P.psum + 1, PSTRIDE, team.size(), sh);
-    const double sH = team_sum(P.psum + 2, PSTRIDE, team.size(), sh);
-    const double sHq = team_sum(P.psum + 3, PSTRIDE, team.size(), sh);
-    const double S = sD + sF + sH;
+    double es[4];
+    team.exp_sums(P, sh, es);
+    const double sD = es[0], sF = es[1], sH = es[2], sHq = es[3];
+    const double Ssum = sD + sF + sH;
     const double cF = 1.0 / ((double)K * (Z - 1)) + 0.5;
     const double invD = 1.0 / (1.0 - 1.0 / K);
-    const double sumYD = sD / S;
-    const double cLF = ((sF / S) / ((double)K * (Z - 1))) / cF;
-    const double cLH = sHq / S;
+    const double sumYD = sD / Ssum;
+    const double cLF = ((sF / Ssum) / ((double)K * (Z - 1))) / cF;
+    const double cLH = sHq / Ssum;
     const double gcoef = (double)(Z - 1) / (2.0 * Z);
     const double eta = P.eta;
     const long long iter = ctrl->iter + it_local;
@@ -644,20 +868,28 @@ __device__ void phase_loss(const Prob<T>& P, const Team& team, int it_local, dou
         ctrl->emax_key = 0ull;  // read by everyone before the previous barrier
     }
 
-    // ---- Y, Y_avgd
-    for (int c = team.rank() * NT + threadIdx.x; c < C; c += team.size() * NT) {
-        P.Ybar[c] += P.Y[c];
-        P.Y[c] = P.u[c] / S;
+    // ---- Y, Y_avgd (the entries this rank owns: own rows' D and H, owned asso edges' F)
+    {
+        const int nr = S.row_hi - S.row_lo;
+        const int tot = 2 * nr + S.n_inc_owned;
+        for (int i = team.rank() * NT + threadIdx.x; i < tot; i += team.size() * NT) {
+            int c;
+            if (i < nr) c = S.row_lo + i;
+            else if (i < nr + S.n_inc_owned) c = K + (S.inc_e ? S.inc_e[i - nr] : i - nr);
+            else c = K + g.E_a + S.row_lo + (i - nr - S.n_inc_owned);
+            P.Ybar[c] += P.Y[c];
+            P.Y[c] = P.u[c] / Ssum;
+        }
     }
 
     // ---- L_accu, the shifted half A = L_accu/2 - mu I in the sketch dtype, and ||A||_1
     double a1 = 0.0;
-    const double invS = 1.0 / S;
+    const double invS = 1.0 / Ssum;
     const double aF = invS * 0.5 / cF;
-    const int ntiles = (K + R - 1) / R;
+    const int ntiles = (S.row_hi - S.row_lo + R - 1) / R;
     for (int t = team.rank(); t < ntiles; t += team.size()) {
-        const int k = t * R + grp;
-        if (k < K) {
+        const int k = S.row_lo + t * R + grp;
+        if (k < S.row_hi) {
             const double wk = P.q[k] * invS;
             double rowabs = 0.0;
             const int p1 = g.rowptr[k + 1];
@@ -718,9 +950,10 @@ __device__ void phase_loss(const Prob<T>& P, const Team& team, int it_local, dou
     const int Dtot = P.Dtot, col0 = P.col0;
     const double sqrtD = sqrt((double)Dtot);
     for (int t = team.rank(); t < ntiles; t += team.size()) {
-        const int k = t * R + grp;
-        if (k < K) {
+        const int k = S.row_lo + t * R + grp;
+        if (k < S.row_hi) {
             const int ko = g.perm ? g.perm[k] : k;
+            const unsigned pm = S.pmask ? S.pmask[k] : 0u;
             double ss = 0.0;
             // the row norm runs over all Dtot columns of the sketch: a column shard generates
             // (or reads) the columns it does not own only for that
@@ -779,6 +1012,10 @@ __device__ void phase_loss(const Prob<T>& P, const Team& team, int it_local, dou
                 }
                 w.store(P.B0 + (size_t)k * Dp + c0);
                 w.store(P.F + (size_t)k * Dp + c0);
+                if (pm) {
+                    push_vec(S, P.B0 + (size_t)k * Dp + c0, w, pm);
+                    push_vec(S, P.F + (size_t)k * Dp + c0, w, pm);
+                }
             }
             rs = group_sum<G>(tile, rs);
             dd = group_sum<G>(tile, dd);
@@ -811,7 +1048,8 @@ __device__ void phase_term(const Prob<T>& P, const Team& team, const T* Bin, T* 
     using V = Vec<T>;
     constexpr int VEC = V::N;
     const PlanDev& g = P.g;
-    const int K = g.n, Dp = P.Dp;
+    const ShardDev& S = P.sh;
+    const int Dp = P.Dp;
     cg::thread_block_tile<G> tile = cg::tiled_partition<G>(cg::this_thread_block());
     const int lane = tile.thread_rank();
     const int grp = threadIdx.x / G;
@@ -823,11 +1061,12 @@ __device__ void phase_term(const Prob<T>& P, const Team& team, const T* Bin, T* 
     }
     const T cf = (T)coeff;
     double bmax = 0.0, fmaxv = 0.0, trp = 0.0;
-    const int ntiles = (K + R - 1) / R;
+    const int ntiles = (S.row_hi - S.row_lo + R - 1) / R;
     for (int t = team.rank(); t < ntiles; t += team.size()) {
-        const int k = t * R + grp;
-        if (k < K) {
+        const int k = S.row_lo + t * R + grp;
+        if (k < S.row_hi) {
             const int p0 = g.rowptr[k], p1 = g.rowptr[k + 1];
+            const unsigned pm = S.pmask ? S.pmask[k] : 0u;
             double rsb = 0.0, rsf = 0.0, dd = 0.0;
             for (int cb = 0; cb < Dp; cb += G * VEC) {
                 // every lane of the group runs every chunk so the shuffles below stay
@@ -871,6 +1110,10 @@ __device__ void phase_term(const Prob<T>& P, const Team& team, const T* Bin, T* 
                     }
                     bn.store(Bout + (size_t)k * Dp + c0);
                     f.store(P.F + (size_t)k * Dp + c0);
+                    if (pm) {
+                        push_vec(S, Bout + (size_t)k * Dp + c0, bn, pm);
+                        push_vec(S, P.F + (size_t)k * Dp + c0, f, pm);
+                    }
                 }
             }
             rsb = group_sum<G>(tile, rsb);
@@ -912,17 +1155,18 @@ __device__ void phase_gram(const Prob<T>& P, const Team& team, double* sh) {
     using V = Vec<T>;
     constexpr int VEC = V::N;
     const PlanDev& g = P.g;
+    const ShardDev& S = P.sh;
     const int K = g.n, Dp = P.Dp;
     cg::thread_block_tile<G> tile = cg::tiled_partition<G>(cg::this_thread_block());
     const int lane = tile.thread_rank();
     const int grp = threadIdx.x / G;
     constexpr int R = NT / G;
-    const double tr = P.split ? 1.0 : team_sum(P.ptr, 1, team.size(), sh) / K;
+    const double tr = P.split ? 1.0 : team.trace_sum(P, sh) / K;
     const bool one_chunk = Dp <= G * VEC;
-    const int ntiles = (K + R - 1) / R;
+    const int ntiles = (S.row_hi - S.row_lo + R - 1) / R;
     for (int t = team.rank(); t < ntiles; t += team.size()) {
-        const int k = t * R + grp;
-        if (k < K) {
+        const int k = S.row_lo + t * R + grp;
+        if (k < S.row_hi) {
             const int p0 = g.rowptr[k], p1 = g.rowptr[k + 1];
             V fk;
 #pragma unroll
@@ -974,7 +1218,10 @@ __device__ void phase_gram(const Prob<T>& P, const Team& team, double* sh) {
                 }
             }
             rsum = group_sum<G>(tile, rsum);
-            if (lane == 0 && !P.split) P.r[k] = rsum;
+            if (lane == 0 && !P.split) {
+                P.r[k] = rsum;
+                if (S.pmask) push_f64(S, P.r + k, rsum, S.pmask[k]);
+            }
         }
     }
 }
@@ -1008,18 +1255,17 @@ __device__ void phase_term_staged(const Prob<T>& P, const Team& team, const T* B
     }
     const T cf = (T)coeff;
     double bmax = 0.0, fmaxv = 0.0, trp = 0.0;
-    const bool timed = team.rank() == 0 && threadIdx.x == 0;
-    long long wait_c = 0;
-    const long long tph0 = timed ? clock64() : 0;
+    const ShardDev& S = P.sh;
     fence_proxy_async();   // order this phase's bulk copies after the barrier that published their source
-    for (int t = team.rank(); t < tl.ntiles; t += team.size()) {
+    for (int t = S.tile_lo + team.rank(); t < S.tile_hi; t += team.size()) {
         const int4 trc = tl.trec[2 * t];
         const int r0 = trc.x, r1 = trc.y;
-        stage_tile(P, Bin, (const T*)P.Aval, t, st, timed ? &wait_c : nullptr);
+        stage_tile(P, Bin, (const T*)P.Aval, t, st);
         for (int kb = r0; kb < r1; kb += R) {   // block-uniform trip count
             const int k = kb + grp;
             const bool valid = k < r1;
             const int p0 = valid ? g.rowptr[k] : 0, len = valid ? g.rowptr[k + 1] - p0 : 0;
+            const unsigned pm = (valid && S.pmask) ? S.pmask[k] : 0u;
             double rsb = 0.0, rsf = 0.0, dd = 0.0;
             for (int cb = 0; cb < Dp; cb += G * VEC) {
                 const int c0 = cb + lane * VEC;
@@ -1070,6 +1316,10 @@ __device__ void phase_term_staged(const Prob<T>& P, const Team& team, const T* B
                     }
                     bn.store(Bout + (size_t)k * Dp + c0);
                     f.store(P.F + (size_t)k * Dp + c0);
+                    if (pm) {
+                        push_vec(S, Bout + (size_t)k * Dp + c0, bn, pm);
+                        push_vec(S, P.F + (size_t)k * Dp + c0, f, pm);
+                    }
                 }
             }
             // all 32 lanes are converged here: xor-shuffles below G stay inside the group
@@ -1095,10 +1345,6 @@ __device__ void phase_term_staged(const Prob<T>& P, const Team& team, const T* B
         atomicMax(&ctrl->nrm_f[slot], dkey_pos(fmaxv));
         P.ptr[team.rank()] = trp;
     }
-    if (timed) {
-        ctrl->dbg[0] += wait_c;
-        ctrl->dbg[1] += clock64() - tph0 - wait_c;
-    }
 }
 
 
@@ -1119,6 +1365,7 @@ __device__ void phase_term_staged2(const Prob<T>& P, const Team& team, const T* 
     constexpr int R = NT / GH;
     const PlanDev& g = P.g;
     const TileDev& tl = P.tl;
+    const ShardDev& S = P.sh;
     const int Dp = P.Dp;
     const unsigned rowb = (unsigned)(Dp * W);
     const int lane = threadIdx.x & (GH - 1);
@@ -1130,19 +1377,14 @@ __device__ void phase_term_staged2(const Prob<T>& P, const Team& team, const T* 
     }
     const T cf = (T)coeff;
     double bmax = 0.0, fmaxv = 0.0, trp = 0.0;
-    const bool timed = team.rank() == 0 && threadIdx.x == 0;
-    long long wait_c = 0;
-    const long long tph0 = timed ? clock64() : 0;
     const int ca = lane * VEC, cb2 = (lane + GH) * VEC;
-    long long prof[6] = {0, 0, 0, 0, 0, 0};
     const bool use_slots = tl.slots != nullptr && tl.slot_r == R;
     fence_proxy_async();
-    for (int t = team.rank(); t < tl.ntiles; t += team.size()) {
+    for (int t = S.tile_lo + team.rank(); t < S.tile_hi; t += team.size()) {
         const int4 trc = tl.trec[2 * t];
         const int r0 = trc.x, r1 = trc.y;
-        stage_tile(P, Bin, (const T*)P.Aval, t, st, timed ? &wait_c : nullptr, timed ? prof : nullptr);
+        stage_tile(P, Bin, (const T*)P.Aval, t, st);
         for (int kb = r0; kb < r1; kb += R) {   // block-uniform trip count (one trip with a slot table)
-            const long long tq0 = timed ? clock64() : 0;
             int k, p0, len, role = 0;
             bool valid;
             if (use_slots) {
@@ -1159,16 +1401,16 @@ __device__ void phase_term_staged2(const Prob<T>& P, const Team& team, const T* 
                 len = valid ? g.rowptr[k + 1] - p0 : 0;
             }
             const bool owner = valid && role != 2;
-            if (timed) prof[3] += clock64() - tq0 + (long long)(len & 0);   // row pointer loads
-            const long long tq1 = timed ? clock64() : 0;
             double rsb = 0.0, rsf = 0.0, dd = 0.0;
             V fa, fb;
             T acca[VEC], accb[VEC];
 #pragma unroll
             for (int v = 0; v < VEC; ++v) acca[v] = accb[v] = fa.v[v] = fb.v[v] = (T)0;
+            unsigned pm = 0u;
             if (owner) {
                 fa.load(P.F + (size_t)k * Dp + ca);   // consumed in the epilogue
                 fb.load(P.F + (size_t)k * Dp + cb2);
+                if (S.pmask) pm = S.pmask[k];
             }
             if (valid) {
                 const unsigned la = st.la + 2u * (unsigned)p0, va = st.va + (unsigned)(W * p0);
@@ -1208,7 +1450,6 @@ __device__ void phase_term_staged2(const Prob<T>& P, const Team& team, const T* 
                         accb[v] = fma(a, bb.v[v], accb[v]);
                     }
                 }
-                if (timed) prof[4] += clock64() - tq1 + (long long)(acca[0] == (T)12345.678 ? 1 : 0);   // multiply loop
             }
             // second halves hand their partial sums to the group on their left (same warp: pairs
             // start at even slots); a warp without split rows skips the shuffles
@@ -1239,6 +1480,12 @@ __device__ void phase_term_staged2(const Prob<T>& P, const Team& team, const T* 
                 bnb.store(Bout + (size_t)k * Dp + cb2);
                 fa.store(P.F + (size_t)k * Dp + ca);
                 fb.store(P.F + (size_t)k * Dp + cb2);
+                if (pm) {   // rows a neighbouring rank reads: the same stores into its copies (NVLink)
+                    push_vec(S, Bout + (size_t)k * Dp + ca, bna, pm);
+                    push_vec(S, Bout + (size_t)k * Dp + cb2, bnb, pm);
+                    push_vec(S, P.F + (size_t)k * Dp + ca, fa, pm);
+                    push_vec(S, P.F + (size_t)k * Dp + cb2, fb, pm);
+                }
             }
             // all 32 lanes are converged here: xor-shuffles below GH stay inside the group
 #pragma unroll
@@ -1263,14 +1510,6 @@ __device__ void phase_term_staged2(const Prob<T>& P, const Team& team, const T* 
         atomicMax(&ctrl->nrm_f[slot], dkey_pos(fmaxv));
         P.ptr[team.rank()] = trp;
     }
-    if (timed) {
-        ctrl->dbg[0] += wait_c;
-        ctrl->dbg[1] += clock64() - tph0 - wait_c;
-        if (P.hist_t) {   // diagnostics: cumulative cycle split of block 0 / thread 0 in the last HIST slot
-            double* d = P.hist_t + (size_t)HIST * 3;   // 8 diagnostic slots behind the ring
-            for (int i = 0; i < 6; ++i) d[i] += (double)prof[i];
-        }
-    }
 }
 
 // Staged Gram: the tile's rows of F (its own rows included: the diagonal is in the
@@ -1286,6 +1525,7 @@ __device__ void phase_gram_staged(const Prob<T>& P, const Team& team, double* sh
     constexpr int W = (int)sizeof(T);
     const PlanDev& g = P.g;
     const TileDev& tl = P.tl;
+    const ShardDev& S = P.sh;
     const int K = g.n, Dp = P.Dp;
     const unsigned rowb = (unsigned)(Dp * W);
     const int nc = Dp / VEC;
@@ -1293,13 +1533,10 @@ __device__ void phase_gram_staged(const Prob<T>& P, const Team& team, double* sh
     const unsigned rmask = rowb - 1u;
     const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
     const bool raw = P.split != 0;
-    const double tr = raw ? 1.0 : team_sum(P.ptr, 1, team.size(), sh) / K;
+    const double tr = raw ? 1.0 : team.trace_sum(P, sh) / K;
     const double inv_tr = 1.0 / tr;
-    const bool timed = team.rank() == 0 && threadIdx.x == 0;
-    long long wait_c = 0;
-    const long long tph0 = timed ? clock64() : 0;
     fence_proxy_async();
-    for (int t = team.rank(); t < tl.ntiles; t += team.size()) {
+    for (int t = S.tile_lo + team.rank(); t < S.tile_hi; t += team.size()) {
         const int4 trc = tl.trec[2 * t];
         const int r0 = trc.x, r1 = trc.y;
         // Row pointers / diagonal positions of this warp's rows (lane i: its i-th row of the
@@ -1314,7 +1551,7 @@ __device__ void phase_gram_staged(const Prob<T>& P, const Team& team, double* sh
                 mpd = g.dpos[kk];
             }
         }
-        stage_tile(P, (const T*)P.F, (const T*)nullptr, t, st, timed ? &wait_c : nullptr);
+        stage_tile(P, (const T*)P.F, (const T*)nullptr, t, st);
         int pass = 0;
         for (int kb = r0; kb < r1; kb += NWARP, ++pass) {   // block-uniform trip count
             const int k = kb + wrp;
@@ -1392,12 +1629,11 @@ __device__ void phase_gram_staged(const Prob<T>& P, const Team& team, double* sh
                 }
             }
             rsum = warp_sum(rsum);
-            if (k < r1 && lane == 0 && !raw) P.r[k] = rsum;
+            if (k < r1 && lane == 0 && !raw) {
+                P.r[k] = rsum;
+                if (S.pmask) push_f64(S, P.r + k, rsum, S.pmask[k]);
+            }
         }
-    }
-    if (timed) {
-        P.ctrl->dbg[2] += wait_c;
-        P.ctrl->dbg[3] += clock64() - tph0 - wait_c;
     }
 }
 
@@ -1420,23 +1656,21 @@ __device__ void phase_gram_staged2(const Prob<T>& P, const Team& team, double* s
     constexpr int R = NT / GH;
     const PlanDev& g = P.g;
     const TileDev& tl = P.tl;
+    const ShardDev& S = P.sh;
     const int K = g.n, Dp = P.Dp;
     const unsigned rowb = (unsigned)(Dp * W);
     const int lane = threadIdx.x & (GH - 1);
     const int grp = threadIdx.x / GH;
     const bool raw = P.split != 0;
-    const double tr = raw ? 1.0 : team_sum(P.ptr, 1, team.size(), sh) / K;
+    const double tr = raw ? 1.0 : team.trace_sum(P, sh) / K;
     const double inv_tr = 1.0 / tr;
-    const bool timed = team.rank() == 0 && threadIdx.x == 0;
-    long long wait_c = 0;
-    const long long tph0 = timed ? clock64() : 0;
     const unsigned ca = (unsigned)(lane * VEC * W), cb2 = (unsigned)((lane + GH) * VEC * W);
     const bool use_slots = tl.slots != nullptr && tl.slot_r == R;
     fence_proxy_async();
-    for (int t = team.rank(); t < tl.ntiles; t += team.size()) {
+    for (int t = S.tile_lo + team.rank(); t < S.tile_hi; t += team.size()) {
         const int4 trc = tl.trec[2 * t];
         const int r0 = trc.x, r1 = trc.y;
-        stage_tile(P, (const T*)P.F, (const T*)nullptr, t, st, timed ? &wait_c : nullptr);
+        stage_tile(P, (const T*)P.F, (const T*)nullptr, t, st);
         for (int kb = r0; kb < r1; kb += R) {   // block-uniform trip count (one trip with a slot table)
             // the term kernel's slot table balances this kernel too: the two halves of a split
             // row finish their own entries independently, only the row sum is combined
@@ -1533,12 +1767,11 @@ __device__ void phase_gram_staged2(const Prob<T>& P, const Team& team, double* s
                 const double right = __shfl_down_sync(0xffffffffu, rsum, GH);
                 if (role == 1) rsum += right;
             }
-            if (valid && role != 2 && lane == 0 && !raw) P.r[k] = rsum;
+            if (valid && role != 2 && lane == 0 && !raw) {
+                P.r[k] = rsum;
+                if (S.pmask) push_f64(S, P.r + k, rsum, S.pmask[k]);
+            }
         }
-    }
-    if (timed) {
-        P.ctrl->dbg[2] += wait_c;
-        P.ctrl->dbg[3] += clock64() - tph0 - wait_c;
     }
 }
 
@@ -1554,7 +1787,7 @@ __device__ void phase_gram_finish(const Prob<T>& P, const Team& team, double* sh
     for (int k = team.rank() * NT + threadIdx.x; k < K; k += team.size() * NT) trp += P.dsq[k];
     trp = block_sum(trp, sh);
     if (threadIdx.x == 0) P.ptr[team.rank()] = trp;
-    team.sync();
+    team.sync(P);
     const double tr = team_sum(P.ptr, 1, team.size(), sh) / K;
     const int lane = threadIdx.x & (G - 1), grp = threadIdx.x / G;
     constexpr int R = NT / G;
@@ -1585,10 +1818,11 @@ struct TaylorState {
     double c1, a1, mu;
 };
 
-__device__ __forceinline__ void taylor_begin(const Ctrl* ctrl, TaylorState& ts) {
-    ts.a1 = dkey_pos_inv(ld_u64(&ctrl->a1_key));
-    ts.c1 = dkey_pos_inv(ld_u64(&ctrl->c1_key));
-    ts.mu = *reinterpret_cast<const volatile double*>(&ctrl->mu);
+template <class Team, typename T>
+__device__ __forceinline__ void taylor_begin(const Prob<T>& P, const Team& team, TaylorState& ts) {
+    ts.a1 = team.a1(P);
+    ts.c1 = team.c1(P);
+    ts.mu = *reinterpret_cast<const volatile double*>(&P.ctrl->mu);
     taylor_select(ts.a1, ts.m_star, ts.s);
 }
 
@@ -1602,7 +1836,6 @@ __device__ __forceinline__ void record_history(const Prob<T>& P, long long iter,
     P.hist_mu[h] = ts.mu;
 }
 
-// The whole MMW loop for one team: n_iters iterations, no host involvement.
 template <typename T>
 __device__ __forceinline__ void stage_setup(const Prob<T>& P, unsigned char* dyn, Stage<T>& st) {
     const TileDev& tl = P.tl;
@@ -1622,50 +1855,43 @@ __device__ __forceinline__ void stage_setup(const Prob<T>& P, unsigned char* dyn
     }
 }
 
+// The whole MMW loop for one team: n_iters iterations, no host involvement.  The leader
+// thread timestamps the phases (globaltimer) for the reference's per-phase logs and adds up
+// what it spends in team barriers (dbg[4], ns): for a row-sharded solver that is the
+// exchange + cross-GPU wait of this rank.
 template <typename T, int G, class Team>
-__device__ void run_iterations(const Prob<T>& P, const Team& team, int n_iters, unsigned char* dyn, int do_finish = 0) {
-    __shared__ double sh[NWARP + 2];
+__device__ void run_iterations(const Prob<T>& P, const Team& team, int n_iters, unsigned char* dyn, double* sh,
+                               int do_finish = 0) {
     Stage<T> st;
     stage_setup(P, dyn, st);
     const bool staged = P.tl.enabled != 0;
     Ctrl* ctrl = P.ctrl;
     long long terms = 0;
     const bool leader = team.rank() == 0 && threadIdx.x == 0;
-    long long sync_c = 0, c_dual = 0, c_exp = 0, c_loss = 0;
-#define TIMED_SYNC()                                   \
-    do {                                               \
-        const long long ts0_ = leader ? clock64() : 0; \
-        team.sync();                                   \
-        if (leader) sync_c += clock64() - ts0_;        \
+    unsigned long long sync_ns = 0;
+#define TIMED_SYNC(WHAT, SLOT)                                    \
+    do {                                                          \
+        const unsigned long long ts0_ = leader ? globaltimer_ns() : 0ull; \
+        team.sync(P, WHAT, SLOT);                                 \
+        if (leader) sync_ns += globaltimer_ns() - ts0_;           \
     } while (0)
     if (do_finish) {   // split mode: complete the previous iteration's Gram from the all-reduced buffer
         phase_gram_finish<T, G>(P, team, sh);
-        TIMED_SYNC();
+        TIMED_SYNC(SY_PLAIN, 0);
     }
     for (int it = 0; it < n_iters; ++it) {
         unsigned long long t0 = 0, t1 = 0, t2 = 0;
-        long long cc = 0;
-        if (leader) {
-            t0 = globaltimer_ns();
-            cc = clock64();
-        }
+        if (leader) t0 = globaltimer_ns();
         phase_dual<T, G>(P, team, sh);
-        if (leader) c_dual += clock64() - cc;
-        TIMED_SYNC();
-        if (leader) cc = clock64();
+        TIMED_SYNC(SY_DUAL, 0);
         phase_exp<T, G>(P, team, sh);
-        if (leader) c_exp += clock64() - cc;
-        TIMED_SYNC();
-        if (leader) {
-            t1 = globaltimer_ns();
-            cc = clock64();
-        }
+        TIMED_SYNC(SY_EXP, 0);
+        if (leader) t1 = globaltimer_ns();
         phase_loss<T, G>(P, team, it, sh);
-        if (leader) c_loss += clock64() - cc;
-        TIMED_SYNC();
+        TIMED_SYNC(SY_LOSS, 0);
         if (leader) t2 = globaltimer_ns();
         TaylorState ts;
-        taylor_begin(ctrl, ts);
+        taylor_begin(P, team, ts);
         T* bin = P.B0;
         T* bout = P.B1;
         int tcount = 0;
@@ -1674,7 +1900,7 @@ __device__ void run_iterations(const Prob<T>& P, const Team& team, int n_iters, 
             if (si > 0) {
                 phase_copy<T, G>(P, team, bin);
                 c1 = fn_last;
-                TIMED_SYNC();
+                TIMED_SYNC(SY_PLAIN, 0);
             }
             for (int j = 0; j < ts.m_star; ++j) {
                 const int slot = tcount % 3;
@@ -1685,9 +1911,9 @@ __device__ void run_iterations(const Prob<T>& P, const Team& team, int n_iters, 
                     phase_term_staged<T, G>(P, team, bin, bout, coeff, slot, sh, st);
                 else
                     phase_term<T, G>(P, team, bin, bout, coeff, ts.mu, slot, sh);
-                TIMED_SYNC();
-                const double c2 = dkey_pos_inv(ld_u64(&ctrl->nrm_b[slot]));
-                fn_last = dkey_pos_inv(ld_u64(&ctrl->nrm_f[slot]));
+                TIMED_SYNC(SY_TERM, slot);
+                double c2;
+                team.term_norms(P, slot, c2, fn_last);
                 T* tmp = bin;
                 bin = bout;
                 bout = tmp;
@@ -1704,7 +1930,7 @@ __device__ void run_iterations(const Prob<T>& P, const Team& team, int n_iters, 
                 phase_gram_staged<T, G>(P, team, sh, st);
         else
             phase_gram<T, G>(P, team, sh);
-        TIMED_SYNC();
+        TIMED_SYNC(SY_PLAIN, 0);
         if (leader) {
             const long long iter = ctrl->iter + it;
             record_history(P, iter, ts, tcount);
@@ -1716,13 +1942,11 @@ __device__ void run_iterations(const Prob<T>& P, const Team& team, int n_iters, 
         }
     }
 #undef TIMED_SYNC
-    if (team.rank() == 0 && threadIdx.x == 0) {
+    if (leader) {
         ctrl->iter += n_iters;
         ctrl->total_terms += terms;
-        ctrl->dbg[4] += sync_c;
-        ctrl->dbg[5] += c_dual;
-        ctrl->dbg[6] += c_exp;
-        ctrl->dbg[7] += c_loss;
+        ctrl->dbg[4] += (long long)sync_ns;
+        team.finish(P);
     }
 }
 

@@ -1,0 +1,177 @@
+// The __global__ kernels of one (sketch dtype, lanes-per-row) instantiation and the table of
+// host launchers the C ABI (mmw_api.cu) calls them through.  Every instantiation is its own
+// translation unit (mmw_inst.cu compiled with -DSIGSDP_T / -DSIGSDP_G / -DSIGSDP_NAME), so the
+// eight of them build in parallel.
+#pragma once
+#include "mmw_device.cuh"
+
+namespace sigsdp {
+
+struct KernelSet {
+    // raises the dynamic shared-memory limit of the staged kernels and reports how many blocks
+    // of the fused kernel (row-sharded variant if `shard`) fit on one SM
+    cudaError_t (*prepare)(size_t smem, int shard, int* blocks_per_sm);
+    // n_iters MMW iterations in ONE persistent launch (cooperative: all blocks co-resident)
+    cudaError_t (*fused)(const void* prob, int grid, size_t smem, int n_iters, int do_finish, int shard,
+                         cudaStream_t st);
+    // one kernel per phase (stepwise mode: profiling / debugging)
+    void (*dual)(const void* prob, int grid, cudaStream_t st);
+    void (*exp)(const void* prob, int grid, cudaStream_t st);
+    void (*loss)(const void* prob, int grid, int it_local, cudaStream_t st);
+    void (*term)(const void* prob, int grid, size_t smem, const void* bin, void* bout, double coeff, double mu, int slot,
+                 cudaStream_t st);
+    void (*copy)(const void* prob, int grid, void* dst, cudaStream_t st);
+    void (*gram)(const void* prob, int grid, size_t smem, cudaStream_t st);
+    void (*record)(const void* prob, int it_local, int m_star, long long s, double a1, double mu, int nterms,
+                   cudaStream_t st);
+    // one thread block per independent instance
+    cudaError_t (*batch)(const void* probs_dev, int count, size_t smem, int n_iters, unsigned long long seed,
+                         cudaStream_t st);
+};
+
+#ifdef SIGSDP_T
+template <typename T, int G>
+__global__ void __launch_bounds__(NT, 2) k_fused(Prob<T> P, int n_iters, int do_finish) {
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    __shared__ double sh[NWARP + 2];
+    GridTeam team(&P.ctrl->bar);
+    run_iterations<T, G>(P, team, n_iters, dyn_smem, sh, do_finish);
+}
+// row-sharded variant: the team spans the GPUs of the box (ShardTeam)
+template <typename T, int G>
+__global__ void __launch_bounds__(NT, 2) k_fused_rows(Prob<T> P, int n_iters) {
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    __shared__ double sh[NWARP + 2];
+    __shared__ double xr[8];
+    ShardTeam team(P, xr);
+    run_iterations<T, G>(P, team, n_iters, dyn_smem, sh, 0);
+}
+template <typename T, int G>
+__global__ void __launch_bounds__(NT, 2) k_dual(Prob<T> P) {
+    __shared__ double sh[NWARP + 2];
+    phase_dual<T, G>(P, StepTeam(), sh);
+}
+template <typename T, int G>
+__global__ void __launch_bounds__(NT, 2) k_exp(Prob<T> P) {
+    __shared__ double sh[NWARP + 2];
+    phase_exp<T, G>(P, StepTeam(), sh);
+}
+template <typename T, int G>
+__global__ void __launch_bounds__(NT, 2) k_loss(Prob<T> P, int it_local) {
+    __shared__ double sh[NWARP + 2];
+    phase_loss<T, G>(P, StepTeam(), it_local, sh);
+}
+template <typename T, int G>
+__global__ void __launch_bounds__(NT, 2) k_term(Prob<T> P, const T* bin, T* bout, double coeff, double mu, int slot) {
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    __shared__ double sh[NWARP + 2];
+    if (P.tl.enabled) {
+        Stage<T> st;
+        stage_setup(P, dyn_smem, st);
+        if (G >= 8 && P.Dp == G * Vec<T>::N)
+            phase_term_staged2<T, G>(P, StepTeam(), bin, bout, coeff, slot, sh, st);
+        else
+            phase_term_staged<T, G>(P, StepTeam(), bin, bout, coeff, slot, sh, st);
+    } else {
+        phase_term<T, G>(P, StepTeam(), bin, bout, coeff, mu, slot, sh);
+    }
+}
+template <typename T, int G>
+__global__ void __launch_bounds__(NT, 2) k_copy(Prob<T> P, T* dst) {
+    phase_copy<T, G>(P, StepTeam(), dst);
+}
+template <typename T, int G>
+__global__ void __launch_bounds__(NT, 2) k_gram(Prob<T> P) {
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    __shared__ double sh[NWARP + 2];
+    if (P.tl.enabled) {
+        Stage<T> st;
+        stage_setup(P, dyn_smem, st);
+        if (G >= 8 && P.Dp == G * Vec<T>::N)
+            phase_gram_staged2<T, G>(P, StepTeam(), sh, st);
+        else
+            phase_gram_staged<T, G>(P, StepTeam(), sh, st);
+    } else {
+        phase_gram<T, G>(P, StepTeam(), sh);
+    }
+}
+// batch: one thread block per independent instance, __syncthreads as the team barrier
+template <typename T, int G>
+__global__ void __launch_bounds__(NT, 2) k_batch(const Prob<T>* probs, int n_iters, unsigned long long seed) {
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    __shared__ double sh[NWARP + 2];
+    __shared__ Prob<T> Ps;
+    {
+        const int* src = reinterpret_cast<const int*>(probs + blockIdx.x);
+        int* dst = reinterpret_cast<int*>(&Ps);
+        for (int i = threadIdx.x; i < (int)(sizeof(Prob<T>) / sizeof(int)); i += NT) dst[i] = src[i];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            Ps.omega = nullptr;   // (the uploaded descriptor carries the instance id in its seed field)
+            Ps.seed = seed + 0x9E3779B97F4A7C15ull * (Ps.seed + 1ull);
+        }
+        __syncthreads();
+    }
+    CtaTeam team;
+    run_iterations<T, G>(Ps, team, n_iters, dyn_smem, sh);
+}
+template <typename T>
+__global__ void k_record(Prob<T> P, int it_local, int m_star, long long s, double a1, double mu, int nterms) {
+    TaylorState ts;
+    ts.m_star = m_star;
+    ts.s = s;
+    ts.a1 = a1;
+    ts.mu = mu;
+    ts.c1 = 0.0;
+    record_history(P, P.ctrl->iter + it_local, ts, nterms);
+    P.ctrl->total_terms += nterms;
+}
+
+template <typename T, int G>
+struct Launchers {
+    static const Prob<T>& prob(const void* p) { return *static_cast<const Prob<T>*>(p); }
+    static cudaError_t prepare(size_t smem, int shard, int* occ) {
+        cudaError_t e = cudaSuccess;
+        if (smem > 48 * 1024) {
+            if ((e = cudaFuncSetAttribute(k_fused<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
+            if ((e = cudaFuncSetAttribute(k_fused_rows<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
+            if ((e = cudaFuncSetAttribute(k_term<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
+            if ((e = cudaFuncSetAttribute(k_gram<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
+            if ((e = cudaFuncSetAttribute(k_batch<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
+        }
+        if (shard) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_fused_rows<T, G>, NT, smem);
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_fused<T, G>, NT, smem);
+    }
+    static cudaError_t fused(const void* p, int grid, size_t smem, int n_iters, int do_finish, int shard, cudaStream_t st) {
+        Prob<T> P = prob(p);
+        if (shard) {
+            void* args[] = {(void*)&P, (void*)&n_iters};
+            return cudaLaunchCooperativeKernel((void*)k_fused_rows<T, G>, dim3(grid), dim3(NT), args, smem, st);
+        }
+        void* args[] = {(void*)&P, (void*)&n_iters, (void*)&do_finish};
+        return cudaLaunchCooperativeKernel((void*)k_fused<T, G>, dim3(grid), dim3(NT), args, smem, st);
+    }
+    static void dual(const void* p, int grid, cudaStream_t st) { k_dual<T, G><<<grid, NT, 0, st>>>(prob(p)); }
+    static void exp_(const void* p, int grid, cudaStream_t st) { k_exp<T, G><<<grid, NT, 0, st>>>(prob(p)); }
+    static void loss(const void* p, int grid, int it_local, cudaStream_t st) { k_loss<T, G><<<grid, NT, 0, st>>>(prob(p), it_local); }
+    static void term(const void* p, int grid, size_t smem, const void* bin, void* bout, double coeff, double mu, int slot,
+                     cudaStream_t st) {
+        k_term<T, G><<<grid, NT, smem, st>>>(prob(p), static_cast<const T*>(bin), static_cast<T*>(bout), coeff, mu, slot);
+    }
+    static void copy(const void* p, int grid, void* dst, cudaStream_t st) { k_copy<T, G><<<grid, NT, 0, st>>>(prob(p), static_cast<T*>(dst)); }
+    static void gram(const void* p, int grid, size_t smem, cudaStream_t st) { k_gram<T, G><<<grid, NT, smem, st>>>(prob(p)); }
+    static void record(const void* p, int it_local, int m_star, long long s, double a1, double mu, int nterms, cudaStream_t st) {
+        k_record<T><<<1, 1, 0, st>>>(prob(p), it_local, m_star, s, a1, mu, nterms);
+    }
+    static cudaError_t batch(const void* probs, int count, size_t smem, int n_iters, unsigned long long seed, cudaStream_t st) {
+        k_batch<T, G><<<dim3((unsigned)count), dim3(NT), smem, st>>>(static_cast<const Prob<T>*>(probs), n_iters, seed);
+        return cudaGetLastError();
+    }
+};
+#endif  // SIGSDP_T
+
+// defined by the eight instantiation units
+extern const KernelSet ks_f64_g4, ks_f64_g8, ks_f64_g16, ks_f64_g32;
+extern const KernelSet ks_f32_g4, ks_f32_g8, ks_f32_g16, ks_f32_g32;
+
+}  // namespace sigsdp
