@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- MMW iterations/s on the 100k-node synthetic topology (BASELINE.json metric,
-configs[3] at one GPU), with the HBM roofline of the fused iteration kernel and the CPU
-baseline timed beside it.
+configs[3]), with the HBM roofline of the fused iteration kernel, a parity check against the
+oracle and the CPU baseline timed beside it.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
@@ -9,6 +9,11 @@ A "step" is one MMW iteration (reference mmw.py:77-197: averaging, dual/soft-max
 matrix, sketched exp(L/2) Omega by truncated Taylor SpMMs, edge-only Gram).  The timed
 region is exactly K iterations from the solver's initial state (the reference's
 `mmw(nit=K)` solve), after W warm-up iterations and a reset.
+
+N = 1: one fused persistent kernel on one GPU.  N > 1 (torchrun, one process per GPU): the SAME
+graph row-sharded across the ranks (sig_sdp_mmw_b200/rowshard.py): strong scaling, halo rows
+pushed through NVLink peer memory from the SpMM epilogue, cross-GPU barrier with packed scalars.
+`--parallel replicas|sketch` select the other multi-GPU modes.
 """
 import argparse
 import json
@@ -16,7 +21,6 @@ import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 import numpy as np
@@ -27,24 +31,27 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     # name: (env kwargs of the sparse twin of sim_src/env, Z, rank_radio, dtype)
     "cfg4_100k": (dict(cell_size=200, sta_density_per_1m2=6.25e-3), 16, 2, "float64"),
+    "cfg4x10_1m": (dict(cell_size=632, sta_density_per_1m2=6.25e-3), 16, 2, "float64"),
     "cfg3_20k": (dict(cell_size=63, sta_density_per_1m2=125e-4), 16, 2, "float64"),
     "cfg2_5k": (dict(cell_size=50, sta_density_per_1m2=5e-3), 8, 8, "float32"),
     "cfg1_500": (dict(cell_size=10, sta_density_per_1m2=125e-4), 4, 2, "float64"),
 }
 ETA = 0.04
-NCU_TRAFFIC_RATIO = 10.846 / 8.453   # measured DRAM bytes / algorithmic bytes of k_fused (see roofline.traffic_source)
 METRIC = "mmw_iters_per_s"
 UNIT = "iterations/s"
+PARITY_TOL = {"float64": 1e-9, "float32": 2e-3}
 
 
-def algorithmic_bytes(n, E_g, E_a, nnzT, D, w, terms, iters):
-    """bytes one iteration must move, summed over the run."""
+def algorithmic_bytes(n, E_g, E_a, nnzT, D, w):
+    """bytes one SpMM term / one edge Gram / the dual+loss+Omega part of
+    an iteration must move (w = bytes per sketch word; indices int32)."""
     E = E_g + E_a
     nnzL = n + 2 * E
     spmm = nnzL * (w + 4) + 4 * (n + 1) + 4 * n * D * w
     edge = (n * D * w + 8 * E + 3 * E * w + 2 * E_g * w + 2 * (E + n) * w + nnzT * (w + 4) + 12 * n * w + 3 * E_a * w)
     omega = 2 * n * D * w
-    return terms * spmm + iters * (edge + omega), spmm, edge + omega
+    gram = n * D * w + 8 * E + 3 * E * w + n * w       # read Y_h once, endpoints, write X + rmw X_avgd, row sums
+    return spmm, gram, edge - gram + omega
 
 
 class ClockSampler:
@@ -102,24 +109,56 @@ def make_state(workload, seed):
     return sparse_env(seed=seed, **kw).generate_S_Q_hmax(), Z, rr, dtype
 
 
-def time_oracle(state, Z, rr, budget_s, max_iters):
+def base_config(workload, n, Z, D):
+    """The workload keys, identical on both arms."""
+    return {"workload": workload, "nodes": int(n), "Z": int(Z), "D": int(D), "eta": ETA,
+            "timed": "K iterations from the initial state",
+            "l2": "inputs larger than L2 (working set > 126 MB, no flush)" if n >= 50000 else
+                  "working set fits L2 after the first pass (no flush)"}
+
+
+def time_oracle(state, Z, rr, budget_s, max_iters, snap_at=0):
     """The reference's CPU path (oracle port of mmw.py:77-197) on this box's host cores:
-    iterations from the initial state, bounded by `budget_s` seconds."""
+    iterations from the initial state, bounded by `budget_s` seconds.  snap_at > 0: also return
+    copies of (Y, Y_h) after that many iterations (untimed), for the parity check."""
     from oracle import mmw_oracle as orc
     K = state[0].shape[0]
     D = Z * rr
     p = orc.build_problem(Z, state)
     st = orc.MMWState(p, ETA)
     rs = np.random.RandomState(0)
-    t0 = time.perf_counter()
-    it = 0
+    dt, it, snap = 0.0, 0, None
     while it < max_iters:
-        st.step(rs.randn(K, D))
+        om = rs.randn(K, D)
+        t0 = time.perf_counter()
+        st.step(om)
+        dt += time.perf_counter() - t0
         it += 1
-        if time.perf_counter() - t0 > budget_s:
+        if it == snap_at:
+            snap = (st.Y.copy(), st.Yh.copy(), list(st.nterms))
+        if dt > budget_s:
             break
-    dt = time.perf_counter() - t0
-    return it / dt, it, dt, int(sum(st.nterms))
+    return it / dt, it, dt, int(sum(st.nterms)), snap
+
+
+def parity_check(make_solver_and_run, state, Z, rr, dtype, snap, iters):
+    """Feeds the oracle's Omega (numpy RandomState(0)) to the GPU path for `iters` iterations and
+    compares Y and Y_h with the oracle's.  make_solver_and_run(om) -> (Y, Yh, nterms)."""
+    K, D = state[0].shape[0], Z * rr
+    rs = np.random.RandomState(0)
+    om = np.empty((iters, K, D))
+    for i in range(iters):
+        om[i] = rs.randn(K, D)
+    Y, Yh, nterms = make_solver_and_run(om)
+    Yo, Yho, nto = snap
+    rel_Y = float(np.max(np.abs(Y - Yo) / np.abs(Yo)))
+    rel_Yh = float(np.max(np.abs(Yh - Yho)) / np.max(np.abs(Yho)))
+    tol = PARITY_TOL[dtype]
+    return {"iterations": iters, "max_rel_Y": rel_Y, "max_rel_Yh": rel_Yh, "tol": tol,
+            "taylor_terms_gpu": [int(x) for x in nterms], "taylor_terms_oracle": [int(x) for x in nto[:iters]],
+            "ok": bool(rel_Y <= tol and rel_Yh <= tol),
+            "what": "same Omega (numpy RandomState(0)) fed to the CUDA path through sigsdp_solver_iterate and to the "
+                    "oracle; Y elementwise relative, Y_h relative to max|Y_h|"}
 
 
 def run_reference(args):
@@ -128,19 +167,21 @@ def run_reference(args):
         return
     state, Z, rr, dtype = make_state(args.workload, 0)
     n = state[0].shape[0]
-    # each step = one reference iteration; the run is capped so it ends within minutes
-    for _ in range(min(args.warmup, 1)):
-        time_oracle(state, Z, rr, 1e9, 1)
-    ips, it, dt, terms = time_oracle(state, Z, rr, args.ref_budget, args.steps)
+    # W warm-up iterations (their own short run), then K timed iterations from the initial state;
+    # --ref-budget caps the timed run (it then reports the iterations it completed)
+    if args.warmup > 0:
+        time_oracle(state, Z, rr, args.ref_budget / 4, args.warmup)
+    ips, it, dt, terms, _ = time_oracle(state, Z, rr, args.ref_budget, args.steps)
     line = {
         "impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": it,
-        "warmup": min(args.warmup, 1), "ms_per_step": 1e3 / ips, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 / ips, "higher_is_better": True,
+        "scaling": "strong" if args.gpus > 1 else "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "nodes": n, "Z": Z, "D": Z * rr, "eta": ETA,
-                   "note": "oracle port of the reference's numpy/scipy path (the reference is pure Python and "
-                           "does not travel to the GPU box); scipy sparse kernels are single-threaded"},
+        "config": base_config(args.workload, n, Z, Z * rr),
+        "note": "oracle port of the reference's numpy/scipy path (the reference is pure Python and does not travel "
+                "to the GPU box); scipy sparse kernels are single-threaded",
         "cpu_baseline": {"value": ips, "unit": UNIT, "cores": 1, "kind": "port",
-                         "sample": "first %d of %d requested iterations from the initial state (%.1f s, %d Taylor terms)"
+                         "sample": "%d of %d requested iterations from the initial state (%.1f s, %d Taylor terms)"
                                    % (it, args.steps, dt, terms)},
         "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -152,7 +193,6 @@ def run_batch(args):
     split across the ranks (no communication).  Reports instance-iterations/s."""
     import torch
     import torch.distributed as dist
-    from sig_sdp_mmw_b200 import _lib
     from sig_sdp_mmw_b200.batch import BatchSolver, shard
     from sig_sdp_mmw_b200.topology import sparse_env
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -195,15 +235,15 @@ def run_batch(args):
                           "config": {"workload": "cfg5_batch", "instances": args.instances, "nodes": K, "Z": Z, "D": Z * rr,
                                      "parallelism": "one thread block per instance, instances split across %d rank(s)" % world,
                                      "taylor_terms_rank0": terms, "topology_s": t_gen, "plan_solver_setup_s": t_setup},
-                          "gpu_launches": 1}))
+                          "gpu_launches": len(bsol.batches)}))
     if world > 1:
         dist.destroy_process_group()
 
 
-def run_sharded(args):
-    """N > 1: ONE graph, the sketch columns sharded across the ranks (sig_sdp_mmw_b200/sharded.py):
-    no exchange inside the Taylor terms, one NCCL all-reduce of nnzL + n doubles per iteration.
-    Strong scaling: the job is the same 150-iteration solve as at N = 1."""
+def run_sketch_sharded(args):
+    """--parallel sketch: ONE graph, the sketch columns sharded across the ranks
+    (sig_sdp_mmw_b200/sharded.py): no exchange inside the Taylor terms, one NCCL all-reduce of
+    nnzL + n doubles per iteration.  Kept for comparison; the row-sharded mode is the default."""
     import torch
     import torch.distributed as dist
     from sig_sdp_mmw_b200 import _lib
@@ -214,25 +254,18 @@ def run_sharded(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
-    state, Z, rr, dtype = make_state(args.workload, 0)        # the same instance on every rank
+    state, Z, rr, dtype = make_state(args.workload, 0)
     K, D = state[0].shape[0], Z * rr
     code = _lib.F64 if dtype == "float64" else _lib.F32
-    w = 8 if dtype == "float64" else 4
-    t0 = time.perf_counter()
     plan = _lib.Plan(state, device=local, order=args.order)
     sh = ShardedSolver(plan, Z, D, ETA, rank, world, dtype=code)
-    setup_s = time.perf_counter() - t0
     stream = torch.cuda.current_stream().cuda_stream
     sh.iterate(max(args.warmup, 3), None, 1, stream)
     sh.finish(stream)
     sh.solver.reset(stream)
     torch.cuda.synchronize()
     dist.barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    dist.barrier()
     torch.cuda.synchronize()
     ev0.record()
     sh.iterate(args.steps, None, 1, stream)
@@ -240,56 +273,88 @@ def run_sharded(args):
     ev1.record()
     torch.cuda.synchronize()
     dist.barrier()
-    ms = ev0.elapsed_time(ev1)
-    terms = sh.solver.total_terms()
-    # end to end: host matrices in, plan + shard set-up, K iterations, running-mean diagonal out
-    dist.barrier()
-    t0 = time.perf_counter()
-    plan2 = _lib.Plan(state, device=local, order=args.order)
-    sh2 = ShardedSolver(plan2, Z, D, ETA, rank, world, dtype=code)
-    sh2.iterate(args.steps, None, 1, stream)
-    sh2.finish(stream)
-    xd, _, _ = sh2.solver.X(True)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max, e2e_ms = [float(x) for x in t.cpu()]
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        tot_bytes, spmm_b, rest_b = algorithmic_bytes(K, plan.E_g, plan.E_a, plan.nnzT, D, w, terms * world, args.steps)
-        S, Q, h = state
-        h2d = (S.indptr.nbytes + S.indices.nbytes + S.data.nbytes + Q.indptr.nbytes + Q.indices.nbytes + Q.data.nbytes + h.nbytes)
-        print(json.dumps({
-            "metric": METRIC, "value": args.steps / (ms_max * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64" if dtype == "float64" else "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "nodes": K, "Z": Z, "D": D, "eta": ETA, "nnzL": plan.nnz,
-                       "parallelism": "sketch columns sharded x%d (D/N = %d columns per GPU), dual/loss state replicated, "
-                                      "one NCCL all-reduce of %d doubles per iteration" % (world, D // world, plan.nnz + K),
-                       "taylor_terms_rank0": terms, "omega": "device Philox", "node_order": args.order,
-                       "launches_per_iteration": 1, "setup_s": setup_s},
-            "gpu_launches": args.steps + 1,
-            "roofline": {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,
-                         "note": "per-GPU roofline is reported at n_gpus = 1; here the replicated phases and the "
-                                 "all-reduce bound the step"},
-            "e2e": {"value": args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps,
-                    "d2h_bytes_per_step": xd.nbytes / args.steps,
-                    "what": "host state -> plan + shard set-up on every rank -> K iterations -> running-mean diagonal on host"},
-            "clocks": clocks}))
+        ms = float(t)
+        cfg = base_config(args.workload, K, Z, D)
+        print(json.dumps({"metric": METRIC, "value": args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+                          "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+                          "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                          "dtype": "f64" if dtype == "float64" else "f32", "data": "synthetic", "config": cfg,
+                          "parallelism": "sketch columns sharded x%d, one NCCL all-reduce of %d doubles per iteration"
+                                         % (world, plan.nnz + K),
+                          "gpu_launches": args.steps + 1}))
     dist.destroy_process_group()
+
+
+def roofline_block(peaks, plan, D, w, terms, steps, ms, phase_us, nshards=1):
+    """roofline of the fused kernel (whole iteration) with the SpMM and Gram phases broken out
+    from the kernel's own per-phase device timers."""
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    spmm_b, gram_b, rest_b = algorithmic_bytes(plan.n, plan.E_g, plan.E_a, plan.nnzT, D, w)
+    tot = terms * spmm_b + steps * (gram_b + rest_b)
+    ach = tot / (ms * 1e-3) / 1e9 / nshards          # per GPU
+    r = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+         "traffic": None,
+         "traffic_note": "not measured in this run; the committed ncu --set full capture of k_fused "
+                         "(profiles/r2_ncu_fused_cfg4_full.txt) gives DRAM bytes = 1.28 x algorithmic",
+         "kernel": "k_fused (whole iteration, per GPU)", "peak_source": peak_src,
+         "algorithmic_bytes_per_launch": tot, "spmm_term_bytes": spmm_b, "gram_bytes_per_iter": gram_b,
+         "dual_loss_omega_bytes_per_iter": rest_b}
+    if phase_us is not None and phase_us[2] > 0 and phase_us[3] > 0:
+        # phase_us: sums over the timed iterations of the leader block's timestamps (barriers included)
+        sp = terms * spmm_b / nshards / (phase_us[2] * 1e-6) / 1e9
+        gr = steps * gram_b / nshards / (phase_us[3] * 1e-6) / 1e9
+        rest = steps * rest_b / nshards / ((phase_us[0] + phase_us[1]) * 1e-6) / 1e9
+        r["spmm"] = {"achieved": sp, "frac": sp / peak, "us_per_term": phase_us[2] / max(terms, 1), "unit": "GB/s"}
+        r["gram"] = {"achieved": gr, "frac": gr / peak, "us_per_iter": phase_us[3] / steps, "unit": "GB/s"}
+        r["dual_loss_omega"] = {"achieved": rest, "frac": rest / peak, "us_per_iter": (phase_us[0] + phase_us[1]) / steps,
+                                "unit": "GB/s"}
+    return r
+
+
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def time_to_eps(sol, torch, stream, iters, Zt, cpu_ips):
+    """Second half of the BASELINE metric: e_max of the running mean X_avgd/i (mmw.py:80-96, the
+    curve plot_convergence_rho.py:47-50 draws, there normalised by its first point) sampled every
+    10 iterations of a fresh run at Z = set_bounds' lower bound; device time from CUDA events
+    around each chunk.  The CPU arm's time to the same point is iterations / its measured rate."""
+    sol.reset(stream)
+    torch.cuda.synchronize()
+    e_first = sol.gap_prepare(stream)            # row 0 of the reference's gap log (X_avgd = X_0 = I)
+    curve, t_acc = [], 0.0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for it in range(10, iters + 1, 10):
+        e0.record()
+        sol.iterate(10, None, 1, stream)
+        e1.record()
+        torch.cuda.synchronize()
+        t_acc += e0.elapsed_time(e1)
+        curve.append((it, t_acc, sol.gap_prepare(stream)))
+    out = {"quantity": "e_max(X_avgd / i) at Z = %d (set_bounds lower bound), eta = %g" % (Zt, ETA), "curve_every": 10,
+           "e_max_first": round(e_first, 5), "e_max": [round(c[2], 5) for c in curve]}
+    for eps in (1.0, 0.5, 0.25):
+        for tag, thr in (("abs", eps), ("rel", eps * e_first)):
+            hit = next((c for c in curve if c[2] <= thr), None)
+            out["eps_%g_%s" % (eps, tag)] = None if not hit else {
+                "iterations": hit[0], "device_ms": round(hit[1], 3),
+                "cpu_s_extrapolated": round(hit[0] / cpu_ips, 1) if cpu_ips else None}
+    return out
 
 
 def run_ours(args):
     import torch
     import torch.distributed as dist
     from sig_sdp_mmw_b200 import _lib, mmw
+    from sig_sdp_mmw_b200.binary_search_relaxation import binary_search_relaxation
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -300,14 +365,15 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    rows = world > 1 and args.parallel == "rows"
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # each rank owns one independent instance (replicas: weak scaling, no data-path collective)
-    state, Z, rr, dtype = make_state(args.workload, rank)
+    # rows: every rank holds the same instance; replicas: one independent instance per rank
+    state, Z, rr, dtype = make_state(args.workload, 0 if (rows or world == 1) else rank)
     K = state[0].shape[0]
     D = Z * rr
     dt_code = _lib.F64 if dtype == "float64" else _lib.F32
@@ -315,13 +381,23 @@ def run_ours(args):
     t0 = time.perf_counter()
     plan = _lib.Plan(state, device=local, order=args.order)
     plan_s = time.perf_counter() - t0
-    sol = _lib.Solver(plan, Z, D, ETA, dt_code, _lib.MODE_FUSED if args.mode == "fused" else _lib.MODE_STEPWISE,
-                      args.tiling)
     stream = torch.cuda.current_stream().cuda_stream
+    shard = None
+    if rows:
+        from sig_sdp_mmw_b200.rowshard import RowShardRank
+        shard = RowShardRank(plan, Z, D, ETA, dtype=dt_code, tiling=args.tiling)
+        sol = shard.solver
+        do_reset = lambda: shard.reset(stream)
+    else:
+        sol = _lib.Solver(plan, Z, D, ETA, dt_code, _lib.MODE_FUSED if args.mode == "fused" else _lib.MODE_STEPWISE,
+                          args.tiling)
+        do_reset = lambda: sol.reset(stream)
 
     # ---- device-resident timing: W warm-up iterations, reset, K timed iterations
-    sol.iterate(max(args.warmup, 3), None, 1, stream)
-    sol.reset(stream)
+    W = max(args.warmup, 3)
+    sol.iterate(W, None, 1, stream)
+    torch.cuda.synchronize()
+    do_reset()
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -329,48 +405,81 @@ def run_ours(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
-    sol.iterate(args.steps, None, 1, stream)        # ONE launch of the fused kernel
+    sol.iterate(args.steps, None, 1, stream)        # ONE launch of the fused kernel (per rank)
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
     terms = sol.total_terms()
     phase = sol.phase_times(min(args.steps, 8192)).sum(axis=0)
+    sync_ms = sol.sync_wait_ns() / 1e6
+    bar_ns = sol.barrier_breakdown_ns()
     if args.skip_e2e:
         if rank == 0:
             sampler.stop()
             print(json.dumps({"profiling_run": True, "mode": args.mode, "workload": args.workload, "steps": args.steps,
                               "ms": ms, "taylor_terms": terms, "phase_us": phase.tolist(), "grid": sol.grid,
-                              "tile_rows": sol.tile_rows, "smem": sol.smem,
-                              "barrier_wait_ms": sol.sync_wait_ns() / 1e6}))
+                              "tile_rows": sol.tile_rows, "smem": sol.smem, "barrier_wait_ms": sync_ms}))
+        if world > 1:
+            dist.destroy_process_group()
         return
 
-    # ---- time-to-epsilon (second half of the BASELINE metric): e_max of the running mean X_avgd/i
-    # (mmw.py:80-96, the quantity plot_convergence_rho.py:47-50 plots) sampled every 10
-    # iterations of a fresh run; device time accumulated with CUDA events around each chunk
-    tte = None
-    if not args.skip_e2e:
-        sol.reset(stream)
-        torch.cuda.synchronize()
-        curve, t_acc = [], 0.0
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        for it in range(10, args.tte_iters + 1, 10):
-            e0.record()
-            sol.iterate(10, None, 1, stream)
-            e1.record()
+    # ---- parity: the oracle on the same instance with the same Omega (rank 0 computes the oracle)
+    parity = None
+    cpu = None
+    P_IT = min(args.parity_iters, args.steps)
+    if P_IT > 0 and not args.no_cpu:
+        snap_state = None
+        if rank == 0:
+            budget = args.cpu_budget if world == 1 else 1e9          # N > 1: just the parity iterations
+            ips, it, dtc, cterms, snap_state = time_oracle(state, Z, rr, budget, max(args.steps, P_IT) if world == 1 else P_IT,
+                                                           snap_at=P_IT)
+            if it < P_IT:      # budget ran out first: finish the parity iterations untimed
+                _, _, _, _, snap_state = time_oracle(state, Z, rr, 1e9, P_IT, snap_at=P_IT)
+            if world == 1:
+                cpu = {"value": ips, "unit": UNIT, "cores": 1, "kind": "port",
+                       "sample": "first %d iterations of the same instance from the initial state (%.1f s, %d Taylor terms)"
+                                 % (it, dtc, cterms)}
+
+        def gpu_run(om):
+            do_reset()
+            om_d = torch.from_numpy(om).to(dev)
+            sol.iterate(om.shape[0], om_d.data_ptr(), 0, stream)
             torch.cuda.synchronize()
-            t_acc += e0.elapsed_time(e1)
-            curve.append((it, t_acc, sol.gap_prepare(stream)))
-        tte = {"quantity": "e_max(X_avgd / i) at Z=%d, eta=%g" % (Z, ETA), "curve_every": 10,
-               "e_max": [round(c[2], 5) for c in curve]}
-        for eps in (1.0, 0.5, 0.25):
-            hit = next((c for c in curve if c[2] <= eps), None)
-            tte["eps_%g" % eps] = {"iterations": hit[0], "device_ms": round(hit[1], 3)} if hit else None
+            nt = sol.history(om.shape[0])["nterms"]
+            if shard is not None:
+                return shard.gather_dual()[0], shard.gather_sketch(), nt
+            return sol.dual()[0], sol.sketch(), nt
+
+        if world == 1:
+            parity = parity_check(gpu_run, state, Z, rr, dtype, snap_state, P_IT)
+        else:
+            # every rank runs the same injected iterations; rank 0 compares
+            rs = np.random.RandomState(0)
+            om = np.stack([rs.randn(K, D) for _ in range(P_IT)])
+            Yg, Yhg, nt = gpu_run(om)
+            if rank == 0:
+                parity = parity_check(lambda _om: (Yg, Yhg, nt), state, Z, rr, dtype, snap_state, P_IT)
+        barrier()
+
+    # ---- time-to-epsilon at Z = set_bounds lower bound (one GPU only: it is a convergence curve)
+    tte = None
+    if world == 1 and args.tte_iters > 0:
+        Zt = binary_search_relaxation().set_bounds(state)[0]
+        sol_t = _lib.Solver(plan, Zt, Zt * rr, ETA, dt_code)
+        tte = time_to_eps(sol_t, torch, stream, args.tte_iters, Zt, cpu["value"] if cpu else None)
+        del sol_t
 
     # ---- end to end through the drop-in object, host buffers in, host factor out
     # one untimed call warms the process (cuBLAS handle, allocator pools); the timed call uses a
     # fresh solver object, so its graph plan is built from the host matrices again
-    mmw(nit=3, eta=ETA, rank_radio=rr, dtype=dtype, omega="device", device=local, order=args.order, seed=1).run_with_state(0, Z, state)
-    alg = mmw(nit=args.steps, eta=ETA, rank_radio=rr, dtype=dtype, omega="device", device=local, order=args.order, seed=1)
+    do_reset()
+    shard = None
+    sol_info = dict(grid=sol.grid, threads=sol.threads, lanes=sol.lanes, tile_rows=sol.tile_rows, smem=sol.smem)
+    sinfo = sol.shard_info() if rows else None
+    del sol
+    kw = dict(eta=ETA, rank_radio=rr, dtype=dtype, omega="device", device=local, order=args.order, seed=1, row_shard=rows)
+    mmw(nit=3, **kw).run_with_state(0, Z, state)
+    alg = mmw(nit=args.steps, **kw)
     barrier()
     t0 = time.perf_counter()
     ok, X_half = alg.run_with_state(0, Z, state)
@@ -382,63 +491,71 @@ def run_ours(args):
     h2d = (S.indptr.nbytes + S.indices.nbytes + S.data.nbytes + Q.indptr.nbytes + Q.indices.nbytes + Q.data.nbytes + h.nbytes)
     d2h = X_half.nbytes
 
-    t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, e2e_s * 1e3, sync_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max, e2e_ms_max = [float(x) for x in t.cpu()]
+    ms_max, e2e_ms_max, sync_max = [float(x) for x in t.cpu()]
 
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-        tot_bytes, spmm_b, rest_b = algorithmic_bytes(K, plan.E_g, plan.E_a, plan.nnzT, D, w, terms, args.steps)
-        achieved = tot_bytes / (ms * 1e-3) / 1e9
-        ws = (plan.nnz * (8 + 4 + 4 + 16) + 3 * K * sol.Dp * w + 4 * (plan.E_g + plan.E_a) * 8) / 1e6
+        peaks = load_peaks()
+        jobs = 1 if (rows or world == 1) else world            # replicas: N independent jobs
+        cfg = base_config(args.workload, K, Z, D)
+        if rows:
+            par = ("one graph row-sharded x%d: contiguous row strips of the locality order, halo rows pushed through "
+                   "NVLink peer memory by the SpMM epilogue, cross-GPU grid barrier with packed scalars" % world)
+        elif world > 1:
+            par = "replicas x%d (one independent instance per GPU)" % world
+        else:
+            par = "single GPU"
         line = {
-            "metric": METRIC, "value": world * args.steps / (ms_max * 1e-3), "unit": UNIT, "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": METRIC, "value": jobs * args.steps / (ms_max * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": W, "ms_per_step": ms_max / args.steps,
+            "higher_is_better": True, "scaling": "strong" if rows else "weak", "vs_baseline": None,
             "dtype": "f64" if dtype == "float64" else "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "nodes": K, "Z": Z, "D": D, "eta": ETA, "E_gain": plan.E_g,
-                       "E_asso": plan.E_a, "nnzL": plan.nnz, "taylor_terms": terms,
-                       "terms_per_iter": terms / args.steps, "parallelism": "replicas x%d" % world,
-                       "omega": "device Philox", "node_order": args.order,
-                       "timed": "K iterations from the initial state in one fused-kernel launch",
-                       "l2": "working set %.0f MB > 126 MB L2 (no flush)" % ws if ws > 126 else
-                             "working set %.0f MB fits L2: traffic is L2-resident after the first pass" % ws,
-                       "grid": sol.grid, "threads": sol.threads, "lanes_per_row": sol.lanes, "tile_rows": sol.tile_rows, "smem_bytes": sol.smem,
-                       "phase_us": {"dual": phase[0], "loss": phase[1], "sketch_gram": phase[2]},
-                       "plan_build_s": plan_s},
-            "gpu_launches": 1,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": tot_bytes * NCU_TRAFFIC_RATIO if args.workload == "cfg4_100k" else None,
-                         "traffic_source": "ncu --set full dram__bytes_read+write of k_fused on this workload "
-                                           "(profiles/r1c_ncu_fused_cfg4_full.txt: 10.85 GB for a 12-iteration launch "
-                                           "whose algorithmic bytes are 8.45 GB), scaled to this launch's algorithmic bytes",
-                         "kernel": "k_fused (whole iteration)", "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": tot_bytes, "spmm_term_bytes": spmm_b,
-                         "edge_dual_loss_omega_bytes_per_iter": rest_b},
-            "e2e": {"value": world * args.steps / (e2e_ms_max * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps,
+            "config": cfg,
+            "parallelism": par,
+            "detail": {"E_gain": plan.E_g, "E_asso": plan.E_a, "nnzL": plan.nnz, "taylor_terms": terms,
+                       "terms_per_iter": terms / args.steps, "omega": "device Philox", "node_order": args.order,
+                       "launches_per_rank": 1, "grid": sol_info["grid"], "threads": sol_info["threads"],
+                       "lanes_per_row": sol_info["lanes"], "tile_rows": sol_info["tile_rows"],
+                       "smem_bytes": sol_info["smem"],
+                       "phase_us_rank0": {"dual": phase[0], "loss": phase[1], "terms": phase[2], "gram": phase[3]},
+                       "barrier_wait_ms_max": sync_max, "plan_build_s": plan_s},
+            "gpu_launches": world if rows else 1,
+            "roofline": roofline_block(peaks, plan, D, w, terms, args.steps, ms_max, phase, world if rows else 1),
+            "e2e": {"value": jobs * args.steps / (e2e_ms_max * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps,
                     "d2h_bytes_per_step": d2h / args.steps,
-                    "what": "mmw(nit=K).run_with_state(state): plan build, upload, K iterations, Lanczos factor, download",
+                    "what": "mmw(nit=K, omega='device'%s).run_with_state(state): host scipy matrices -> plan build, upload, "
+                            "K iterations, final factor (eigen-solver), X_half on the host.  omega='numpy' (the parity "
+                            "mode an unchanged driver gets) draws K x n x D normals on the host instead"
+                            % (", row_shard=True" if rows else ""),
                     "breakdown_ms": {"state_process": float(alg.LOGGED_NP_DATA["mmw_state_process"][-1, 5]) / 1e3,
                                      "iterations_device": float(alg.LOGGED_NP_DATA["mmw_per_it"][:, 5].sum()) / 1e3,
                                      "final_factor": float(alg.LOGGED_NP_DATA["mmw_xavg"][-1, 5]) / 1e3,
                                      "total": e2e_s * 1e3,
-                                     "lanczos": getattr(alg, "last_eig_info", None)}},
+                                     "eig": getattr(alg, "last_eig_info", None)}},
             "clocks": clocks,
-            "time_to_eps": tte,
         }
-        if world == 1 and not args.no_cpu:
-            ips, it, dt, cterms = time_oracle(state, Z, rr, args.cpu_budget, args.steps)
-            line["cpu_baseline"] = {"value": ips, "unit": UNIT, "cores": 1, "kind": "port",
-                                    "sample": "first %d iterations of the same instance from the initial state "
-                                              "(%.1f s, %d Taylor terms)" % (it, dt, cterms)}
+        if rows:
+            halo = sinfo["halo_send_rows"]
+            line["exchange"] = {"halo_rows_sent_per_term_rank0": halo, "own_rows_rank0": sinfo["row_hi"] - sinfo["row_lo"],
+                                "bytes_per_term_rank0": halo * 2 * D * w,
+                                "barriers_per_iteration": 4 + terms / args.steps,
+                                "leader_barrier_ms_rank0": {"total": bar_ns[0] / 1e6, "wait_own_blocks": bar_ns[1] / 1e6,
+                                                            "reduce_and_send": bar_ns[2] / 1e6, "wait_peers": bar_ns[3] / 1e6},
+                                "transport": "st.global through CUDA-IPC peer mappings (NVLink), no NCCL inside iterate"}
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        if parity is not None:
+            line["parity"] = parity
+        if tte is not None:
+            line["time_to_eps"] = tte
         print(json.dumps(line))
+        if parity is not None and not parity["ok"]:
+            sys.stderr.write("PARITY FAILURE: %s\n" % json.dumps(parity))
+            if world > 1:
+                dist.destroy_process_group()
+            sys.exit(3)
     if world > 1:
         dist.destroy_process_group()
 
@@ -454,12 +571,13 @@ def main():
     ap.add_argument("--order", type=int, default=1, help="node renumbering inside the kernels (0 = caller's order)")
     ap.add_argument("--tiling", type=int, default=-1, help="rows per staged tile (-1 auto, 0 = direct-gather kernels)")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
-    ap.add_argument("--ref-budget", type=float, default=60.0)
-    ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--parallel", default="replicas", choices=["sketch", "replicas"],
-                    help="N > 1: one independent instance per GPU (weak scaling, default) or shard one graph's sketch "
-                         "columns across the GPUs (strong scaling, one all-reduce per iteration)")
-    ap.add_argument("--tte-iters", type=int, default=300, help="iterations of the time-to-epsilon run")
+    ap.add_argument("--ref-budget", type=float, default=240.0)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the oracle legs (cpu_baseline and parity)")
+    ap.add_argument("--parity-iters", type=int, default=4, help="iterations compared with the oracle on the same Omega")
+    ap.add_argument("--parallel", default="rows", choices=["rows", "sketch", "replicas"],
+                    help="N > 1: ONE graph row-sharded across the GPUs (default, strong scaling), its sketch columns "
+                         "sharded (one all-reduce per iteration), or one independent instance per GPU (weak scaling)")
+    ap.add_argument("--tte-iters", type=int, default=300, help="iterations of the time-to-epsilon run (0 = skip)")
     ap.add_argument("--mode", default="fused", choices=["fused", "stepwise"],
                     help="stepwise = one kernel per phase / Taylor term (profiling only, not a bench value)")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs: only the device-timed region")
@@ -467,10 +585,10 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.workload == "cfg5_batch":
         run_batch(args)
-    elif args.impl == "ours" and world > 1 and args.parallel == "sketch":
-        run_sharded(args)
     elif args.impl == "reference":
         run_reference(args)
+    elif world > 1 and args.parallel == "sketch":
+        run_sketch_sharded(args)
     else:
         run_ours(args)
 

@@ -198,16 +198,32 @@ int sigsdp_solver_set_X(sigsdp_solver* s, int averaged, const double* diag_host,
  * terms (int32 each) and ||A - mu I||_1, mu (fp64 each).  Any pointer may be NULL. */
 int sigsdp_solver_get_history(sigsdp_solver* s, int count, int32_t* m_star_host, int32_t* s_host,
                               int32_t* nterms_host, double* a1norm_host, double* mu_host);
-/* Device-timed microseconds of the last `count` iterations, count x 3 row-major:
- * dual (mmw.py:124-142) | loss (:144-170) | sketch + Gram (:172-197) -- what the
- * reference logs as mmw_dual / mmw_loss / mmw_expm.  Fused mode only (zeros otherwise). */
+/* Device-timed microseconds of the last `count` iterations, count x 4 row-major:
+ * dual (mmw.py:124-142) | loss (:144-170) | Taylor terms of the sketch (:180, :224-229) |
+ * edge Gram (:182-194) -- the reference logs the first two as mmw_dual / mmw_loss and the sum
+ * of the last two as mmw_expm.  Fused mode only (zeros otherwise). */
 int sigsdp_solver_get_phase_times(sigsdp_solver* s, int count, double* us_host);
 /* Diagnostics since create/reset: out8[4] = nanoseconds the fused kernel's leader thread spent
- * in team barriers (grid barriers; for a row shard this includes the cross-GPU wait), the other
+ * in team barriers (grid barriers; for a row shard this includes the cross-GPU wait).  Row shards
+ * split that: out8[5] = waiting for this GPU's other blocks, out8[6] = reducing and sending the
+ * packed scalars and epoch flags to the peers, out8[7] = waiting for the peers' flags.  The other
  * entries are reserved (0). */
 int sigsdp_solver_debug_cycles(sigsdp_solver* s, int64_t out8[8]);
 /* total Taylor terms (SpMM passes) executed since create/reset */
 int sigsdp_solver_total_terms(sigsdp_solver* s, int64_t* out);
+/* Device pointer and length (doubles) of one of the solver's fp64 state arrays in its INTERNAL
+ * layout, so that the host language can run a collective on it in place (NCCL through
+ * torch.distributed) without a trip through host memory:
+ *   SIGSDP_ARR_X_AVGD / SIGSDP_ARR_X : nnzL values in the pattern's CSR order (sigsdp_plan_pattern)
+ *   SIGSDP_ARR_Y_AVGD / SIGSDP_ARR_Y : C values [D | F | H], D and H in the internal node numbering
+ * A row shard only ever writes the X_AVGD / Y_AVGD entries it owns (the rest stay zero), so an
+ * all-reduce (sum) over the ranks leaves the complete running sums on every rank -- what the
+ * final factor (mmw.py:202-216) and the gap log need. */
+#define SIGSDP_ARR_X_AVGD 1
+#define SIGSDP_ARR_X 2
+#define SIGSDP_ARR_Y_AVGD 3
+#define SIGSDP_ARR_Y 4
+int sigsdp_solver_device_array(sigsdp_solver* s, int which, void** dev_ptr, int64_t* count);
 
 /* Row-tile statistics of a plan for given caps (host only, no device needed): tiles, bulk-copy
  * runs, staged rows (incl. gap rows), max staged rows / non-zeros of a tile, nnz. */

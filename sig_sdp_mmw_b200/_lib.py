@@ -9,6 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SIGSDP_LIB") or os.path.join(_HERE, "libsigsdp_mmw.so")
 
 F64, F32 = 0, 1
+ARR_X_AVGD, ARR_X, ARR_Y_AVGD, ARR_Y = 1, 2, 3, 4
 MODE_FUSED, MODE_STEPWISE = 0, 1
 
 _lib = None
@@ -47,6 +48,7 @@ def load():
         "sigsdp_solver_create_sharded": [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.POINTER(vp)],
         "sigsdp_solver_split_step": [vp, C.c_int, vp, C.c_uint64, vp],
         "sigsdp_solver_exchange_buffer": [vp, C.POINTER(vp), i64p],
+        "sigsdp_solver_device_array": [vp, C.c_int, C.POINTER(vp), i64p],
         "sigsdp_solver_create_rows": [vp, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)],
         "sigsdp_solver_shard_info": [vp, i64p],
         "sigsdp_solver_shard_arena": [vp, C.POINTER(vp), i64p],
@@ -259,6 +261,13 @@ class Solver:
         check(load().sigsdp_solver_exchange_buffer(self.handle, C.byref(ptr), C.byref(cnt)))
         return int(ptr.value), int(cnt.value)
 
+    def device_array(self, which):
+        """(device pointer, number of doubles) of a state array in the internal layout (ARR_*)."""
+        ptr = C.c_void_p()
+        cnt = C.c_int64()
+        check(load().sigsdp_solver_device_array(self.handle, int(which), C.byref(ptr), C.byref(cnt)))
+        return int(ptr.value), int(cnt.value)
+
     def dual(self):
         Y = np.empty(self.C); e = np.empty(self.C); Yb = np.empty(self.C)
         check(load().sigsdp_solver_get_dual(self.handle, _p(Y, C.c_double), _p(e, C.c_double), _p(Yb, C.c_double)))
@@ -289,7 +298,7 @@ class Solver:
         return dict(m_star=m, s=s, nterms=nt, a1norm=a1, mu=mu)
 
     def phase_times(self, count):
-        t = np.empty((count, 3))
+        t = np.empty((count, 4))
         check(load().sigsdp_solver_get_phase_times(self.handle, count, _p(t, C.c_double)))
         return t
 
@@ -317,6 +326,12 @@ class Solver:
         a = (C.c_int64 * 8)()
         check(load().sigsdp_solver_debug_cycles(self.handle, a))
         return int(a[4])
+
+    def barrier_breakdown_ns(self):
+        """Row shards: leader's barrier nanoseconds since reset as (total, local wait, send, peer wait)."""
+        a = (C.c_int64 * 8)()
+        check(load().sigsdp_solver_debug_cycles(self.handle, a))
+        return int(a[4]), int(a[5]), int(a[6]), int(a[7])
 
     def total_terms(self):
         v = C.c_int64()

@@ -753,7 +753,7 @@ static int solver_alloc(sigsdp_solver* s) {
     CK(s->mem.alloc(&P.hist_nt, HIST));
     CK(s->mem.alloc(&P.hist_a1, HIST));
     CK(s->mem.alloc(&P.hist_mu, HIST));
-    CK(s->mem.alloc(&P.hist_t, (size_t)HIST * 3 + 8));
+    CK(s->mem.alloc(&P.hist_t, (size_t)HIST * 4 + 8));
     P.omega = nullptr;
     P.seed = 0;
     tm.lap("solver alloc");
@@ -1009,7 +1009,7 @@ static int solver_reset_impl(sigsdp_solver* s, cudaStream_t st) {
     CK(cudaMemsetAsync(P.hist_nt, 0, HIST * sizeof(int), st));
     CK(cudaMemsetAsync(P.hist_a1, 0, HIST * sizeof(double), st));
     CK(cudaMemsetAsync(P.hist_mu, 0, HIST * sizeof(double), st));
-    CK(cudaMemsetAsync(P.hist_t, 0, ((size_t)HIST * 3 + 8) * sizeof(double), st));
+    CK(cudaMemsetAsync(P.hist_t, 0, ((size_t)HIST * 4 + 8) * sizeof(double), st));
     k_fill<double><<<64, 256, 0, st>>>(P.Y, (size_t)s->C, 1.0 / (double)s->C);  // Y = 1/C (mmw.py:62)
     k_set_diag<<<64, 256, 0, st>>>(P.Xv, P.g.dpos, (int)n, 1.0);                // X = I   (mmw.py:67)
     CK(cudaGetLastError());
@@ -1475,12 +1475,12 @@ int sigsdp_solver_get_phase_times(sigsdp_solver* s, int count, double* us_host) 
     if (count < 0 || count > HIST || count > s->iters_done) return fail(SIGSDP_EINVAL, "count out of range");
     CK(cudaSetDevice(s->plan->device));
     CK(cudaDeviceSynchronize());
-    std::vector<double> ht((size_t)HIST * 3);
+    std::vector<double> ht((size_t)HIST * 4);
     CK(cudaMemcpy(ht.data(), s->dtype == SIGSDP_F64 ? s->p64.hist_t : s->p32.hist_t, ht.size() * sizeof(double),
                   cudaMemcpyDeviceToHost));
     for (int i = 0; i < count; ++i) {
         const long long it = s->iters_done - count + i;
-        for (int j = 0; j < 3; ++j) us_host[(size_t)i * 3 + j] = ht[(size_t)(it % HIST) * 3 + j];
+        for (int j = 0; j < 4; ++j) us_host[(size_t)i * 4 + j] = ht[(size_t)(it % HIST) * 4 + j];
     }
     return SIGSDP_OK;
 }
@@ -1502,6 +1502,19 @@ int sigsdp_solver_total_terms(sigsdp_solver* s, int64_t* out) {
     Ctrl hc;
     CK(cudaMemcpy(&hc, s->dtype == SIGSDP_F64 ? s->p64.ctrl : s->p32.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost));
     *out = hc.total_terms;
+    return SIGSDP_OK;
+}
+
+int sigsdp_solver_device_array(sigsdp_solver* s, int which, void** dev_ptr, int64_t* count) {
+    if (!s || !dev_ptr || !count) return fail(SIGSDP_EINVAL, "null argument");
+    const bool d = s->dtype == SIGSDP_F64;
+    switch (which) {
+        case SIGSDP_ARR_X_AVGD: *dev_ptr = d ? s->p64.Xbarv : s->p32.Xbarv; *count = s->plan->h.nnz; break;
+        case SIGSDP_ARR_X: *dev_ptr = d ? s->p64.Xv : s->p32.Xv; *count = s->plan->h.nnz; break;
+        case SIGSDP_ARR_Y_AVGD: *dev_ptr = d ? s->p64.Ybar : s->p32.Ybar; *count = s->C; break;
+        case SIGSDP_ARR_Y: *dev_ptr = d ? s->p64.Y : s->p32.Y; *count = s->C; break;
+        default: return fail(SIGSDP_EINVAL, "unknown array id");
+    }
     return SIGSDP_OK;
 }
 

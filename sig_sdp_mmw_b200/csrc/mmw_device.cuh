@@ -80,8 +80,8 @@ struct ShardDev {
     const int* inc_pos;          // position of that edge's entry in an own row
     const unsigned char* pmask;  // n: bit p set = rank p reads row k of B / F / r / q (nullptr: unsharded)
     long long delta[MAXR];       // bytes from this rank's exchange arena to rank p's
-    unsigned long long* flags;   // [MAXR] barrier epochs the peers have reached (in this rank's arena)
-    unsigned long long* inbox;   // [2][MAXR][8] packed scalars of the peers, by barrier parity
+    unsigned long long* flags;   // (reserved: first 256 bytes of the arena)
+    unsigned long long* inbox;   // [2][MAXR][16] the ranks' scalar words {epoch | half}, by barrier parity
     unsigned long long timeout_ns;
 };
 
@@ -140,7 +140,7 @@ struct Prob {
     int* hist_nt;
     double* hist_a1;
     double* hist_mu;
-    double* hist_t;        // HIST x 3: device-timed microseconds of dual / loss / sketch+Gram
+    double* hist_t;        // HIST x 4: device-timed microseconds of dual / loss / Taylor terms / Gram
     const double* omega;   // raw normals for this call (caller numbering) or nullptr
     unsigned long long seed;
     TileDev tl;
@@ -175,6 +175,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 __device__ __forceinline__ unsigned long long ld_u64(const unsigned long long* p) {
     return *reinterpret_cast<const volatile unsigned long long*>(p);
 }
+__device__ __forceinline__ double ld_f64(const double* p) { return *reinterpret_cast<const volatile double*>(p); }
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -213,19 +214,47 @@ __device__ __forceinline__ double block_max(double v, double* sh) {
     __syncthreads();
     return sh[NWARP];
 }
+// One warp sums part[b * stride], b < nblk, in a fixed order with eight independent loads in flight
+// per lane (a dynamic-trip-count loop of dependent loads would expose one L2 latency per 32 blocks:
+// measured 5 us for 296 blocks).  Result valid in every lane.
+__device__ __forceinline__ double warp_strided_sum(const double* part, int stride, int nblk, int lane) {
+    double t = 0.0;
+    for (int b0 = 0; b0 < nblk; b0 += 256) {
+        double v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int b = b0 + 32 * i + lane;
+            v[i] = b < nblk ? ld_f64(part + (size_t)b * stride) : 0.0;
+        }
+        t += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+    }
+    return warp_sum(t);
+}
 // sum of one double per block written by every block of the team before the last
 // barrier; fixed order, so every block (and every run) gets the same bits
 __device__ __forceinline__ double team_sum(const double* part, int stride, int nblk, double* sh) {
-    double t = 0.0;
     if (threadIdx.x < 32) {
-        for (int b = threadIdx.x; b < nblk; b += 32) t += part[(size_t)b * stride];
-        t = warp_sum(t);
+        const double t = warp_strided_sum(part, stride, nblk, threadIdx.x);
         if (threadIdx.x == 0) sh[NWARP] = t;
     }
     __syncthreads();
-    t = sh[NWARP];
+    const double t = sh[NWARP];
     __syncthreads();
     return t;
+}
+// four such sums (columns 0..3 of a [blocks][PSTRIDE] array) by four warps at once
+__device__ __forceinline__ void team_sum4(const double* part, int nblk, double* sh, double s[4]) {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (w < 4) {
+        const double t = warp_strided_sum(part + w, PSTRIDE, nblk, lane);
+        if (lane == 0) sh[w] = t;
+    }
+    __syncthreads();
+    s[0] = sh[0];
+    s[1] = sh[1];
+    s[2] = sh[2];
+    s[3] = sh[3];
+    __syncthreads();
 }
 
 template <int G>
@@ -261,12 +290,10 @@ struct SpinGuard {
 
 // shared by the single-GPU teams: the scalars live in this solver's Ctrl / partial arrays
 struct LocalScalars {
+    __device__ void note_push() const {}
     template <typename T> __device__ double emax(const Prob<T>& P) const { return dkey_any_inv(ld_u64(&P.ctrl->emax_key)); }
     template <typename T> __device__ void exp_sums(const Prob<T>& P, int nblk, double* sh, double s[4]) const {
-        s[0] = team_sum(P.psum + 0, PSTRIDE, nblk, sh);
-        s[1] = team_sum(P.psum + 1, PSTRIDE, nblk, sh);
-        s[2] = team_sum(P.psum + 2, PSTRIDE, nblk, sh);
-        s[3] = team_sum(P.psum + 3, PSTRIDE, nblk, sh);
+        team_sum4(P.psum, nblk, sh, s);
     }
     template <typename T> __device__ double a1(const Prob<T>& P) const { return dkey_pos_inv(ld_u64(&P.ctrl->a1_key)); }
     template <typename T> __device__ double c1(const Prob<T>& P) const { return dkey_pos_inv(ld_u64(&P.ctrl->c1_key)); }
@@ -331,22 +358,32 @@ struct CtaTeam : LocalScalars {  // batch: one block owns the instance
 };
 
 // Row-sharded solver: the blocks of this GPU plus, through peer-mapped memory, the blocks of
-// the other ranks.  A barrier is (1) every block of this GPU arrives on the local counter with
-// a system-scope release (its halo pushes into the peers' arrays are ordered before it);
-// (2) block 0 waits for the local count, reduces this rank's partial scalars in a fixed order,
-// stores them into slot [parity][rank] of EVERY rank's inbox and then releases its epoch number
-// into every rank's flag array; (3) every block of every rank polls its own flag array until
-// all ranks have reached the epoch, then reduces the inbox over the ranks in rank order -- so
-// every block on every GPU continues with bit-identical scalars (same Taylor degree, same
-// early exit, same trace), which is what keeps the ranks' control flow in step without a host.
+// the other ranks.  A barrier is
+//  (1) every block of this GPU arrives on the local counter; a block that pushed halo rows into
+//      a peer's arrays since the last barrier first orders them with a system-scope fence (the
+//      stores have reached the peer), the others only need a GPU-scope fence;
+//  (2) block 0 waits for the local count, reduces this rank's partial scalars in a fixed order
+//      and stores them into slot [parity][rank] of EVERY rank's inbox as 16 self-validating
+//      words {epoch : 32 | half of a scalar : 32} (the "LL" protocol of collective libraries: an
+//      8-byte store is atomic, so no fence is needed between payload and flag and the words
+//      double as the arrival flags);
+//  (3) every block of every rank polls its own inbox until all ranks' words carry the epoch,
+//      then reduces the scalars over the ranks in rank order -- so every block on every GPU
+//      continues with bit-identical scalars (same Taylor degree, same early exit, same trace),
+//      which is what keeps the ranks' control flow in step without a host.
 // The inbox is double-buffered by barrier parity: a rank can be at most one barrier ahead.
+// Measured on 2 x B200 (scripts/micro/p2p_fence.cu): fence.sys 0.9 us idle, 1.7 us after a peer
+// store, one-way peer store 1.2 us, red.release.sys 1.8 us vs red.release.gpu 0.4 us.
+constexpr int LLW = 16;   // LL words per rank and barrier: 8 scalars x 2 halves
 struct ShardTeam {
     unsigned long long* ctr;
     mutable unsigned long long next;
     mutable unsigned long long epoch;
-    double* xr;   // shared memory, 8 doubles: [0..3] keys (as doubles' bit patterns), [4..7] sums
+    mutable int pushed;
+    double* xr;      // shared memory, 8 doubles: [0..3] keys (as doubles' bit patterns), [4..7] sums
+    unsigned* xh;    // shared memory, MAXR * LLW halves as received
     template <typename T>
-    __device__ ShardTeam(const Prob<T>& P, double* xr_) : ctr(&P.ctrl->bar), xr(xr_) {
+    __device__ ShardTeam(const Prob<T>& P, double* xr_, unsigned* xh_) : ctr(&P.ctrl->bar), pushed(0), xr(xr_), xh(xh_) {
         unsigned long long v;
         asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(ctr) : "memory");
         next = (v / gridDim.x + 1ull) * gridDim.x;
@@ -354,27 +391,33 @@ struct ShardTeam {
     }
     __device__ int rank() const { return blockIdx.x; }
     __device__ int size() const { return gridDim.x; }
+    __device__ void note_push() const { pushed = 1; }
     template <typename T>
     __device__ void sync(const Prob<T>& P, int what = SY_PLAIN, int slot = 0) const {
         const ShardDev& S = P.sh;
         Ctrl* ctrl = P.ctrl;
         const unsigned long long ep = epoch + 1ull;
         const unsigned par = (unsigned)(ep & 1ull);
-        __syncthreads();
+        const unsigned ep32 = (unsigned)ep;
+        const int any_push = __syncthreads_or(pushed);
+        pushed = 0;
         if (threadIdx.x == 0) {
-            __threadfence_system();
-            asm volatile("red.release.sys.global.add.u64 [%0], 1;" ::"l"(ctr) : "memory");
+            if (any_push) __threadfence_system(); else __threadfence();
+            asm volatile("red.relaxed.gpu.global.add.u64 [%0], 1;" ::"l"(ctr) : "memory");
         }
+        unsigned long long tb0 = 0, tb1 = 0, tb2 = 0;   // leader's timestamps: arrived / local complete / words sent
         if (blockIdx.x == 0 && threadIdx.x < 32) {
             const int lane = threadIdx.x;
             if (lane == 0) {
+                tb0 = globaltimer_ns();
                 unsigned long long v;
                 SpinGuard g;
                 for (;;) {
-                    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(ctr) : "memory");
+                    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(ctr) : "memory");
                     if (v >= next) break;
                     g.step(S.timeout_ns);
                 }
+                tb1 = globaltimer_ns();
             }
             __syncwarp();
             // this rank's payload: 4 keys (max-reduced across ranks) and 4 sums
@@ -385,64 +428,84 @@ struct ShardTeam {
                 pk[0] = ld_u64(&ctrl->emax_key);
             } else if (what == SY_EXP) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    double t = 0.0;
-                    for (int b = lane; b < nblk; b += 32) t += P.psum[(size_t)b * PSTRIDE + i];
-                    ps[i] = warp_sum(t);
-                }
+                for (int i = 0; i < 4; ++i) ps[i] = warp_strided_sum(P.psum + i, PSTRIDE, nblk, lane);
             } else if (what == SY_LOSS || what == SY_TERM) {
                 pk[0] = what == SY_LOSS ? ld_u64(&ctrl->a1_key) : ld_u64(&ctrl->nrm_b[slot]);
                 pk[1] = what == SY_LOSS ? ld_u64(&ctrl->c1_key) : ld_u64(&ctrl->nrm_f[slot]);
-                double t = 0.0;
-                for (int b = lane; b < nblk; b += 32) t += P.ptr[b];
-                ps[0] = warp_sum(t);
+                ps[0] = warp_strided_sum(P.ptr, 1, nblk, lane);
             }
-            if (lane < S.nranks) {
-                char* peer = reinterpret_cast<char*>(S.inbox) + S.delta[lane];
-                unsigned long long* dst = reinterpret_cast<unsigned long long*>(peer) + ((size_t)par * MAXR + S.rank) * 8;
-                if (what != SY_PLAIN) {
+            // lane l < 16 sends half (l & 1) of scalar l >> 1, tagged with the epoch
+            const int si = lane >> 1;
+            unsigned long long full = 0ull;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        dst[i] = pk[i];
-                        dst[4 + i] = (unsigned long long)__double_as_longlong(ps[i]);
-                    }
-                    __threadfence_system();
-                }
-                unsigned long long* fl = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(S.flags) + S.delta[lane]) + S.rank;
-                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(fl), "l"(ep) : "memory");
+            for (int i = 0; i < 4; ++i) {
+                if (si == i) full = pk[i];
+                if (si == 4 + i) full = (unsigned long long)__double_as_longlong(ps[i]);
             }
+            const unsigned half = (lane & 1) ? (unsigned)(full >> 32) : (unsigned)full;
+            const unsigned long long word = ((unsigned long long)ep32 << 32) | (unsigned long long)half;
+            // release: what this GPU's blocks published before arriving is ordered before the words
+            // (halo rows were already fenced at system scope by the blocks that wrote them)
+            __threadfence_system();
+            if (lane < LLW) {
+                for (int r = 0; r < S.nranks; ++r) {
+                    unsigned long long* dst = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(S.inbox) + S.delta[r]) +
+                                              ((size_t)par * MAXR + S.rank) * LLW + lane;
+                    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(word) : "memory");
+                }
+            }
+            __syncwarp();
+            if (lane == 0) tb2 = globaltimer_ns();
         }
-        if (threadIdx.x < S.nranks) {   // one poller per peer
+        if (threadIdx.x < LLW * S.nranks) {   // one reader per word; the acquire load also drops stale L1 lines
+            // only the reader of a rank's LAST word polls (with a short sleep: thousands of tight
+            // pollers slow the leader's own memory operations down); when that word is there the
+            // other fifteen almost always are, and every reader still checks its own word
+            const unsigned grp_mask = __activemask();
+            const unsigned long long* src = S.inbox + ((size_t)par * MAXR + (threadIdx.x / LLW)) * LLW + (threadIdx.x % LLW);
             unsigned long long v;
             SpinGuard g;
+            if ((threadIdx.x % LLW) == LLW - 1) {
+                for (;;) {
+                    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(src) : "memory");
+                    if ((unsigned)(v >> 32) == ep32) break;
+                    __nanosleep(40);
+                    g.step(S.timeout_ns);
+                }
+            }
+            __syncwarp(grp_mask);
             for (;;) {
-                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(S.flags + threadIdx.x) : "memory");
-                if (v >= ep) break;
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(src) : "memory");
+                if ((unsigned)(v >> 32) == ep32) break;
                 g.step(S.timeout_ns);
             }
+            xh[threadIdx.x] = (unsigned)v;
         }
         __syncthreads();
         if (what != SY_PLAIN && threadIdx.x < 8) {
-            const unsigned long long* in = S.inbox + (size_t)par * MAXR * 8 + threadIdx.x;
             if (threadIdx.x < 4) {
                 unsigned long long m = 0ull;
                 for (int r = 0; r < S.nranks; ++r) {
-                    unsigned long long v;
-                    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(in + (size_t)r * 8) : "memory");
+                    const unsigned long long v = ((unsigned long long)xh[r * LLW + 2 * threadIdx.x + 1] << 32) | xh[r * LLW + 2 * threadIdx.x];
                     m = v > m ? v : m;
                 }
                 xr[threadIdx.x] = __longlong_as_double((long long)m);
             } else {
                 double a = 0.0;
                 for (int r = 0; r < S.nranks; ++r) {
-                    unsigned long long v;
-                    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(in + (size_t)r * 8) : "memory");
+                    const unsigned long long v = ((unsigned long long)xh[r * LLW + 2 * threadIdx.x + 1] << 32) | xh[r * LLW + 2 * threadIdx.x];
                     a += __longlong_as_double((long long)v);
                 }
                 xr[threadIdx.x] = a;
             }
         }
         __syncthreads();
+        if (blockIdx.x == 0 && threadIdx.x == 0) {   // where the leader's barrier time goes (ns, see sigsdp_solver_debug_cycles)
+            const unsigned long long tb3 = globaltimer_ns();
+            ctrl->dbg[5] += (long long)(tb1 - tb0);   // waiting for this GPU's blocks
+            ctrl->dbg[6] += (long long)(tb2 - tb1);   // reducing + sending the scalar words to the peers
+            ctrl->dbg[7] += (long long)(tb3 - tb2);   // waiting for the peers' words
+        }
         next += gridDim.x;
         epoch = ep;
     }
@@ -461,16 +524,20 @@ struct ShardTeam {
     template <typename T> __device__ void finish(const Prob<T>& P) const { P.ctrl->xepoch = epoch; }
 };
 
-// halo pushes: the same element of every peer's copy of an exchange-arena array
-template <typename V, typename T>
-__device__ __forceinline__ void push_vec(const ShardDev& S, T* local, const V& v, unsigned mask) {
+// halo pushes: the same element of every peer's copy of an exchange-arena array.  The team is
+// told, so that its next barrier orders these stores at system scope before it signals the peers.
+template <class Team, typename V, typename T>
+__device__ __forceinline__ void push_vec(const Team& team, const ShardDev& S, T* local, const V& v, unsigned mask) {
+    if (mask) team.note_push();
     while (mask) {
         const int r = __ffs((int)mask) - 1;
         mask &= mask - 1u;
         v.store(reinterpret_cast<T*>(reinterpret_cast<char*>(local) + S.delta[r]));
     }
 }
-__device__ __forceinline__ void push_f64(const ShardDev& S, double* local, double v, unsigned mask) {
+template <class Team>
+__device__ __forceinline__ void push_f64(const Team& team, const ShardDev& S, double* local, double v, unsigned mask) {
+    if (mask) team.note_push();
     while (mask) {
         const int r = __ffs((int)mask) - 1;
         mask &= mask - 1u;
@@ -806,7 +873,7 @@ __device__ void phase_exp(const Prob<T>& P, const Team& team, double* sh) {
             P.u[K + g.E_a + k] = v;
             const double qq = v / P.nH[k];
             P.q[k] = qq;
-            if (S.pmask) push_f64(S, P.q + k, qq, S.pmask[k]);
+            if (S.pmask) push_f64(team, S, P.q + k, qq, S.pmask[k]);
             sH += v;
             sHq += P.hcoef[k] * qq;
         }
@@ -1013,8 +1080,8 @@ __device__ void phase_loss(const Prob<T>& P, const Team& team, int it_local, dou
                 w.store(P.B0 + (size_t)k * Dp + c0);
                 w.store(P.F + (size_t)k * Dp + c0);
                 if (pm) {
-                    push_vec(S, P.B0 + (size_t)k * Dp + c0, w, pm);
-                    push_vec(S, P.F + (size_t)k * Dp + c0, w, pm);
+                    push_vec(team, S, P.B0 + (size_t)k * Dp + c0, w, pm);
+                    push_vec(team, S, P.F + (size_t)k * Dp + c0, w, pm);
                 }
             }
             rs = group_sum<G>(tile, rs);
@@ -1111,8 +1178,8 @@ __device__ void phase_term(const Prob<T>& P, const Team& team, const T* Bin, T* 
                     bn.store(Bout + (size_t)k * Dp + c0);
                     f.store(P.F + (size_t)k * Dp + c0);
                     if (pm) {
-                        push_vec(S, Bout + (size_t)k * Dp + c0, bn, pm);
-                        push_vec(S, P.F + (size_t)k * Dp + c0, f, pm);
+                        push_vec(team, S, Bout + (size_t)k * Dp + c0, bn, pm);
+                        push_vec(team, S, P.F + (size_t)k * Dp + c0, f, pm);
                     }
                 }
             }
@@ -1220,7 +1287,7 @@ __device__ void phase_gram(const Prob<T>& P, const Team& team, double* sh) {
             rsum = group_sum<G>(tile, rsum);
             if (lane == 0 && !P.split) {
                 P.r[k] = rsum;
-                if (S.pmask) push_f64(S, P.r + k, rsum, S.pmask[k]);
+                if (S.pmask) push_f64(team, S, P.r + k, rsum, S.pmask[k]);
             }
         }
     }
@@ -1317,8 +1384,8 @@ __device__ void phase_term_staged(const Prob<T>& P, const Team& team, const T* B
                     bn.store(Bout + (size_t)k * Dp + c0);
                     f.store(P.F + (size_t)k * Dp + c0);
                     if (pm) {
-                        push_vec(S, Bout + (size_t)k * Dp + c0, bn, pm);
-                        push_vec(S, P.F + (size_t)k * Dp + c0, f, pm);
+                        push_vec(team, S, Bout + (size_t)k * Dp + c0, bn, pm);
+                        push_vec(team, S, P.F + (size_t)k * Dp + c0, f, pm);
                     }
                 }
             }
@@ -1481,10 +1548,10 @@ __device__ void phase_term_staged2(const Prob<T>& P, const Team& team, const T* 
                 fa.store(P.F + (size_t)k * Dp + ca);
                 fb.store(P.F + (size_t)k * Dp + cb2);
                 if (pm) {   // rows a neighbouring rank reads: the same stores into its copies (NVLink)
-                    push_vec(S, Bout + (size_t)k * Dp + ca, bna, pm);
-                    push_vec(S, Bout + (size_t)k * Dp + cb2, bnb, pm);
-                    push_vec(S, P.F + (size_t)k * Dp + ca, fa, pm);
-                    push_vec(S, P.F + (size_t)k * Dp + cb2, fb, pm);
+                    push_vec(team, S, Bout + (size_t)k * Dp + ca, bna, pm);
+                    push_vec(team, S, Bout + (size_t)k * Dp + cb2, bnb, pm);
+                    push_vec(team, S, P.F + (size_t)k * Dp + ca, fa, pm);
+                    push_vec(team, S, P.F + (size_t)k * Dp + cb2, fb, pm);
                 }
             }
             // all 32 lanes are converged here: xor-shuffles below GH stay inside the group
@@ -1631,7 +1698,7 @@ __device__ void phase_gram_staged(const Prob<T>& P, const Team& team, double* sh
             rsum = warp_sum(rsum);
             if (k < r1 && lane == 0 && !raw) {
                 P.r[k] = rsum;
-                if (S.pmask) push_f64(S, P.r + k, rsum, S.pmask[k]);
+                if (S.pmask) push_f64(team, S, P.r + k, rsum, S.pmask[k]);
             }
         }
     }
@@ -1769,7 +1836,7 @@ __device__ void phase_gram_staged2(const Prob<T>& P, const Team& team, double* s
             }
             if (valid && role != 2 && lane == 0 && !raw) {
                 P.r[k] = rsum;
-                if (S.pmask) push_f64(S, P.r + k, rsum, S.pmask[k]);
+                if (S.pmask) push_f64(team, S, P.r + k, rsum, S.pmask[k]);
             }
         }
     }
@@ -1880,7 +1947,7 @@ __device__ void run_iterations(const Prob<T>& P, const Team& team, int n_iters, 
         TIMED_SYNC(SY_PLAIN, 0);
     }
     for (int it = 0; it < n_iters; ++it) {
-        unsigned long long t0 = 0, t1 = 0, t2 = 0;
+        unsigned long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
         if (leader) t0 = globaltimer_ns();
         phase_dual<T, G>(P, team, sh);
         TIMED_SYNC(SY_DUAL, 0);
@@ -1923,6 +1990,7 @@ __device__ void run_iterations(const Prob<T>& P, const Team& team, int n_iters, 
             }
         }
         terms += tcount;
+        if (leader) t3 = globaltimer_ns();
         if (staged)
             if (G >= 8 && P.Dp == G * Vec<T>::N)
                 phase_gram_staged2<T, G>(P, team, sh, st);
@@ -1934,11 +2002,12 @@ __device__ void run_iterations(const Prob<T>& P, const Team& team, int n_iters, 
         if (leader) {
             const long long iter = ctrl->iter + it;
             record_history(P, iter, ts, tcount);
-            const unsigned long long t3 = globaltimer_ns();
-            double* ht = P.hist_t + (size_t)(iter % HIST) * 3;
+            const unsigned long long t4 = globaltimer_ns();
+            double* ht = P.hist_t + (size_t)(iter % HIST) * 4;
             ht[0] = (double)(t1 - t0) * 1e-3;
             ht[1] = (double)(t2 - t1) * 1e-3;
             ht[2] = (double)(t3 - t2) * 1e-3;
+            ht[3] = (double)(t4 - t3) * 1e-3;
         }
     }
 #undef TIMED_SYNC

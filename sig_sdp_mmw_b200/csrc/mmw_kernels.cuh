@@ -43,7 +43,8 @@ __global__ void __launch_bounds__(NT, 2) k_fused_rows(Prob<T> P, int n_iters) {
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     __shared__ double sh[NWARP + 2];
     __shared__ double xr[8];
-    ShardTeam team(P, xr);
+    __shared__ unsigned xh[MAXR * LLW];
+    ShardTeam team(P, xr, xh);
     run_iterations<T, G>(P, team, n_iters, dyn_smem, sh, 0);
 }
 template <typename T, int G>

@@ -15,6 +15,11 @@ has no notion of (all default to the reference's behaviour):
   device  : CUDA device index
   order   : 1 (default) renumber nodes inside the kernels for locality (transparent: all
             inputs and outputs stay in the caller's numbering), 0 keep the caller's order
+  row_shard : True -- the process is one rank of a torch.distributed job (one process per
+            GPU) and the ranks solve ONE graph together, each owning a strip of rows
+            (sig_sdp_mmw_b200/rowshard.py, BASELINE configs[3]); every rank passes the same
+            state and gets the same X_half back.  `shard_group`: the process group (default
+            world).
 
 There is no CPU fallback: a missing library or CUDA device raises."""
 import math
@@ -32,7 +37,7 @@ _OMEGA_CHUNK_BYTES = 1 << 30
 
 class mmw(STATS_OBJECT, sdp_solver):
     def __init__(self, nit=100, rank_radio=2, alpha=1., eta=0.1, log_gap=False,
-                 dtype="float64", omega="numpy", device=0, order=1, seed=0):
+                 dtype="float64", omega="numpy", device=0, order=1, seed=0, row_shard=False, shard_group=None):
         sdp_solver.__init__(self, nit=nit, rank_radio=rank_radio, alpha=alpha)
         self.eta = eta
         self.LOG_GAP = log_gap
@@ -43,6 +48,8 @@ class mmw(STATS_OBJECT, sdp_solver):
         self.seed = seed
         self.mode = _lib.MODE_FUSED
         self.eig_tol = 1e-10          # relative residual of the final factor's eigenpairs
+        self.row_shard = bool(row_shard)
+        self.shard_group = shard_group
         self.last_solver = None
 
     def run_with_state(self, bs_iteration, Z, state):
@@ -148,7 +155,15 @@ class mmw(STATS_OBJECT, sdp_solver):
         K = state[0].shape[0]
         D = Z * self.rank_radio                                   # mmw.py:180
         plan = self._plan_for(state)
-        solver = _lib.Solver(plan, Z, D, self.eta, self._dtype_code(), self.mode)
+        shard = None
+        if self.row_shard:
+            from .rowshard import RowShardRank
+            if self.LOG_GAP:
+                raise _lib.SigSdpError("LOG_GAP is not available on a row-sharded solve")
+            shard = RowShardRank(plan, Z, D, self.eta, dtype=self._dtype_code(), group=self.shard_group)
+            solver = shard.solver
+        else:
+            solver = _lib.Solver(plan, Z, D, self.eta, self._dtype_code(), self.mode)
         self.last_solver = solver
         dev = torch.device("cuda", plan.device)
         self._add_np_log("mmw_state_process", 0, np.array([Z, K, self._get_tim(sp_tic)]))
@@ -186,18 +201,20 @@ class mmw(STATS_OBJECT, sdp_solver):
 
             # per-iteration phase logs, device-timed (mmw.py:142,170,197,200)
             cnt = min(nit, 8192)
-            pt = solver.phase_times(cnt) if self.mode == _lib.MODE_FUSED else np.zeros((cnt, 3))
+            pt = solver.phase_times(cnt) if self.mode == _lib.MODE_FUSED else np.zeros((cnt, 4))
             if not pt.any():
-                pt = np.full((cnt, 3), wall_us / max(nit, 1) / 3.0)
+                pt = np.full((cnt, 4), wall_us / max(nit, 1) / 4.0)
             for i in range(cnt):
                 it = nit - cnt + i
                 self._add_np_log("mmw_dual", it, np.array([Z, K, pt[i, 0]]))
                 self._add_np_log("mmw_loss", it, np.array([Z, K, pt[i, 1]]))
-                self._add_np_log("mmw_expm", it, np.array([Z, K, pt[i, 2]]))
+                self._add_np_log("mmw_expm", it, np.array([Z, K, pt[i, 2] + pt[i, 3]]))
                 self._add_np_log("mmw_per_it", it, np.array([Z, K, pt[i].sum()]))
 
             # final factor (mmw.py:202-216): top-r |lambda| eigenpairs of X_avgd / nit
             tic_xavg = self._get_tic()
+            if shard is not None:
+                shard.complete_averages()      # every rank now holds the whole running sum
             X_half = self._final_factor(solver, Z, nit, torch, dev, stream)
             self._add_np_log("mmw_xavg", 0, np.array([Z, K, self._get_tim(tic_xavg)]))
         return True, X_half

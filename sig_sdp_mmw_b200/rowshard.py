@@ -113,7 +113,29 @@ class RowShardRank:
         running kernel must not see a peer's epochs from before the reset)."""
         self.barrier()
         self.solver.reset(stream)
+        self._completed = False
         self.barrier()
+
+    def complete_averages(self):
+        """All-reduce (sum, in place on the device, NCCL) of the running sums X_avgd and Y_avgd: a
+        shard only ever writes the entries it owns, so afterwards every rank holds the complete
+        sums and can run the final factor (mmw.py:202-216) or the gap log on its own solver.
+        Once per solve: the foreign entries are no longer zero afterwards (reset() clears them)."""
+        from .sharded import _DevView
+        if getattr(self, "_completed", False):
+            raise _lib.SigSdpError("complete_averages was already called since the last reset")
+        self._completed = True
+        torch, dist = self.torch, self.dist
+        dev = torch.device("cuda", self.plan.device)
+        for which in (_lib.ARR_X_AVGD, _lib.ARR_Y_AVGD):
+            ptr, cnt = self.solver.device_array(which)
+            t = torch.as_tensor(_DevView(ptr, cnt), device=dev)
+            if dist.get_backend(self.group) == "nccl":
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            else:
+                h = t.cpu()
+                dist.all_reduce(h, op=dist.ReduceOp.SUM, group=self.group)
+                t.copy_(h)
 
     def _allsum(self, arrays):
         torch, dist = self.torch, self.dist
