@@ -295,7 +295,12 @@ class Solver:
         a1 = np.empty(count); mu = np.empty(count)
         check(load().sigsdp_solver_get_history(self.handle, count, _p(m, C.c_int32), _p(s, C.c_int32), _p(nt, C.c_int32),
                                                _p(a1, C.c_double), _p(mu, C.c_double)))
-        return dict(m_star=m, s=s, nterms=nt, a1norm=a1, mu=mu)
+        # scipy's _fragment_3_1 only uses the ||A||_1 rule while condition (3.13) holds,
+        # ||A||_1 <= 2 l p_max (p_max + 3) theta_55 / (55 n0) = 63.36 / D (_expm_multiply.py:519-531); beyond
+        # it the reference estimates ||A^p||_1^(1/p) with a randomised norm estimator and may pick a cheaper
+        # (m*, s).  The kernels always use the ||A||_1 rule (conservative: never fewer terms); `cond313`
+        # says, per iteration, whether both sides provably took the same branch.
+        return dict(m_star=m, s=s, nterms=nt, a1norm=a1, mu=mu, cond313=a1 <= 63.36 / self.D_total)
 
     def phase_times(self, count):
         t = np.empty((count, 4))

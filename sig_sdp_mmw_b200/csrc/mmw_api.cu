@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <tuple>
 #include <string>
 #include <vector>
@@ -109,6 +110,9 @@ struct sigsdp_plan {
     };
     mutable std::map<std::tuple<int, int, int>, TileCache> tiles;
     mutable DevArena tile_mem;
+    // the lazily built parts above (tile cache, conflict-counter data) are written through a const
+    // plan: solvers created / rounding calls made from several host threads take this lock
+    mutable std::mutex lazy_mu;
 };
 
 struct sigsdp_solver {
@@ -377,11 +381,18 @@ __global__ void k_lz_finish(const double* w, int n, const double* partn, int nbl
         if (threadIdx.x == 0) s_beta = sqrt(t);
     }
     __syncthreads();
-    const double beta = s_beta;
+    // breakdown: w vanished against its own scale (q_0..q_j span an invariant subspace, e.g. X_avgd = I
+    // after one iteration, or a component of a disconnected graph is exhausted).  Then beta_j = 0 and
+    // q_{j+1} = 0 are written instead of noise / NaN; every later step of the cycle then produces zeros
+    // as well, and the host, which sees the first zero beta, supplies a fresh direction and resumes.
+    const double a = *alpha;
+    const double prev = j > 0 ? be[j - 1] : 0.0;
+    const bool broke = !(s_beta > 1e-12 * fmax(fabs(a), prev));
+    const double beta = broke ? 0.0 : s_beta;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) qnext[i] = w[i] / beta;
+    if (i < n) qnext[i] = broke ? 0.0 : w[i] / beta;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        al[j] = *alpha;
+        al[j] = a;
         be[j] = beta;
     }
 }
@@ -764,6 +775,7 @@ static int solver_alloc(sigsdp_solver* s) {
     P.tl = TileDev{};
     s->smem = 0;
     s->RT = 0;
+    std::unique_lock<std::mutex> tile_lock(pl->lazy_mu);   // tile cache of the (shared) plan
     if (s->tiling != 0) {
         const size_t rowbytes = (size_t)s->Dp * sizeof(T);
         const size_t budget = 106 * 1024;
@@ -829,7 +841,9 @@ static int solver_alloc(sigsdp_solver* s) {
     }
     tm.lap("tiles build + upload");
     // ---- row shard: this rank's rows (whole tiles), halo masks, incident association edges
+    // (std::map never moves its nodes: the pointer stays valid after the lock is dropped)
     const HostTiles* htiles = s->RT > 0 ? &pl->tiles.at(std::make_tuple(s->RT, P.tl.ucap, P.tl.nnzcap)).h : nullptr;
+    tile_lock.unlock();
     {
         const int nr = s->nranks;
         // cut points: the boundary (tile start, or row when untiled) closest to r/nranks of the non-zeros
@@ -1713,13 +1727,15 @@ int sigsdp_round_project(const sigsdp_plan* plan, const double* gX_dev, int r, c
     CK(cudaSetDevice(plan->device));
     cudaStream_t st = (cudaStream_t)stream;
     const int n = (int)plan->h.n;
+    // scratch from the stream-ordered pool (no device-wide synchronisation, unlike cudaMalloc / cudaFree)
     double* inprod = nullptr;
-    CK(cudaMalloc(&inprod, (size_t)n * Z * sizeof(double)));
+    CK(cudaMallocAsync(&inprod, (size_t)n * Z * sizeof(double), st));
     const int blocks = plan->num_sms * 4;
     k_round_inprod<<<blocks, 256, 0, st>>>(gX_dev, n, r, randv_dev, Z, inprod, norm_dev);
     k_round_pref<<<blocks, 256, 0, st>>>(inprod, n, Z, pref_dev);
-    cudaError_t e = cudaStreamSynchronize(st);
-    cudaFree(inprod);
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(inprod, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return fail(SIGSDP_ECUDA, cudaGetErrorString(e));
     return SIGSDP_OK;
 }
@@ -1728,6 +1744,7 @@ int sigsdp_round_project(const sigsdp_plan* plan, const double* gX_dev, int r, c
 // S^T without its diagonal / explicit zeros, asso-UT edges and h_max in the caller's numbering
 // (rounding.py:56-60), built and uploaded when the conflict counter is first used
 static int ensure_conflict_data(const sigsdp_plan* pl) {
+    std::lock_guard<std::mutex> lock(pl->lazy_mu);
     if (pl->conflict_ready) return SIGSDP_OK;
     const int64_t n = pl->h.n;
     const int32_t* Sp = pl->hSp.data();
@@ -1770,15 +1787,15 @@ int sigsdp_round_conflicts(const sigsdp_plan* plan, const int32_t* z_dev, double
     }
     cudaStream_t st = (cudaStream_t)stream;
     unsigned long long* d_counts = nullptr;
-    CK(cudaMalloc(&d_counts, 2 * sizeof(unsigned long long)));
+    CK(cudaMallocAsync(&d_counts, 2 * sizeof(unsigned long long), st));
     CK(cudaMemsetAsync(d_counts, 0, 2 * sizeof(unsigned long long), st));
     k_round_conflicts<<<plan->num_sms * 4, 256, 0, st>>>((int)plan->h.n, plan->d_STp, plan->d_STi, plan->d_STx,
                                                          plan->d_hmax_caller, z_dev, (int)plan->h.E_a, plan->d_ai,
                                                          plan->d_aj, I_dev_or_null, d_counts);
     unsigned long long hcounts[2] = {0, 0};
     cudaError_t e = cudaMemcpyAsync(hcounts, d_counts, sizeof(hcounts), cudaMemcpyDeviceToHost, st);
+    cudaFreeAsync(d_counts, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cudaFree(d_counts);
     if (e != cudaSuccess) return fail(SIGSDP_ECUDA, cudaGetErrorString(e));
     counts_host[0] = (int64_t)hcounts[0];
     counts_host[1] = (int64_t)hcounts[1];

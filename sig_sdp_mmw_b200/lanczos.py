@@ -74,11 +74,14 @@ def thick_restart_lanczos(matmat, n, k, which, v0, ncv=None, tol=1e-12, max_rest
     matvecs = 0
     arrow = None
     theta_keep = None
-    def cycle(j0):
+    gen = torch.Generator(device="cpu").manual_seed(987654321)
+    breakdowns = 0
+
+    def steps(j0, j1):
         if native_steps is not None:
-            native_steps(Q, m, j0, m, al, be)
+            native_steps(Q, m, j0, j1, al, be)
             return
-        for j in range(j0, m):
+        for j in range(j0, j1):
             w = matmat(Q[j:j + 1])[0]
             h = torch.mv(Q, w)
             w = torch.addmv(w, Qt, h, alpha=-1.0)
@@ -86,8 +89,36 @@ def thick_restart_lanczos(matmat, n, k, which, v0, ncv=None, tol=1e-12, max_rest
             w = torch.addmv(w, Qt, h2, alpha=-1.0)
             al[j] = h[j] + h2[j]
             beta = torch.linalg.norm(w)
-            be[j] = beta
-            Q[j + 1] = w / beta
+            prev = be[j - 1] if j > 0 else torch.zeros((), dtype=torch.float64, device=dev)
+            ok = beta > 1e-12 * torch.maximum(al[j].abs(), prev)
+            be[j] = torch.where(ok, beta, torch.zeros_like(beta))
+            Q[j + 1] = torch.where(ok, w / beta, torch.zeros_like(w))
+
+    def cycle(j0):
+        """Lanczos steps j0 .. m-1.  A zero beta_j marks a breakdown (q_0..q_j span an invariant
+        subspace: X_avgd = I after one iteration, an exhausted component of a disconnected
+        graph): the steps after it produced zeros, so q_{j+1} is replaced by a fresh random
+        direction orthogonalised against the basis (beta_j stays 0: the projected matrix
+        decouples there) and the cycle resumes from j + 1."""
+        nonlocal breakdowns
+        steps(j0, m)
+        while True:
+            be_h = be.cpu().numpy()
+            brk = np.nonzero(be_h[j0:m] == 0.0)[0]
+            if brk.size == 0:
+                return
+            j = j0 + int(brk[0])
+            breakdowns += 1
+            if j + 1 >= m:
+                Q[m].zero_()
+                return
+            v = torch.randn(n, dtype=torch.float64, generator=gen).to(dev)
+            for _ in range(2):
+                v = torch.addmv(v, Qt[:, :j + 1], torch.mv(Q[:j + 1], v), alpha=-1.0)
+            Q[j + 1] = v / torch.linalg.norm(v)
+            Q[j + 2:].zero_()
+            j0 = j + 1
+            steps(j0, m)
 
     import time as _t
     t_cycle = t_host = 0.0
@@ -115,7 +146,8 @@ def thick_restart_lanczos(matmat, n, k, which, v0, ncv=None, tol=1e-12, max_rest
         beta_m = be_h[m - 1]
         resid = np.abs(beta_m * S[m - 1, want])
         scale = np.abs(theta).max()
-        if np.all(resid <= tol * scale):
+        converged = bool(np.all(resid <= tol * scale))
+        if converged:
             t_host += _t.perf_counter() - t0
             break
         # thick restart: keep the wanted Ritz vectors plus a buffer of the next best
@@ -137,6 +169,10 @@ def thick_restart_lanczos(matmat, n, k, which, v0, ncv=None, tol=1e-12, max_rest
     if which == "LM":
         o = torch.argsort(lam.abs())
         lam, V = lam[o], V[:, o]
-    return lam, V, dict(restarts=restart, matvecs=matvecs, dense=False,
+    if not converged:
+        import warnings
+        warnings.warn("thick-restart Lanczos stopped after %d restarts with residual %.3e > %.1e * %.3e: the returned "
+                      "eigenpairs are not converged" % (max_restarts, float(resid.max()), tol, float(scale)), RuntimeWarning)
+    return lam, V, dict(restarts=restart, matvecs=matvecs, dense=False, converged=converged, breakdowns=breakdowns,
                         resid=float(resid.max()), scale=float(scale), ncv=m, cycle_s=round(t_cycle, 4),
                         restart_s=round(t_host, 4), total_s=round(_t.perf_counter() - t_all, 4))

@@ -15,6 +15,31 @@ import numpy as np
 from . import _lib
 
 
+_weights = {}
+
+
+def _w(n):
+    """Fixed position weights for the checksums (cached per length)."""
+    w = _weights.get(n)
+    if w is None:
+        if len(_weights) > 8:
+            _weights.clear()
+        w = (np.arange(n, dtype=np.float64) % 8191.0) + 1.0
+        _weights[n] = w
+    return w
+
+
+def _digest_vec(v):
+    v = np.ascontiguousarray(v)
+    if v.size == 0:
+        return (0, 0.0)
+    return (int(v.size), float(np.dot(v.astype(np.float64, copy=False), _w(v.size))))
+
+
+def _digest(M):
+    return (int(M.nnz),) + _digest_vec(M.data)[1:] + _digest_vec(M.indices)[1:] + _digest_vec(M.indptr)[1:]
+
+
 class sdp_solver:
     def __init__(self, nit=100, rank_radio=2, alpha=1.):
         self.nit = nit
@@ -30,14 +55,23 @@ class sdp_solver:
 
     # ---- plan cache: the graph plan is Z-independent and reused across the binary search
     def _plan_for(self, state):
+        """The plan of `state`, rebuilt when the state's content changes.  The key is a position-
+        weighted checksum of every buffer (values AND structure: an in-place permutation of the
+        values, or a changed pattern with the same nnz, changes it), about 2 ms at 100k nodes
+        against a ~50 ms plan build; the keyed objects are kept alive so id() cannot be reused."""
         S, Q, h = state
-        key = (id(S), id(Q), S.shape, S.nnz, Q.nnz, float(S.data.sum()) if S.nnz else 0.0,
-               float(np.asarray(h).sum()), self.device, self.plan_order)
+        key = (id(S), id(Q), S.shape, self.device, self.plan_order) + _digest(S) + _digest(Q) + _digest_vec(np.asarray(h))
         cache = self.__dict__.setdefault("_plan_cache", {})
         if cache.get("key") != key:
             cache["plan"] = _lib.Plan(state, device=self.device, order=self.plan_order)
             cache["key"] = key
+            cache["objects"] = (S, Q, h)
         return cache["plan"]
+
+    def invalidate_plan(self):
+        """Forget the cached graph plan (call after changing a state in place in a way the checksum
+        cannot see, or to release its device memory)."""
+        self.__dict__.pop("_plan_cache", None)
 
     def rounding(self, Z, gX, state, nattempt=10):
         z_vec = None
@@ -125,3 +159,13 @@ class sdp_solver:
                                                 pref_d.data_ptr(), norm_d.data_ptr(),
                                                 torch.cuda.current_stream().cuda_stream))
             return pref_d[:, 0].cpu().numpy().astype(np.int64)
+
+
+class rand_sdp_solver(sdp_solver):
+    """The reference's random baseline (sdp_solver.py:109-114): unit-norm random rows instead of an
+    SDP factor, rounded by the same greedy pass.  The drivers use it as the "rand" arm."""
+
+    def run_with_state(self, bs_iteration, Z, state):
+        K = state[0].shape[0]
+        randv = np.random.randn(K, Z * self.rank_radio)
+        return True, randv / np.linalg.norm(randv, axis=1, keepdims=True)

@@ -60,11 +60,29 @@ class ShardedSolver:
     def iterate(self, n_iters, omega_dev=None, seed=0, stream=None):
         """omega_dev: optional torch tensor (n_iters, n, D_total) of raw normals, identical on
         every rank."""
-        for i in range(n_iters):
-            ptr = omega_dev[i].data_ptr() if omega_dev is not None else None
-            self.solver.split_step(True, ptr, seed, stream)
-            self.reduce_fn(self.buffer)
+        with self._on(stream) as st:
+            for i in range(n_iters):
+                ptr = omega_dev[i].data_ptr() if omega_dev is not None else None
+                self.solver.split_step(True, ptr, seed, st)
+                self.reduce_fn(self.buffer)
 
     def finish(self, stream=None):
         """Complete the last Gram; call before reading any state from self.solver."""
-        self.solver.split_step(False, None, 0, stream)
+        with self._on(stream) as st:
+            self.solver.split_step(False, None, 0, st)
+
+    def _on(self, stream):
+        """Kernel and collective must be ordered on ONE stream: the all-reduce runs on torch's
+        current stream, so a caller-supplied raw stream is made current for the duration."""
+        import contextlib
+        import torch
+
+        @contextlib.contextmanager
+        def ctx():
+            if stream is None or stream == torch.cuda.current_stream().cuda_stream:
+                yield torch.cuda.current_stream().cuda_stream
+            else:
+                ext = torch.cuda.ExternalStream(stream)
+                with torch.cuda.stream(ext):
+                    yield stream
+        return ctx()

@@ -267,6 +267,74 @@ def test_example_driver_runs(tmp_path):
     assert len(rows) == 8 and float(rows[2]) > 0
 
 
+def _example(name):
+    import importlib.util
+    path = os.path.join(os.path.dirname(GOLD), "..", "examples", name + ".py")
+    spec = importlib.util.spec_from_file_location("examples_" + name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod, path
+
+
+@pytest.mark.gpu
+def test_example_sim_all_bler_rows(tmp_path):
+    """sim_all_bler.py:33-47 mirrored: one CSV row `[g_it, it, Z_fin, *bler]` per arm and seed."""
+    import subprocess
+    import sys
+    _, path = _example("sim_all_bler")
+    out = subprocess.run([sys.executable, path, "--cells", "5", "--repeat", "2", "--out", str(tmp_path / "log")],
+                         capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-2000:]
+    for arm in ("mmw", "rand"):
+        lines = open(tmp_path / "log" / ("%s-5-75" % arm)).read().strip().splitlines()
+        assert len(lines) == 2
+        for seed, line in enumerate(lines):
+            row = [float(x) for x in line.split(",")]
+            assert row[0] == 0 and row[1] == seed and len(row) == 3 + 75       # 75 stations in a 5 x 5 cell grid
+            assert 2 <= row[2] <= 60 and all(0.0 <= b <= 1.0 for b in row[3:])
+    mm = [float(x) for x in open(tmp_path / "log" / "mmw-5-75").read().splitlines()[0].split(",")]
+    rr = [float(x) for x in open(tmp_path / "log" / "rand-5-75").read().splitlines()[0].split(",")]
+    assert np.mean(mm[3:]) <= np.mean(rr[3:]) + 1e-12      # the SDP colouring is no worse than random rows
+
+
+@pytest.mark.gpu
+def test_example_sim_all_mmw_gap_curves_match_reference(tmp_path):
+    """sim_all_mmw.py:46-53 mirrored: the (ub, lb) = gap[:, 3:5] curves of a LOG_GAP solve equal the
+    unmodified reference's on its own seed (fixture n75_z8), and the script writes them as two rows."""
+    import subprocess
+    import sys
+    mod, path = _example("sim_all_mmw")
+    g = load_case("n75_z8")
+    assert g["log_gap"]
+    np.random.seed(g["seed"])
+    ub, lb = mod.gap_curves(g["state"], g["Z"], g["eta"], g["nit"], g["rank_radio"])
+    np.testing.assert_allclose(ub, g["gap"][:, 0], rtol=1e-8)
+    np.testing.assert_allclose(lb, g["gap"][:, 1], rtol=1e-8, atol=1e-10)
+    out = subprocess.run([sys.executable, path, "--cells", "5", "--etas", "0.2", "--repeat", "1", "--Z", "8",
+                          "--out", str(tmp_path / "log")], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = open(tmp_path / "log" / "mmw-dual-5-75-20").read().strip().splitlines()
+    assert len(lines) == 2                                   # ub row, then lb row (same name, as the reference does)
+    rows = [[float(x) for x in ln.split(",")] for ln in lines]
+    assert all(len(r) == 2 + 25 for r in rows)               # nit = ceil(1 / 0.2^2) = 25 values per curve
+    assert all(u >= l - 1e-9 for u, l in zip(rows[0][2:], rows[1][2:]))   # upper curve above the lower one
+
+
+@pytest.mark.gpu
+def test_example_sim_mmw_scs_iter_time_rows(tmp_path):
+    """sim_mmw_scs_iter_time.py:36-70 mirrored (MMW and force_full_bound arms)."""
+    import subprocess
+    import sys
+    _, path = _example("sim_mmw_scs_iter_time")
+    out = subprocess.run([sys.executable, path, "--cells", "5", "--repeat", "1", "--out", str(tmp_path / "log")],
+                         capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-2000:]
+    row = open(tmp_path / "log" / "time-5-75").read().strip().split(",")
+    assert len(row) == 8
+    d_mmw, t_mmw, d_nb, t_nb = float(row[2]), float(row[3]), float(row[6]), float(row[7])
+    assert 1 <= d_mmw <= d_nb and t_mmw > 0 and t_nb > 0     # the 1..K search needs at least as many probes
+
+
 @pytest.mark.gpu
 def test_run_many_with_states_equals_single_runs():
     """The batched drop-in call gives, instance by instance, the factor a standalone solver

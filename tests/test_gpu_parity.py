@@ -333,6 +333,76 @@ def test_lanczos_path_equals_dense_path():
     assert abs(M - ref).max() < 1e-14
 
 
+def _mm_of(sol):
+    def mm(X):
+        X = X.contiguous()
+        Y = torch.empty_like(X)
+        sol.symv(X.data_ptr(), Y.data_ptr(), X.shape[0], None)
+        return Y
+    return mm
+
+
+def test_lanczos_breakdown_identity_matrix():
+    """nit = 1: X_avgd = X_0 = I (mmw.py:67,77), every Krylov space is invariant after one step
+    (beta = 0).  The solver must return finite orthonormal eigenvectors with eigenvalue 1 instead
+    of NaN -- natively and through the torch steps."""
+    from sig_sdp_mmw_b200.lanczos import thick_restart_lanczos
+    g = load_case("n300_z10")
+    _, sol, _ = _run_device(g, 1)
+    sol.xavg_matrix(1.0)
+    n, dev = sol.plan.n, torch.device("cuda", 0)
+    v0 = torch.randn(n, dtype=torch.float64, device=dev)
+    for native in (mmw._native_steps(sol, torch), None):
+        lam, V, info = thick_restart_lanczos(_mm_of(sol), n, 18, "LM", v0, ncv=40, native_steps=native)
+        assert not info["dense"] and info["converged"] and info["breakdowns"] > 0
+        assert torch.isfinite(V).all() and torch.isfinite(lam).all()
+        np.testing.assert_allclose(lam.cpu().numpy(), 1.0, rtol=1e-12)
+        assert float((V.T @ V - torch.eye(18, dtype=torch.float64, device=dev)).abs().max()) < 1e-10
+    # and the drop-in object end to end
+    alg = mmw(nit=1, eta=g["eta"], rank_radio=g["rank_radio"])
+    np.random.seed(0)
+    ok, X_half = alg.run_with_state(0, g["Z"], g["state"])
+    assert ok and np.isfinite(X_half).all()
+    np.testing.assert_allclose(X_half.T @ X_half, np.eye(X_half.shape[1]), atol=1e-10)
+
+
+def test_lanczos_on_disconnected_graph_matches_dense():
+    """Two graphs side by side (block-diagonal state): a Krylov space started inside one component
+    never leaves it; the factor must still equal the dense eigen-decomposition of X_avgd / nit."""
+    from sig_sdp_mmw_b200.lanczos import eig_dense, thick_restart_lanczos
+    _require_gpu()
+    a, b = load_case("n75_z8"), load_case("n300_z10")
+    S = sp.block_diag([a["state"][0], b["state"][0]], format="csr")
+    Q = sp.block_diag([a["state"][1], b["state"][1]], format="csr")
+    h = np.concatenate([a["state"][2], b["state"][2]])
+    state = (S, Q, h)
+    Z, rr, nit = 8, 2, 12
+    n = S.shape[0]
+    om = np.random.RandomState(5).randn(nit, n, Z * rr)
+    plan = _lib.Plan(state, device=0, order=1)
+    sol = _lib.Solver(plan, Z, Z * rr, 0.04)
+    om_d = torch.from_numpy(om).cuda()
+    sol.iterate(nit, om_d.data_ptr(), 0, None)
+    torch.cuda.synchronize()
+    st = orc.MMWState(orc.build_problem(Z, state), 0.04)
+    for i in range(nit):
+        st.step(om[i])
+    np.testing.assert_allclose(sol.dual()[0], st.Y, rtol=RTOL64)
+    sol.xavg_matrix(1.0 / nit)
+    dev = torch.device("cuda", 0)
+    k = 14
+    lam_d, V_d = eig_dense(_mm_of(sol), n, k, "LM", dev)
+    # a start vector supported on the small component only: its Krylov space breaks down after 75 steps
+    v0 = torch.zeros(n, dtype=torch.float64, device=dev)
+    iperm = np.argsort(plan.perm())
+    v0[torch.from_numpy(iperm[:75]).to(dev)] = torch.randn(75, dtype=torch.float64, device=dev)
+    lam_l, V_l, info = thick_restart_lanczos(_mm_of(sol), n, k, "LM", v0, ncv=90, tol=1e-11,
+                                            native_steps=mmw._native_steps(sol, torch))
+    assert info["converged"] and info["breakdowns"] >= 1 and torch.isfinite(V_l).all()
+    np.testing.assert_allclose(lam_l.cpu().numpy(), lam_d.cpu().numpy(), rtol=1e-10)
+    assert float((Gd_ref(V_d, lam_d) - Gd_ref(V_l, lam_l)).abs().max()) < 1e-8
+
+
 # --------------------------------------------------- size-independent properties
 def test_properties_at_5k_nodes():
     """cfg2-sized graph (5,000 nodes): invariants that need no oracle run."""
