@@ -18,3 +18,15 @@ for rep in range(2):
     ok, X_half = alg.run_with_state(0, Z, state)
     t1 = time.perf_counter()
     print(f"e2e {1e3 * (t1 - t0):.1f} ms; eig info {alg.last_eig_info}", file=sys.stderr)
+
+# Python-side laps of the set-up (what LOGGED_NP_DATA["mmw_state_process"] covers)
+from sig_sdp_mmw_b200 import _lib
+from sig_sdp_mmw_b200 import sdp_solver as _sd
+import importlib
+_sdm = importlib.import_module("sig_sdp_mmw_b200.sdp_solver")
+for rep in range(2):
+    t0 = time.perf_counter(); _sdm._digest(state[0]); _sdm._digest(state[1]); _sdm._digest_vec(state[2]); t1 = time.perf_counter()
+    plan = _lib.Plan(state, device=0, order=1); t2 = time.perf_counter()
+    sol = _lib.Solver(plan, Z, Z * rr, bench.ETA, _lib.F64 if dtype == "float64" else _lib.F32); t3 = time.perf_counter()
+    print(f"python laps: digest {1e3*(t1-t0):.1f} ms, Plan() {1e3*(t2-t1):.1f} ms, Solver() {1e3*(t3-t2):.1f} ms", file=sys.stderr)
+    del sol, plan

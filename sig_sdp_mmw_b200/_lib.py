@@ -102,12 +102,16 @@ def check(rc):
         raise SigSdpError("libsigsdp_mmw error %d: %s" % (rc, load().sigsdp_last_error().decode()))
 
 
-def csr_arrays(M):
+def csr_arrays(M, canonicalize=True):
     """(indptr int32, indices int32, data float64) of a scipy matrix as canonical CSR
-    (sorted, duplicates summed) without touching the caller's object."""
+    (sorted, duplicates summed) without touching the caller's object.  canonicalize=False skips
+    scipy's O(nnz) sortedness scan: the library validates the structure itself and reports
+    unsorted / duplicate indices, upon which the caller retries with canonicalize=True."""
     import scipy.sparse as sp
-    M = sp.csr_matrix(M, copy=False)
-    if not M.has_canonical_format:
+    if not (sp.isspmatrix_csr(M) or isinstance(M, getattr(sp, "csr_array", ()))):
+        M = sp.csr_matrix(M)
+        canonicalize = True
+    if canonicalize and not M.has_canonical_format:
         M = M.copy()
         M.sum_duplicates()
     return (np.ascontiguousarray(M.indptr, dtype=np.int32), np.ascontiguousarray(M.indices, dtype=np.int32),
@@ -123,13 +127,17 @@ class Plan:
         n = S.shape[0]
         if S.shape != (n, n) or Q.shape != (n, n) or np.asarray(h).shape != (n,):
             raise ValueError("state must be (S_gain n x n, Q_asso n x n, h_max (n,))")
-        self._S = csr_arrays(S)
-        self._Q = csr_arrays(Q)
         self._h = np.ascontiguousarray(np.asarray(h, dtype=np.float64))
         self.handle = C.c_void_p()
-        check(lib.sigsdp_plan_create(n, _p(self._S[0], C.c_int32), _p(self._S[1], C.c_int32), _p(self._S[2], C.c_double),
-                                     _p(self._Q[0], C.c_int32), _p(self._Q[1], C.c_int32), _p(self._Q[2], C.c_double),
-                                     _p(self._h, C.c_double), device, order, C.byref(self.handle)))
+        for canonicalize in (False, True):
+            self._S = csr_arrays(S, canonicalize)
+            self._Q = csr_arrays(Q, canonicalize)
+            rc = lib.sigsdp_plan_create(n, _p(self._S[0], C.c_int32), _p(self._S[1], C.c_int32), _p(self._S[2], C.c_double),
+                                        _p(self._Q[0], C.c_int32), _p(self._Q[1], C.c_int32), _p(self._Q[2], C.c_double),
+                                        _p(self._h, C.c_double), device, order, C.byref(self.handle))
+            if rc == 0 or canonicalize or b"sorted and duplicate-free" not in lib.sigsdp_last_error():
+                break      # (non-canonical input: second pass on a canonicalised copy)
+        check(rc)
         info = (C.c_int64 * 8)()
         check(lib.sigsdp_plan_info(self.handle, info))
         self.n, self.E_g, self.E_a, self.nnz, self.nnzT, self.device, self.order, self.max_row = [int(x) for x in info]

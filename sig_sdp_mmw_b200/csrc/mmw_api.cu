@@ -100,8 +100,8 @@ struct sigsdp_plan {
     mutable double* d_hmax_caller = nullptr;
     // host copy of S / h_max (caller numbering) so that data is only built when the conflict
     // counter is first used (it is not needed by the solve)
-    std::vector<int32_t> hSp, hSi;
-    std::vector<double> hSx, hh;
+    hvec<int32_t> hSp, hSi;
+    hvec<double> hSx, hh;
     mutable bool conflict_ready = false;
     // row tiles per (max_rows, ucap, nnzcap), built on first use (see TileDev)
     struct TileCache {
@@ -597,36 +597,68 @@ int sigsdp_plan_create(int64_t n, const int32_t* Sp, const int32_t* Si, const do
     d.nnz = (int)h.nnz;
     d.E_g = (int)h.E_g;
     d.E_a = (int)h.E_a;
-    int *rowptr, *col, *eid, *perm = nullptr, *dpos, *apos;
-    double *tfwd, *tbwd, *S_sum, *tnorm, *hm;
-    if ((e = pl->mem.upload(&rowptr, h.rowptr)) != cudaSuccess) return bail(e, "upload rowptr");
-    if ((e = pl->mem.upload(&col, h.col)) != cudaSuccess) return bail(e, "upload col");
-    if ((e = pl->mem.upload(&eid, h.eid)) != cudaSuccess) return bail(e, "upload eid");
-    if ((e = pl->mem.upload(&tfwd, h.tfwd)) != cudaSuccess) return bail(e, "upload tfwd");
-    if ((e = pl->mem.upload(&tbwd, h.tbwd)) != cudaSuccess) return bail(e, "upload tbwd");
-    if ((e = pl->mem.upload(&S_sum, h.S_sum)) != cudaSuccess) return bail(e, "upload S_sum");
-    if ((e = pl->mem.upload(&tnorm, h.tnorm)) != cudaSuccess) return bail(e, "upload tnorm");
-    if ((e = pl->mem.upload(&hm, h.h_max)) != cudaSuccess) return bail(e, "upload h_max");
-    if (h.order != 0 && (e = pl->mem.upload(&perm, h.perm)) != cudaSuccess) return bail(e, "upload perm");
-    if ((e = pl->mem.upload(&dpos, h.dpos)) != cudaSuccess) return bail(e, "upload dpos");
-    if ((e = pl->mem.upload(&apos, h.apos)) != cudaSuccess) return bail(e, "upload apos");
-    d.dpos = dpos;
-    d.apos = apos;
-    d.rowptr = rowptr;
-    d.col = col;
-    d.eid = eid;
-    d.tfwd = tfwd;
-    d.tbwd = tbwd;
-    d.S_sum = S_sum;
-    d.tnorm = tnorm;
-    d.h_max = hm;
-    d.perm = perm;
+    // All plan arrays travel as ONE slab: staged into a process-wide pinned buffer by all host cores
+    // (next to the host copies of S / h_max the conflict counter needs later) and moved by one DMA
+    // copy, instead of eleven pageable cudaMemcpy calls fed by one thread (9 + 3 ms -> ~3 ms at 100k
+    // nodes).  The pinned buffer is kept (and grown on demand) for the next plan of this process.
+    struct Arr { const void* src; size_t bytes; size_t off; };
+    std::vector<Arr> arrs;
+    size_t total = 0;
+    auto add = [&](const void* src, size_t bytes) {
+        arrs.push_back(Arr{src, bytes, total});
+        total += (bytes + 255) & ~(size_t)255;
+        return arrs.size() - 1;
+    };
+    const size_t i_rowptr = add(h.rowptr.data(), h.rowptr.size() * 4), i_col = add(h.col.data(), h.col.size() * 4);
+    const size_t i_eid = add(h.eid.data(), h.eid.size() * 4), i_tfwd = add(h.tfwd.data(), h.tfwd.size() * 8);
+    const size_t i_tbwd = add(h.tbwd.data(), h.tbwd.size() * 8), i_ssum = add(h.S_sum.data(), h.S_sum.size() * 8);
+    const size_t i_tnorm = add(h.tnorm.data(), h.tnorm.size() * 8), i_hm = add(h.h_max.data(), h.h_max.size() * 8);
+    const size_t i_perm = add(h.perm.data(), h.order != 0 ? h.perm.size() * 4 : 0);
+    const size_t i_dpos = add(h.dpos.data(), h.dpos.size() * 4), i_apos = add(h.apos.data(), h.apos.size() * 4);
+    char* slab = nullptr;
+    if ((e = pl->mem.alloc(&slab, total)) != cudaSuccess) return bail(e, "plan slab");
+    {
+        static std::mutex stage_mu;
+        static char* stage = nullptr;
+        static size_t stage_cap = 0;
+        std::lock_guard<std::mutex> lock(stage_mu);
+        if (stage_cap < total) {
+            if (stage) cudaFreeHost(stage);
+            stage = nullptr;
+            stage_cap = 0;
+            const size_t want = total + total / 4;
+            if ((e = cudaHostAlloc((void**)&stage, want, cudaHostAllocDefault)) != cudaSuccess) return bail(e, "pinned staging buffer");
+            stage_cap = want;
+        }
+        pl->hSp.resize(n + 1);
+        pl->hSi.resize(Sp[n]);
+        pl->hSx.resize(Sp[n]);
+        pl->hh.resize(n);
+        std::vector<CopySeg> segs;
+        for (const Arr& a : arrs)
+            if (a.bytes) segs.push_back(CopySeg{stage + a.off, a.src, a.bytes});
+        segs.push_back(CopySeg{pl->hSp.data(), Sp, (size_t)(n + 1) * 4});
+        segs.push_back(CopySeg{pl->hSi.data(), Si, (size_t)Sp[n] * 4});
+        segs.push_back(CopySeg{pl->hSx.data(), Sx, (size_t)Sp[n] * 8});
+        segs.push_back(CopySeg{pl->hh.data(), h_max, (size_t)n * 8});
+        parallel_copy(segs);
+        tm.lap("stage + host copies");
+        if ((e = cudaMemcpyAsync(slab, stage, total, cudaMemcpyHostToDevice, (cudaStream_t)0)) != cudaSuccess) return bail(e, "plan upload");
+        if ((e = cudaStreamSynchronize((cudaStream_t)0)) != cudaSuccess) return bail(e, "plan upload");
+    }
+    auto at = [&](size_t i) { return slab + arrs[i].off; };
+    d.rowptr = reinterpret_cast<const int*>(at(i_rowptr));
+    d.col = reinterpret_cast<const int*>(at(i_col));
+    d.eid = reinterpret_cast<const int*>(at(i_eid));
+    d.tfwd = reinterpret_cast<const double*>(at(i_tfwd));
+    d.tbwd = reinterpret_cast<const double*>(at(i_tbwd));
+    d.S_sum = reinterpret_cast<const double*>(at(i_ssum));
+    d.tnorm = reinterpret_cast<const double*>(at(i_tnorm));
+    d.h_max = reinterpret_cast<const double*>(at(i_hm));
+    d.perm = h.order != 0 ? reinterpret_cast<const int*>(at(i_perm)) : nullptr;
+    d.dpos = reinterpret_cast<const int*>(at(i_dpos));
+    d.apos = reinterpret_cast<const int*>(at(i_apos));
     tm.lap("plan upload");
-    pl->hSp.assign(Sp, Sp + n + 1);
-    pl->hSi.assign(Si, Si + Sp[n]);
-    pl->hSx.assign(Sx, Sx + Sp[n]);
-    pl->hh.assign(h_max, h_max + n);
-    tm.lap("host copies");
     *out = pl;
     return SIGSDP_OK;
 }
@@ -803,6 +835,7 @@ static int solver_alloc(sigsdp_solver* s) {
             if (it == pl->tiles.end()) {
                 sigsdp_plan::TileCache tc;
                 build_tiles(h, max_rows, ucap, nnzcap, tc.h);
+                tm.lap("tiles build");
                 tc.d = TileDev{};
                 tc.d.ntiles = tc.h.ntiles;
                 tc.d.ucap = ucap;
@@ -927,10 +960,26 @@ static int solver_alloc(sigsdp_solver* s) {
         P.sh.n_inc = s->n_inc;
         P.sh.n_inc_owned = s->n_inc_owned;
     }
+    tm.lap("shard partition");
     // launch geometry: persistent grid, one tile per block iteration
     int occ = 0;
-    CK(kset_of(s->dtype, s->G).prepare(s->smem, s->nranks > 1, &occ));
+    {
+        // the kernels' shared-memory opt-in and occupancy depend on (device, dtype, G, smem, variant)
+        // only: asked once per process (six runtime calls, ~2.5 ms, otherwise paid by every solver)
+        static std::mutex mu;
+        static std::map<std::tuple<int, int, int, size_t, int>, int> cache;
+        std::lock_guard<std::mutex> lock(mu);
+        const auto key = std::make_tuple(pl->device, s->dtype, s->G, s->smem, s->nranks > 1 ? 1 : 0);
+        auto it = cache.find(key);
+        if (it == cache.end()) {
+            CK(kset_of(s->dtype, s->G).prepare(s->smem, s->nranks > 1, &occ));
+            cache[key] = occ;
+        } else {
+            occ = it->second;
+        }
+    }
     if (occ < 1) return fail(SIGSDP_ECUDA, "fused kernel does not fit on an SM");
+    tm.lap("occupancy");
     int64_t tiles = s->RT > 0 ? (s->tile_hi - s->tile_lo) : (s->row_hi - s->row_lo + R - 1) / R;
     int64_t blocks = (int64_t)pl->num_sms * occ;
     if (s->max_blocks > 0 && blocks > s->max_blocks) blocks = s->max_blocks;
@@ -950,10 +999,11 @@ static int solver_alloc(sigsdp_solver* s) {
         bool fits = true;
         for (int t = 0; t < nt && fits; ++t) fits = ht.trow[t + 1] - ht.trow[t] <= Rs;
         if (fits) {
-            std::vector<int32_t> slots((size_t)nt * Rs * 4);
+            hvec<int32_t> slots((size_t)nt * Rs * 4);
+            parallel_for(nt, [&](int64_t t0, int64_t t1) {
             std::vector<int> idx;
             std::vector<uint8_t> split;
-            for (int t = 0; t < nt; ++t) {
+            for (int t = (int)t0; t < (int)t1; ++t) {
                 const int r0 = ht.trow[t], r1 = ht.trow[t + 1], nr = r1 - r0;
                 int32_t* sl = slots.data() + (size_t)t * Rs * 4;
                 for (int g2 = 0; g2 < Rs; ++g2) {
@@ -986,12 +1036,14 @@ static int solver_alloc(sigsdp_solver* s) {
                     ++pos;
                 }
             }
+            }, 256);
             int32_t* d_slots = nullptr;
             CK(s->mem.upload(&d_slots, slots));
             P.tl.slots = reinterpret_cast<const int4*>(d_slots);
             P.tl.slot_r = Rs;
         }
     }
+    tm.lap("slot table");
     return SIGSDP_OK;
 }
 }  // extern "C++"
@@ -1090,8 +1142,10 @@ static int solver_create_common(const sigsdp_plan* plan, int Z, int D_total, int
     s->G = lanes <= 4 ? 4 : lanes <= 8 ? 8 : lanes <= 16 ? 16 : 32;
     s->C = (int)(plan->h.E_a + 2 * plan->h.n);
     int rc = dtype == SIGSDP_F64 ? solver_alloc<double>(s) : solver_alloc<float>(s);
+    ApiTimer tm;
     if (rc == SIGSDP_OK) rc = dtype == SIGSDP_F64 ? solver_reset_impl<double>(s, 0) : solver_reset_impl<float>(s, 0);
     if (rc == SIGSDP_OK && cudaDeviceSynchronize() != cudaSuccess) rc = fail(SIGSDP_ECUDA, "solver initialisation failed");
+    tm.lap("solver reset");
     if (rc != SIGSDP_OK) {
         std::string keep = g_err;
         s->mem.release();

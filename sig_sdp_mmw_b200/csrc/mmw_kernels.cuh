@@ -133,12 +133,21 @@ struct Launchers {
     static const Prob<T>& prob(const void* p) { return *static_cast<const Prob<T>*>(p); }
     static cudaError_t prepare(size_t smem, int shard, int* occ) {
         cudaError_t e = cudaSuccess;
-        if (smem > 48 * 1024) {
-            if ((e = cudaFuncSetAttribute(k_fused<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
-            if ((e = cudaFuncSetAttribute(k_fused_rows<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
-            if ((e = cudaFuncSetAttribute(k_term<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
-            if ((e = cudaFuncSetAttribute(k_gram<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
-            if ((e = cudaFuncSetAttribute(k_batch<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
+        // the staged kernels are opted in to the device's whole shared memory once per device (a
+        // per-solver limit would break an older solver with larger tiles on its next launch)
+        static bool opted[64] = {false};
+        int dev = 0;
+        if ((e = cudaGetDevice(&dev))) return e;
+        if (dev >= 0 && dev < 64 && !opted[dev]) {
+            int optin = 0;
+            if ((e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev))) return e;
+            optin -= 4096;   // room for the kernels' static shared memory (reduction scratch, barrier words)
+            if ((e = cudaFuncSetAttribute(k_fused<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin))) return e;
+            if ((e = cudaFuncSetAttribute(k_fused_rows<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin))) return e;
+            if ((e = cudaFuncSetAttribute(k_term<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin))) return e;
+            if ((e = cudaFuncSetAttribute(k_gram<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin))) return e;
+            if ((e = cudaFuncSetAttribute(k_batch<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin))) return e;
+            opted[dev] = true;
         }
         if (shard) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_fused_rows<T, G>, NT, smem);
         return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_fused<T, G>, NT, smem);

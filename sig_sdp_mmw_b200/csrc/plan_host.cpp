@@ -10,6 +10,8 @@
 #include <cstdio>
 #include <chrono>
 #include <cstdlib>
+#include <cstring>
+#include <functional>
 #include <numeric>
 #include <queue>
 #include <thread>
@@ -18,6 +20,17 @@
 
 namespace sigsdp {
 namespace {
+struct StageTimer {
+    bool on = getenv("SIGSDP_PLAN_TIMING") != nullptr;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    void lap(const char* what) {
+        if (!on) return;
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[plan] %-24s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 
 // first problem of rows [r0, r1) of a CSR structure, or nullptr
 const char* check_csr_rows(int64_t n, const int32_t* p, const int32_t* idx, int64_t r0, int64_t r1) {
@@ -57,10 +70,12 @@ unsigned host_threads() {
     return std::max(1u, std::min(nt, 32u));
 }
 
+std::atomic<int> g_side_threads{0};   // sequential helper threads running next to the parallel stages
+
 template <class F>
-void parallel_rows(int64_t n, F fn) {
-    const unsigned nt = host_threads();
-    if (n < 4096 || nt == 1) {
+void parallel_rows(int64_t n, F fn, int64_t min_parallel = 4096) {
+    const unsigned nt = (unsigned)std::max(1, (int)host_threads() - g_side_threads.load());
+    if (n < min_parallel || nt == 1) {
         fn(0, n);
         return;
     }
@@ -76,38 +91,54 @@ void parallel_rows(int64_t n, F fn) {
 
 // Clustered BFS ordering: grow clusters of ~cluster nodes breadth-first, visiting the
 // graph cluster by cluster so that the rows of one CTA tile are a compact patch of
-// the (geometric) interference graph and share their neighbours.
-void locality_order(const HostPlan& P, int cluster, std::vector<int32_t>& perm) {
-    const int64_t n = P.n;
+// the (geometric) interference graph and share their neighbours.  It walks the INPUTS (row u of
+// S_gain and of Q_asso: every pair of the union pattern is in the row of at least one of its two
+// ends), so it can start right after validation and run on its own thread while the other
+// cores build T and the union pattern; the tiles it gives are as compact as those of a walk over
+// the symmetric pattern (cfg4: 414.8k staged rows / 39.1k copy runs against 421.6k / 41.3k).
+void locality_order_inputs(int64_t n, const int32_t* Sp, const int32_t* Si, const int32_t* Qp, const int32_t* Qi,
+                           int cluster, std::vector<int32_t>& perm) {
     perm.clear();
     perm.reserve(n);
     std::vector<uint8_t> seen(n, 0);
     std::vector<int32_t> frontier;  // nodes adjacent to finished clusters, FIFO
+    frontier.reserve(n);
     size_t fhead = 0;
     std::vector<int32_t> q;
+    q.reserve(cluster + 8);
+    auto visit = [&](int32_t v) {
+        if (seen[v]) return;
+        if ((int)q.size() < cluster) {
+            seen[v] = 1;
+            q.push_back(v);
+            __builtin_prefetch(Sp + v);   // its row pointers now, its rows when it is two pops away:
+            __builtin_prefetch(Qp + v);   // the walk is bound by the latency of these scattered reads
+        } else {
+            frontier.push_back(v);
+        }
+    };
     for (int64_t start = 0; start < n; ++start) {
         if (seen[start]) continue;
         frontier.push_back((int32_t)start);
         while (fhead < frontier.size()) {
-            int32_t seed = frontier[fhead++];
+            const int32_t seed = frontier[fhead++];
             if (seen[seed]) continue;
-            // BFS from seed limited to `cluster` nodes
             q.clear();
             q.push_back(seed);
             seen[seed] = 1;
             size_t qh = 0;
             while (qh < q.size()) {
-                int32_t u = q[qh++];
-                for (int32_t e = P.rowptr[u]; e < P.rowptr[u + 1]; ++e) {
-                    int32_t v = P.col[e];
-                    if (seen[v]) continue;
-                    if ((int)q.size() < cluster) {
-                        seen[v] = 1;
-                        q.push_back(v);
-                    } else {
-                        frontier.push_back(v);
-                    }
+                const int32_t u = q[qh++];
+                if (qh + 1 < q.size()) {
+                    const int32_t u2 = q[qh + 1];
+                    __builtin_prefetch(Si + Sp[u2]);
+                    __builtin_prefetch(Si + Sp[u2] + 16);
+                    __builtin_prefetch(Qi + Qp[u2]);
                 }
+                // (stored zeros are walked like any entry: this is an ordering heuristic, and not
+                // touching the value arrays halves the memory traffic of the one sequential stage)
+                for (int32_t e = Sp[u]; e < Sp[u + 1]; ++e) visit(Si[e]);
+                for (int32_t e = Qp[u]; e < Qp[u + 1]; ++e) visit(Qi[e]);
             }
             for (int32_t u : q) perm.push_back(u);
         }
@@ -116,18 +147,30 @@ void locality_order(const HostPlan& P, int cluster, std::vector<int32_t>& perm) 
 
 }  // namespace
 
-namespace {
-struct StageTimer {
-    bool on = getenv("SIGSDP_PLAN_TIMING") != nullptr;
-    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
-    void lap(const char* what) {
-        if (!on) return;
-        auto t1 = std::chrono::steady_clock::now();
-        fprintf(stderr, "[plan] %-24s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
-        t0 = t1;
+
+void parallel_for(int64_t n, const std::function<void(int64_t, int64_t)>& fn, int64_t min_parallel) {
+    parallel_rows(n, fn, min_parallel);
+}
+
+void parallel_copy(const std::vector<CopySeg>& segs) {
+    constexpr size_t CH = (size_t)1 << 20;
+    std::vector<CopySeg> tasks;
+    for (const CopySeg& s : segs)
+        for (size_t o = 0; o < s.bytes; o += CH)
+            tasks.push_back(CopySeg{static_cast<char*>(s.dst) + o, static_cast<const char*>(s.src) + o, std::min(CH, s.bytes - o)});
+    const unsigned nt = std::min<unsigned>(host_threads(), (unsigned)std::max<size_t>(1, tasks.size()));
+    if (nt <= 1) {
+        for (const CopySeg& t : tasks) std::memcpy(t.dst, t.src, t.bytes);
+        return;
     }
-};
-}  // namespace
+    std::atomic<size_t> next{0};
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; ++t)
+        th.emplace_back([&] {
+            for (size_t i = next.fetch_add(1); i < tasks.size(); i = next.fetch_add(1)) std::memcpy(tasks[i].dst, tasks[i].src, tasks[i].bytes);
+        });
+    for (auto& x : th) x.join();
+}
 
 int build_host_plan(int64_t n, const int32_t* Sp, const int32_t* Si, const double* Sx,
                     const int32_t* Qp, const int32_t* Qi, const double* Qx, const double* h_max,
@@ -203,6 +246,24 @@ int build_host_plan(int64_t n, const int32_t* Sp, const int32_t* Si, const doubl
     P.order = order;
 
     tm.lap("validate");
+    // The locality ordering is the one sequential stage (~14 ms at 100k nodes): it only needs the
+    // inputs, so it runs on its own thread (the parallel stages leave it a core) while the other
+    // cores build T, the union pattern and the edge ids; it is joined in front of the renumbering.
+    std::vector<int32_t> bfs_perm;
+    std::thread bfs_thread;
+    if (order != 0) {
+        g_side_threads.fetch_add(1);
+        bfs_thread = std::thread([&, n] {
+            StageTimer bt;
+            locality_order_inputs(n, Sp, Si, Qp, Qi, order > 1 ? order : 64, bfs_perm);
+            g_side_threads.fetch_sub(1);
+            bt.lap("  (clustered BFS thread)");
+        });
+    }
+    struct Joiner {   // every early return below must not leave the thread running on dead locals
+        std::thread& t;
+        ~Joiner() { if (t.joinable()) t.join(); }
+    } bfs_joiner{bfs_thread};
     // ---- T = S^T with association pairs and the diagonal zeroed (mmw.py:28-33)
     std::vector<int32_t> Tp(n + 1, 0);
     hvec<int32_t> Ti;
@@ -212,7 +273,23 @@ int build_host_plan(int64_t n, const int32_t* Sp, const int32_t* Si, const doubl
         // S entry (j, i) becomes T[i][j] unless i == j, the value is zero, or Q[i][j] != 0.
         // Q is symmetric (checked above), so Q[i][j] != 0 <=> Q[j][i] != 0: merge S row j with
         // Q row j (both sorted) instead of searching Q row i.
-        parallel_rows(n, [&](int64_t j0, int64_t j1) {
+        // Transpose = counting sort with one histogram per thread: thread t owns the S rows
+        // [j0_t, j1_t); its entries of T row i go behind those of the threads before it, so every
+        // T row comes out sorted by column whatever the thread count.
+        const unsigned nt = (unsigned)std::max(1, (int)host_threads() - g_side_threads.load());
+        const unsigned nth = n < 4096 ? 1u : nt;
+        const int64_t chunk = (n + nth - 1) / nth;
+        std::vector<std::vector<int32_t>> cnt(nth);
+        auto run_threads = [&](auto fn) {
+            if (nth == 1) { fn(0u); return; }
+            std::vector<std::thread> th;
+            for (unsigned t = 0; t < nth; ++t) th.emplace_back([=] { fn(t); });
+            for (auto& x : th) x.join();
+        };
+        run_threads([&](unsigned t) {
+            std::vector<int32_t>& c = cnt[t];
+            c.assign(n, 0);
+            const int64_t j0 = t * chunk, j1 = std::min<int64_t>(n, j0 + chunk);
             for (int64_t j = j0; j < j1; ++j) {
                 int32_t qq = Qp[j];
                 const int32_t qe = Qp[j + 1];
@@ -222,43 +299,41 @@ int build_host_plan(int64_t n, const int32_t* Sp, const int32_t* Si, const doubl
                     while (qq < qe && Qi[qq] < i) ++qq;
                     if (qq < qe && Qi[qq] == i && Qx[qq] != 0.0) continue;
                     keep[q] = 1;
+                    c[i]++;
                 }
             }
         });
-        // Transpose without scattered writes from one thread: each thread owns a range of T rows
-        // [i0, i1) and walks every S row j (ascending, so T rows come out sorted), binary-searching
-        // the part of the row that falls into its range.  Pass 0 counts, pass 1 fills.
-        for (int pass = 0; pass < 2; ++pass) {
-            if (pass == 1) {
-                for (int64_t i = 0; i < n; ++i) Tp[i + 1] += Tp[i];
-                Ti.resize(Tp[n]);
-                Tx.resize(Tp[n]);
-            }
-            parallel_rows(n, [&](int64_t i0, int64_t i1) {
-                std::vector<int32_t> fill;
-                if (pass == 1) fill.assign(Tp.begin() + i0, Tp.begin() + i1);
-                for (int64_t j = 0; j < n; ++j) {
-                    const int32_t* b = Si + Sp[j];
-                    const int32_t* e = Si + Sp[j + 1];
-                    if (b == e || e[-1] < i0 || b[0] >= i1) continue;
-                    for (const int32_t* it = std::lower_bound(b, e, (int32_t)i0); it != e && *it < i1; ++it) {
-                        const int32_t q = (int32_t)(it - Si);
-                        if (!keep[q]) continue;
-                        if (pass == 0) {
-                            Tp[*it + 1]++;
-                        } else {
-                            int32_t& f = fill[*it - i0];
-                            Ti[f] = (int32_t)j;
-                            Tx[f] = Sx[q];
-                            ++f;
-                        }
-                    }
+        // per row: exclusive scan over the threads (its start inside the row), total into Tp
+        parallel_rows(n, [&](int64_t i0, int64_t i1) {
+            for (int64_t i = i0; i < i1; ++i) {
+                int32_t run = 0;
+                for (unsigned t = 0; t < nth; ++t) {
+                    const int32_t c = cnt[t][i];
+                    cnt[t][i] = run;
+                    run += c;
                 }
-            });
-        }
+                Tp[i + 1] = run;
+            }
+        });
+        for (int64_t i = 0; i < n; ++i) Tp[i + 1] += Tp[i];
+        Ti.resize(Tp[n]);
+        Tx.resize(Tp[n]);
+        run_threads([&](unsigned t) {
+            std::vector<int32_t>& c = cnt[t];
+            const int64_t j0 = t * chunk, j1 = std::min<int64_t>(n, j0 + chunk);
+            for (int64_t j = j0; j < j1; ++j)
+                for (int32_t q = Sp[j]; q < Sp[j + 1]; ++q) {
+                    if (!keep[q]) continue;
+                    const int32_t i = Si[q];
+                    const int32_t f = Tp[i] + c[i]++;
+                    Ti[f] = (int32_t)j;
+                    Tx[f] = Sx[q];
+                }
+        });
     }
     P.nnzT = Tp[n];
     tm.lap("  T = S^T filtered");
+
     // T^T needs no second transpose: row i of T^T is row i of S restricted to the kept entries
     // ---- S_sum = T 1 and sqrt((T o T) 1) (mmw.py:34-39)
     std::vector<double> S_sum(n), tnorm(n);
@@ -345,48 +420,90 @@ int build_host_plan(int64_t n, const int32_t* Sp, const int32_t* Si, const doubl
     P.nnz = total;
     tm.lap("union pattern");
 
-    // ---- edge ids in the reference's order (row-major upper triangle, mmw.py:56-57)
+    // ---- node numbering of the kernels: the locality order (joined here) or the caller's
+    std::vector<int32_t> perm(n), iperm(n);
+    if (order != 0) {
+        bfs_thread.join();
+        perm.swap(bfs_perm);
+        tm.lap("  clustered BFS (join)");
+    } else {
+        std::iota(perm.begin(), perm.end(), 0);
+    }
+    for (int64_t k = 0; k < n; ++k) iperm[perm[k]] = (int32_t)k;
+    std::vector<int32_t> rp(n + 1, 0);
+    for (int64_t k = 0; k < n; ++k) rp[k + 1] = rp[k] + (rowptr[perm[k] + 1] - rowptr[perm[k]]);
+
+    // ---- rows of the union pattern written straight in the kernels' numbering (one pass: no
+    // separate renumbering), edge ids in the reference's order (row-major upper triangle of the
+    // CALLER's numbering, mmw.py:56-57): the entry whose caller row < caller column owns the id,
+    // its mirror is marked and resolved in the pass below
     hvec<int32_t> col(P.nnz), eid(P.nnz);
     hvec<double> tfwd(P.nnz), tbwd(P.nnz);
     P.gi.resize(P.E_g); P.gj.resize(P.E_g); P.tij.resize(P.E_g); P.tji.resize(P.E_g);
     P.ai.resize(P.E_a); P.aj.resize(P.E_a);
-    parallel_rows(n, [&](int64_t r0, int64_t r1) {
+    constexpr int32_t MIRROR = -2;
+    parallel_rows(n, [&](int64_t k0, int64_t k1) {
         std::vector<Ent> row;
-        for (int64_t i = r0; i < r1; ++i) {
+        std::vector<uint64_t> ord;
+        std::vector<int32_t> ids;
+        for (int64_t k = k0; k < k1; ++k) {
+            const int64_t i = perm[k];
+            if (k + 2 < k1) {   // the next rows' inputs are scattered over memory: start fetching them
+                const int64_t i2 = perm[k + 2];
+                __builtin_prefetch(Si + Sp[i2]);
+                __builtin_prefetch(Sx + Sp[i2]);
+                __builtin_prefetch(Ti.data() + Tp[i2]);
+                __builtin_prefetch(Tx.data() + Tp[i2]);
+                __builtin_prefetch(keep.data() + Sp[i2]);
+            }
             build_row(i, row);
             int64_t g = g_ut[i], a = a_ut[i];
-            int32_t q = rowptr[i];
-            for (const Ent& e : row) {
-                col[q] = e.col;
-                tfwd[q] = e.tf;
-                tbwd[q] = e.tb;
-                eid[q] = -1;
+            const int m = (int)row.size();
+            ids.resize(m);
+            ord.resize(m);
+            for (int t = 0; t < m; ++t) {
+                const Ent& e = row[t];
+                int32_t id = -1;
                 if (e.col > i) {
                     if (e.kind == 1) {
                         P.gi[g] = (int32_t)i; P.gj[g] = e.col; P.tij[g] = e.tf; P.tji[g] = e.tb;
-                        eid[q] = (int32_t)g++;
+                        id = (int32_t)g++;
                     } else {
                         P.ai[a] = (int32_t)i; P.aj[a] = e.col;
-                        eid[q] = (int32_t)(P.E_g + a++);
+                        id = (int32_t)(P.E_g + a++);
                     }
+                } else if (e.col < i) {
+                    id = MIRROR;
                 }
-                ++q;
+                ids[t] = id;
+                ord[t] = ((uint64_t)(uint32_t)iperm[e.col] << 32) | (uint32_t)t;
+            }
+            if (order != 0) std::sort(ord.begin(), ord.end());
+            int32_t w = rp[k];
+            for (int t = 0; t < m; ++t, ++w) {
+                const int src = (int)(ord[t] & 0xffffffffu);
+                col[w] = (int32_t)(ord[t] >> 32);
+                eid[w] = ids[src];
+                tfwd[w] = row[src].tf;
+                tbwd[w] = row[src].tb;
             }
         }
     });
     tm.lap("  fill rows");
     {
-        // the pattern is symmetric: a lower entry (i, j < i) takes the id of its mirror (j, i),
-        // found by binary search in row j (rows are independent: all host cores)
+        // the pattern is symmetric: a mirror entry (k, c) takes the id of (c, k), found by binary
+        // search in row c (rows are independent: all host cores; only mirror slots are written,
+        // only owner slots are read)
         std::atomic<int> asym{0};
-        parallel_rows(n, [&](int64_t r0, int64_t r1) {
-            for (int64_t i = r0; i < r1; ++i)
-                for (int32_t q = rowptr[i]; q < rowptr[i + 1] && col[q] < i; ++q) {
-                    const int32_t j = col[q];
-                    const int32_t* b = col.data() + rowptr[j];
-                    const int32_t* e = col.data() + rowptr[j + 1];
-                    const int32_t* it = std::lower_bound(b, e, (int32_t)i);
-                    if (it == e || *it != i) {
+        parallel_rows(n, [&](int64_t k0, int64_t k1) {
+            for (int64_t k = k0; k < k1; ++k)
+                for (int32_t q = rp[k]; q < rp[k + 1]; ++q) {
+                    if (eid[q] != MIRROR) continue;
+                    const int32_t c = col[q];
+                    const int32_t* b = col.data() + rp[c];
+                    const int32_t* e = col.data() + rp[c + 1];
+                    const int32_t* it = std::lower_bound(b, e, (int32_t)k);
+                    if (it == e || *it != k) {
                         asym.store(1);
                         return;
                     }
@@ -398,68 +515,24 @@ int build_host_plan(int64_t n, const int32_t* Sp, const int32_t* Si, const doubl
             return SIGSDP_EINVAL;
         }
     }
+    tm.lap("edge ids");
 
-    P.rowptr.swap(rowptr);
+    P.rowptr.swap(rp);
     P.col.swap(col);
     P.eid.swap(eid);
     P.tfwd.swap(tfwd);
     P.tbwd.swap(tbwd);
-    P.S_sum.swap(S_sum);
-    P.tnorm.swap(tnorm);
-    P.h_max.assign(h_max, h_max + n);
-    P.perm.resize(n);
-    P.iperm.resize(n);
-    std::iota(P.perm.begin(), P.perm.end(), 0);
-    std::iota(P.iperm.begin(), P.iperm.end(), 0);
-
-    tm.lap("edge ids");
-    if (order != 0) {
-        // renumber nodes for locality; edge ids and edge lists keep the caller's order
-        std::vector<int32_t> perm;
-        locality_order(P, order > 1 ? order : 64, perm);
-        tm.lap("  clustered BFS");
-        std::vector<int32_t> iperm(n);
-        for (int64_t k = 0; k < n; ++k) iperm[perm[k]] = (int32_t)k;
-        std::vector<int32_t> rp(n + 1, 0);
-        hvec<int32_t> c2(P.nnz), e2(P.nnz);
-        hvec<double> f2(P.nnz), b2(P.nnz);
-        for (int64_t k = 0; k < n; ++k) rp[k + 1] = rp[k] + (P.rowptr[perm[k] + 1] - P.rowptr[perm[k]]);
-        parallel_rows(n, [&](int64_t k0, int64_t k1) {
-            std::vector<uint64_t> ord;
-            for (int64_t k = k0; k < k1; ++k) {
-                const int32_t o = perm[k];
-                const int32_t b = P.rowptr[o], e = P.rowptr[o + 1];
-                ord.resize(e - b);
-                for (int32_t q = b; q < e; ++q) ord[q - b] = ((uint64_t)(uint32_t)iperm[P.col[q]] << 32) | (uint32_t)q;
-                std::sort(ord.begin(), ord.end());
-                int32_t w = rp[k];
-                for (uint64_t key : ord) {
-                    const int32_t q = (int32_t)(key & 0xffffffffu);
-                    c2[w] = (int32_t)(key >> 32);
-                    e2[w] = P.eid[q];
-                    f2[w] = P.tfwd[q];
-                    b2[w] = P.tbwd[q];
-                    ++w;
-                }
-            }
-        });
-        auto permute = [&](std::vector<double>& v) {
-            std::vector<double> t(n);
-            for (int64_t k = 0; k < n; ++k) t[k] = v[perm[k]];
-            v.swap(t);
-        };
-        permute(P.S_sum);
-        permute(P.tnorm);
-        permute(P.h_max);
-        P.rowptr.swap(rp);
-        P.col.swap(c2);
-        P.eid.swap(e2);
-        P.tfwd.swap(f2);
-        P.tbwd.swap(b2);
-        P.perm.swap(perm);
-        P.iperm.swap(iperm);
+    P.S_sum.resize(n);
+    P.tnorm.resize(n);
+    P.h_max.resize(n);
+    for (int64_t k = 0; k < n; ++k) {
+        P.S_sum[k] = S_sum[perm[k]];
+        P.tnorm[k] = tnorm[perm[k]];
+        P.h_max[k] = h_max[perm[k]];
     }
-    tm.lap("locality renumbering");
+    P.perm.swap(perm);
+    P.iperm.swap(iperm);
+    tm.lap("node vectors");
     P.dpos.assign(n, -1);
     P.apos.assign(P.E_a, -1);
     parallel_rows(n, [&](int64_t k0, int64_t k1) {   // every slot has exactly one writer

