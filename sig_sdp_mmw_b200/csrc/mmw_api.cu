@@ -191,6 +191,7 @@ __global__ void k_decide(Ctrl* ctrl, int slot, double c1, double tol) {
     ctrl->a1 = fn;
 }
 __global__ void k_advance(Ctrl* ctrl, int n_iters) { ctrl->iter += n_iters; }
+__global__ void k_clear_emax(Ctrl* ctrl) { ctrl->emax_key = 0ull; }
 
 __global__ void k_set_diag(double* v, const int* dpos, int n, double x) {
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) v[dpos[k]] = x;
@@ -538,6 +539,7 @@ static int run_stepwise(sigsdp_solver* s, int n_iters, cudaStream_t st) {
             }
         }
         ks.record(pp, it, m_star, ss, a1, mu, tcount, st);
+        k_clear_emax<<<1, 1, 0, st>>>(P.ctrl);
         ks.gram(pp, grid, s->smem, st);
         CK(cudaGetLastError());
     }

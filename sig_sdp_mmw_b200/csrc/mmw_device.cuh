@@ -95,6 +95,7 @@ struct Ctrl {
     unsigned long long emax_key;   // max e_accu (order-preserving key)
     double trL[2];                 // tr(L_accu), double-buffered by iteration parity
     double mu;                     // shift of the current sketch (for exporting Y_h)
+    double smax_shift;             // soft-max shift of the next iteration: max e_accu of the last one (0 after reset)
     long long total_terms;
     long long iter;                // iterations done since reset
     // stepwise-mode controller (host reads these back)
@@ -270,7 +271,7 @@ __device__ __forceinline__ double group_sum(cg::thread_block_tile<G>& tile, doub
 // the Taylor terms, trace).  The phases are written against this interface:
 //   sync(P, what, slot)   barrier; `what` names the scalars the finished phase produced
 //   emax / exp_sums / a1 / c1 / trace_sum / term_norms   those scalars, valid after the sync
-enum SyncWhat { SY_PLAIN = 0, SY_DUAL = 1, SY_EXP = 2, SY_LOSS = 3, SY_TERM = 4 };
+enum SyncWhat { SY_PLAIN = 0, SY_DUAL = 1, SY_LOSS = 3, SY_TERM = 4 };
 
 // spin-wait helper: tight polls first, then back off; a barrier that does not complete
 // within `limit_ns` (a block died, a peer never launched) traps instead of hanging the GPU
@@ -426,7 +427,6 @@ struct ShardTeam {
             const int nblk = gridDim.x;
             if (what == SY_DUAL) {
                 pk[0] = ld_u64(&ctrl->emax_key);
-            } else if (what == SY_EXP) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) ps[i] = warp_strided_sum(P.psum + i, PSTRIDE, nblk, lane);
             } else if (what == SY_LOSS || what == SY_TERM) {
@@ -762,13 +762,20 @@ __device__ __forceinline__ void taylor_select(double a1, int& m_star, long long&
 }
 
 // ===========================================================================
-// Phase DUAL (mmw.py:124-137): e = [eD | eF | eH], e_accu += eta e, running max.
+// Phase DUAL (mmw.py:124-139): e = [eD | eF | eH], e_accu += eta e, and the soft-max numerators.
 //   eD_k = (X_kk - 1)/(1 - 1/K)
 //   eF_e = (X_e + 1/(Z-1)) / (1/(K(Z-1)) + 1/2)            asso-UT edges
 //   eH_k = ((T r)_k (Z-1)/Z - (h_k - S_sum_k/Z)) / norm_H_k,  r = row sums of X_offdiag
 //          (quirk Q1: the reference's `*` is a sparse mat-mul)
+// scipy.special.softmax (mmw.py:139) is exp(e - max e) / sum: ANY shift gives the same Y, so the
+// numerators u = exp(e_accu - shift) are formed right here with the PREVIOUS iteration's maximum
+// as the shift (e_accu moves by eta * e per iteration, so the exponent stays O(eta |e|) above
+// zero) while the new maximum is reduced for the next iteration.  That removes a pass over the
+// dual vector and one team barrier (a cross-GPU one when row-sharded) per iteration.  Outputs:
+//   u, q_k = u_Hk / norm_H_k, partial sums S_D = sum u_D, S_F = sum u_F, S_H = sum u_H,
+//   S_hq = sum_k hcoef_k q_k, and max e_accu.
 template <typename T, int G, class Team>
-__device__ void phase_dual(const Prob<T>& P, const Team& team, double* sh) {
+__device__ void phase_dual(const Prob<T>& P, const Team& team, double shift, double* sh) {
     const PlanDev& g = P.g;
     const ShardDev& S = P.sh;
     const int K = g.n, Z = P.Z;
@@ -780,6 +787,7 @@ __device__ void phase_dual(const Prob<T>& P, const Team& team, double* sh) {
     const double zr = (double)(Z - 1) / (double)Z;
     const double cF = 1.0 / ((double)K * (Z - 1)) + 0.5;
     double emax = -INFINITY;
+    double sD = 0.0, sF = 0.0, sH = 0.0, sHq = 0.0;
     if (team.rank() == 0 && threadIdx.x < 3) {  // all of these are idle between gram and the loss phase
         P.ctrl->nrm_b[threadIdx.x] = 0ull;
         P.ctrl->nrm_f[threadIdx.x] = 0ull;
@@ -795,11 +803,12 @@ __device__ void phase_dual(const Prob<T>& P, const Team& team, double* sh) {
             // every load of the row is issued before the first use: the phase is bound by
             // memory latency, not bytes, so what counts is the number of loads in flight
             const int pa = g.rowptr[k], p1 = g.rowptr[k + 1];
-            double hm = 0.0, ssum = 0.0, nh = 1.0, xd = 0.0, ea = 0.0, eb = 0.0;
+            double hm = 0.0, ssum = 0.0, nh = 1.0, xd = 0.0, ea = 0.0, eb = 0.0, hc = 0.0;
             if (lane == 0) {
                 hm = g.h_max[k];
                 ssum = g.S_sum[k];
                 nh = P.nH[k];
+                hc = P.hcoef[k];
                 xd = P.Xv[g.dpos[k]];
                 ea = P.e_acc[k];
                 eb = P.e_acc[K + g.E_a + k];
@@ -823,6 +832,15 @@ __device__ void phase_dual(const Prob<T>& P, const Team& team, double* sh) {
                 P.e_acc[k] = a;
                 P.e_acc[K + g.E_a + k] = b;
                 emax = fmax(emax, fmax(a, b));
+                const double vD = exp(a - shift), vH = exp(b - shift);
+                P.u[k] = vD;
+                P.u[K + g.E_a + k] = vH;
+                const double qq = vH / nh;
+                P.q[k] = qq;
+                if (S.pmask) push_f64(team, S, P.q + k, qq, S.pmask[k]);
+                sD += vD;
+                sH += vH;
+                sHq += hc * qq;
             }
         }
     }
@@ -835,54 +853,20 @@ __device__ void phase_dual(const Prob<T>& P, const Team& team, double* sh) {
         double eF = (P.Xv[pos] + zf) / cF;
         double a = P.e_acc[K + e] + P.eta * eF;
         P.e_acc[K + e] = a;
-        if (i < S.n_inc_owned) emax = fmax(emax, a);
-    }
-    emax = block_max(emax, sh);
-    if (threadIdx.x == 0 && emax > -INFINITY) atomicMax(&P.ctrl->emax_key, dkey_any(emax));
-}
-
-// ===========================================================================
-// Phase EXP (mmw.py:139, scipy.special.softmax): u = exp(e_accu - max); partial sums
-//   S = sum u,  S_D = sum u_D,  S_F = sum u_F,  S_hq = sum_k hcoef_k u_Hk / norm_H_k
-// and q_k = u_Hk / norm_H_k for the loss phase.
-template <typename T, int G, class Team>
-__device__ void phase_exp(const Prob<T>& P, const Team& team, double* sh) {
-    const PlanDev& g = P.g;
-    const ShardDev& S = P.sh;
-    const int K = g.n;
-    const double emax = team.emax(P);
-    double sD = 0.0, sF = 0.0, sH = 0.0, sHq = 0.0;
-    // this rank's part of the constraint vector [D | F | H]: own rows, incident asso edges, own rows
-    const int nr = S.row_hi - S.row_lo;
-    const int tot = 2 * nr + S.n_inc;
-    for (int i = team.rank() * NT + threadIdx.x; i < tot; i += team.size() * NT) {
-        if (i < nr) {
-            const int c = S.row_lo + i;
-            const double v = exp(P.e_acc[c] - emax);
-            P.u[c] = v;
-            sD += v;
-        } else if (i < nr + S.n_inc) {
-            const int j = i - nr;
-            const int c = K + (S.inc_e ? S.inc_e[j] : j);
-            const double v = exp(P.e_acc[c] - emax);
-            P.u[c] = v;
-            if (j < S.n_inc_owned) sF += v;
-        } else {
-            const int k = S.row_lo + (i - nr - S.n_inc);
-            const double v = exp(P.e_acc[K + g.E_a + k] - emax);
-            P.u[K + g.E_a + k] = v;
-            const double qq = v / P.nH[k];
-            P.q[k] = qq;
-            if (S.pmask) push_f64(team, S, P.q + k, qq, S.pmask[k]);
-            sH += v;
-            sHq += P.hcoef[k] * qq;
+        const double v = exp(a - shift);
+        P.u[K + e] = v;
+        if (i < S.n_inc_owned) {
+            emax = fmax(emax, a);
+            sF += v;
         }
     }
+    emax = block_max(emax, sh);
     sD = block_sum(sD, sh);
     sF = block_sum(sF, sh);
     sH = block_sum(sH, sh);
     sHq = block_sum(sHq, sh);
     if (threadIdx.x == 0) {
+        if (emax > -INFINITY) atomicMax(&P.ctrl->emax_key, dkey_any(emax));
         double* o = P.psum + (size_t)team.rank() * PSTRIDE;
         o[0] = sD;
         o[1] = sF;
@@ -932,7 +916,6 @@ __device__ void phase_loss(const Prob<T>& P, const Team& team, int it_local, dou
     if (team.rank() == 0 && threadIdx.x == 0) {
         ctrl->trL[(iter + 1) & 1] = trL;
         ctrl->mu = mu;
-        ctrl->emax_key = 0ull;  // read by everyone before the previous barrier
     }
 
     // ---- Y, Y_avgd (the entries this rank owns: own rows' D and H, owned asso edges' F)
@@ -1946,13 +1929,13 @@ __device__ void run_iterations(const Prob<T>& P, const Team& team, int n_iters, 
         phase_gram_finish<T, G>(P, team, sh);
         TIMED_SYNC(SY_PLAIN, 0);
     }
+    double shift = *reinterpret_cast<const volatile double*>(&ctrl->smax_shift);
     for (int it = 0; it < n_iters; ++it) {
         unsigned long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
         if (leader) t0 = globaltimer_ns();
-        phase_dual<T, G>(P, team, sh);
+        phase_dual<T, G>(P, team, shift, sh);
         TIMED_SYNC(SY_DUAL, 0);
-        phase_exp<T, G>(P, team, sh);
-        TIMED_SYNC(SY_EXP, 0);
+        shift = team.emax(P);   // this iteration's maximum is the next one's soft-max shift
         if (leader) t1 = globaltimer_ns();
         phase_loss<T, G>(P, team, it, sh);
         TIMED_SYNC(SY_LOSS, 0);
@@ -1990,7 +1973,10 @@ __device__ void run_iterations(const Prob<T>& P, const Team& team, int n_iters, 
             }
         }
         terms += tcount;
-        if (leader) t3 = globaltimer_ns();
+        if (leader) {
+            t3 = globaltimer_ns();
+            ctrl->emax_key = 0ull;   // everyone read it right after the dual barrier, at least one barrier ago
+        }
         if (staged)
             if (G >= 8 && P.Dp == G * Vec<T>::N)
                 phase_gram_staged2<T, G>(P, team, sh, st);
@@ -2013,6 +1999,7 @@ __device__ void run_iterations(const Prob<T>& P, const Team& team, int n_iters, 
 #undef TIMED_SYNC
     if (leader) {
         ctrl->iter += n_iters;
+        ctrl->smax_shift = shift;
         ctrl->total_terms += terms;
         ctrl->dbg[4] += (long long)sync_ns;
         team.finish(P);

@@ -16,7 +16,7 @@ struct KernelSet {
                          cudaStream_t st);
     // one kernel per phase (stepwise mode: profiling / debugging)
     void (*dual)(const void* prob, int grid, cudaStream_t st);
-    void (*exp)(const void* prob, int grid, cudaStream_t st);
+    void (*exp)(const void* prob, int grid, cudaStream_t st);   // after the dual kernel: next soft-max shift
     void (*loss)(const void* prob, int grid, int it_local, cudaStream_t st);
     void (*term)(const void* prob, int grid, size_t smem, const void* bin, void* bout, double coeff, double mu, int slot,
                  cudaStream_t st);
@@ -50,12 +50,13 @@ __global__ void __launch_bounds__(NT, 2) k_fused_rows(Prob<T> P, int n_iters) {
 template <typename T, int G>
 __global__ void __launch_bounds__(NT, 2) k_dual(Prob<T> P) {
     __shared__ double sh[NWARP + 2];
-    phase_dual<T, G>(P, StepTeam(), sh);
+    phase_dual<T, G>(P, StepTeam(), *reinterpret_cast<const volatile double*>(&P.ctrl->smax_shift), sh);
 }
-template <typename T, int G>
-__global__ void __launch_bounds__(NT, 2) k_exp(Prob<T> P) {
-    __shared__ double sh[NWARP + 2];
-    phase_exp<T, G>(P, StepTeam(), sh);
+// stepwise: what the fused kernel does between the dual barrier and the Gram phase -- this iteration's
+// maximum becomes the next one's soft-max shift and the reduction key is cleared
+template <typename T>
+__global__ void k_after_dual(Ctrl* ctrl) {
+    ctrl->smax_shift = dkey_any_inv(ld_u64(&ctrl->emax_key));
 }
 template <typename T, int G>
 __global__ void __launch_bounds__(NT, 2) k_loss(Prob<T> P, int it_local) {
@@ -162,7 +163,7 @@ struct Launchers {
         return cudaLaunchCooperativeKernel((void*)k_fused<T, G>, dim3(grid), dim3(NT), args, smem, st);
     }
     static void dual(const void* p, int grid, cudaStream_t st) { k_dual<T, G><<<grid, NT, 0, st>>>(prob(p)); }
-    static void exp_(const void* p, int grid, cudaStream_t st) { k_exp<T, G><<<grid, NT, 0, st>>>(prob(p)); }
+    static void exp_(const void* p, int, cudaStream_t st) { k_after_dual<T><<<1, 1, 0, st>>>(prob(p).ctrl); }
     static void loss(const void* p, int grid, int it_local, cudaStream_t st) { k_loss<T, G><<<grid, NT, 0, st>>>(prob(p), it_local); }
     static void term(const void* p, int grid, size_t smem, const void* bin, void* bout, double coeff, double mu, int slot,
                      cudaStream_t st) {
