@@ -11,7 +11,7 @@ timeout 300 $STEP >> $LOG 2>&1 || { echo "plain stepwise run failed" >> $LOG; ta
 echo "$(date +%T) ncu launches step" >> $LOG
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches_step_$TAG.csv $STEP >> $LOG 2>&1
 echo "$(date +%T) rc=$? ncu full step" >> $LOG
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k_term|k_gram|k_loss|k_dual|k_exp' -s 40 -c 9 -o gpurun_out/prof_step_$TAG -f $STEP >> $LOG 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k_term|k_gram|k_loss|k_dual' -s 40 -c 9 -o gpurun_out/prof_step_$TAG -f $STEP >> $LOG 2>&1
 echo "$(date +%T) rc=$? plain fused" >> $LOG
 timeout 300 $FUSE >> $LOG 2>&1 || { echo "plain fused run failed" >> $LOG; exit 1; }
 echo "$(date +%T) ncu launches fused" >> $LOG

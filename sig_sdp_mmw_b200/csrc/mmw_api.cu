@@ -1004,7 +1004,8 @@ static int solver_alloc(sigsdp_solver* s) {
             hvec<int32_t> slots((size_t)nt * Rs * 4);
             parallel_for(nt, [&](int64_t t0, int64_t t1) {
             std::vector<int> idx;
-            std::vector<uint8_t> split;
+            std::vector<uint8_t> split, used;
+            std::vector<std::pair<int, int>> units;   // (work, row)
             for (int t = (int)t0; t < (int)t1; ++t) {
                 const int r0 = ht.trow[t], r1 = ht.trow[t + 1], nr = r1 - r0;
                 int32_t* sl = slots.data() + (size_t)t * Rs * 4;
@@ -1023,19 +1024,46 @@ static int solver_alloc(sigsdp_solver* s) {
                     split[idx[nsplit] - r0] = 1;
                     ++nsplit;
                 }
-                int pos = 0;
-                for (int i = 0; i < nsplit; ++i) {   // pairs first: they start at even slots, i.e. inside a warp
-                    const int k = idx[i], p0 = h.rowptr[k], len = h.rowptr[k + 1] - p0, half = (len + 1) / 2;
-                    int32_t* a = sl + (size_t)pos * 4;
-                    a[0] = k; a[1] = p0; a[2] = half; a[3] = 1;
-                    a[4] = k; a[5] = p0 + half; a[6] = len - half; a[7] = 2;
-                    pos += 2;
+                // (an odd number of whole rows can cost one idle slot in front of a pair: keep room for it)
+                if (nsplit > 0 && ((nr - nsplit) & 1) && nr + nsplit + 1 > Rs) {
+                    --nsplit;
+                    split[idx[nsplit] - r0] = 0;
                 }
-                for (int k = r0; k < r1; ++k) {
-                    if (split[k - r0]) continue;
+                // Slots are dealt in order of decreasing work (a split row counts as its longer half):
+                // the groups of one warp run in lock-step, so a warp lasts as long as its longest
+                // row -- and the Gram kernel's warp-wide shuffles make every group of a warp load for
+                // that many non-zeros -- and neighbours in this order have (nearly) equal lengths.  A
+                // split row's halves sit side by side starting at an even slot, i.e. inside one warp.
+                units.clear();
+                for (int i = 0; i < nr; ++i) {
+                    const int k = idx[i], len = h.rowptr[k + 1] - h.rowptr[k];
+                    units.push_back({split[k - r0] ? (len + 1) / 2 : len, k});
+                }
+                std::stable_sort(units.begin(), units.end(), [](const std::pair<int, int>& a, const std::pair<int, int>& b) { return a.first > b.first; });
+                used.assign(nr, 0);
+                int pos = 0;
+                auto place = [&](int u) {
+                    const int k = units[u].second, p0 = h.rowptr[k], len = h.rowptr[k + 1] - p0;
                     int32_t* a = sl + (size_t)pos * 4;
-                    a[0] = k; a[1] = h.rowptr[k]; a[2] = h.rowptr[k + 1] - h.rowptr[k]; a[3] = 0;
-                    ++pos;
+                    if (split[k - r0]) {
+                        const int half = (len + 1) / 2;
+                        a[0] = k; a[1] = p0; a[2] = half | (1 << 16); a[3] = h.dpos[k];
+                        a[4] = k; a[5] = p0 + half; a[6] = (len - half) | (2 << 16); a[7] = h.dpos[k];
+                        pos += 2;
+                    } else {
+                        a[0] = k; a[1] = p0; a[2] = len; a[3] = h.dpos[k];
+                        ++pos;
+                    }
+                    used[u] = 1;
+                };
+                for (int u = 0; u < nr; ++u) {
+                    if (used[u]) continue;
+                    if (split[units[u].second - r0] && (pos & 1)) {   // fill the odd slot with the next whole row
+                        int v = u + 1;
+                        while (v < nr && (used[v] || split[units[v].second - r0])) ++v;
+                        if (v < nr) place(v); else ++pos;   // (no whole row left: leave the slot idle)
+                    }
+                    place(u);
                 }
             }
             }, 256);

@@ -50,8 +50,9 @@ struct TileDev {
     const int4* runs;            // {first column, first shared-memory slot, length, 0}
     const unsigned short* lcol;  // nnz (+ padding)
     const int4* trec;            // 2 per tile: {r0, r1, p0, p1}, {run0, run1, distinct columns, 0}
-    // phase_term_staged2 only (per solver, nullptr otherwise): what each of the slot_r lane
-    // groups of a block does in a tile, {row or -1, first non-zero, non-zeros, role}.  A tile has
+    // phase_term_staged2 / phase_gram_staged2 only (per solver, nullptr otherwise): what each of the
+    // slot_r lane groups of a block does in a tile, {row or -1, first non-zero, non-zeros | role << 16,
+    // position of the row's diagonal entry}.  A tile has
     // fewer rows than groups; the spare groups take the second halves of its longest rows
     // (role 1 = first half, adds the partial sums of the group to its right; 2 = second half, no
     // epilogue; 0 = whole row), so the multiply ends with the longest HALF row.
@@ -1433,17 +1434,20 @@ __device__ void phase_term_staged2(const Prob<T>& P, const Team& team, const T* 
     for (int t = S.tile_lo + team.rank(); t < S.tile_hi; t += team.size()) {
         const int4 trc = tl.trec[2 * t];
         const int r0 = trc.x, r1 = trc.y;
+        // this group's slot record is requested before the stage: its latency (and that of the
+        // F row it names) hides behind the bulk copies instead of following them
+        int4 sr = make_int4(-1, 0, 0, 0);
+        if (use_slots) sr = tl.slots[(size_t)t * R + grp];
         stage_tile(P, Bin, (const T*)P.Aval, t, st);
         for (int kb = r0; kb < r1; kb += R) {   // block-uniform trip count (one trip with a slot table)
             int k, p0, len, role = 0;
             bool valid;
             if (use_slots) {
-                const int4 sr = tl.slots[(size_t)t * R + grp];
                 k = sr.x;
                 valid = k >= 0;
                 p0 = sr.y;
-                len = sr.z;
-                role = sr.w;
+                len = sr.z & 0xffff;
+                role = sr.z >> 16;
             } else {
                 k = kb + grp;
                 valid = k < r1;
@@ -1720,6 +1724,8 @@ __device__ void phase_gram_staged2(const Prob<T>& P, const Team& team, double* s
     for (int t = S.tile_lo + team.rank(); t < S.tile_hi; t += team.size()) {
         const int4 trc = tl.trec[2 * t];
         const int r0 = trc.x, r1 = trc.y;
+        int4 sr = make_int4(-1, 0, 0, 0);   // requested before the stage (see phase_term_staged2)
+        if (use_slots) sr = tl.slots[(size_t)t * R + grp];
         stage_tile(P, (const T*)P.F, (const T*)nullptr, t, st);
         for (int kb = r0; kb < r1; kb += R) {   // block-uniform trip count (one trip with a slot table)
             // the term kernel's slot table balances this kernel too: the two halves of a split
@@ -1727,13 +1733,12 @@ __device__ void phase_gram_staged2(const Prob<T>& P, const Team& team, double* s
             int k, p0 = 0, len = 0, pd = 0, role = 0;
             bool valid;
             if (use_slots) {
-                const int4 sr = tl.slots[(size_t)t * R + grp];
                 k = sr.x;
                 valid = k >= 0;
                 p0 = sr.y;
-                len = sr.z;
-                role = sr.w;
-                if (valid) pd = g.dpos[k];
+                len = sr.z & 0xffff;
+                role = sr.z >> 16;
+                pd = sr.w;   // position of the row's diagonal entry
             } else {
                 k = kb + grp;
                 valid = k < r1;
