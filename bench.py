@@ -234,6 +234,7 @@ def run_batch(args):
                           "scaling": "strong", "dtype": "f64", "data": "synthetic",
                           "config": {"workload": "cfg5_batch", "instances": args.instances, "nodes": K, "Z": Z, "D": Z * rr,
                                      "parallelism": "one thread block per instance, instances split across %d rank(s)" % world,
+                                     "blocks_per_instance": [b.blocks_per_instance() for b in bsol.batches],
                                      "taylor_terms_rank0": terms, "topology_s": t_gen, "plan_solver_setup_s": t_setup},
                           "gpu_launches": len(bsol.batches)}))
     if world > 1:

@@ -295,7 +295,11 @@ int sigsdp_batch_create(sigsdp_solver* const* solvers, int count, sigsdp_batch**
  * Omega from the stream keyed by seed + 0x9E3779B97F4A7C15 * (i + 1), whichever launch it is in. */
 int sigsdp_batch_create_ids(sigsdp_solver* const* solvers, const int64_t* ids, int count, sigsdp_batch** out);
 void sigsdp_batch_destroy(sigsdp_batch* b);
+/* When the batch has fewer instances than the device has resident block slots, every instance is
+ * given several co-resident blocks (a team with its own barrier, cooperative launch); the count
+ * used by the last sigsdp_batch_iterate is returned by sigsdp_batch_blocks_per_instance (>= 1). */
 int sigsdp_batch_iterate(sigsdp_batch* b, int n_iters, uint64_t seed, void* stream);
+int sigsdp_batch_blocks_per_instance(const sigsdp_batch* b);
 
 #ifdef __cplusplus
 }

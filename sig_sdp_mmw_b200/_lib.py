@@ -93,6 +93,8 @@ def load():
     lib.sigsdp_solver_destroy.restype = None
     lib.sigsdp_batch_destroy.argtypes = [vp]
     lib.sigsdp_batch_destroy.restype = None
+    lib.sigsdp_batch_blocks_per_instance.argtypes = [vp]
+    lib.sigsdp_batch_blocks_per_instance.restype = C.c_int
     _lib = lib
     return lib
 
@@ -375,6 +377,10 @@ class Batch:
 
     def iterate(self, n_iters, seed=0, stream=None):
         check(load().sigsdp_batch_iterate(self.handle, int(n_iters), int(seed), stream))
+
+    def blocks_per_instance(self):
+        """Thread blocks each instance got in the last iterate (> 1 when the batch under-fills the GPU)."""
+        return int(load().sigsdp_batch_blocks_per_instance(self.handle))
 
 
 def debug_normals(seed, it, n, D, dtype=F64):

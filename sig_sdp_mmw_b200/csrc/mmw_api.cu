@@ -164,7 +164,7 @@ struct sigsdp_solver {
 
 struct sigsdp_batch {
     std::vector<sigsdp_solver*> solvers;
-    int device = 0, dtype = 0, G = 0;
+    int device = 0, dtype = 0, G = 0, last_bpi = 1;
     size_t smem = 0;
     void* d_probs = nullptr;
 };
@@ -1951,10 +1951,32 @@ int sigsdp_batch_iterate(sigsdp_batch* b, int n_iters, uint64_t seed, void* stre
     const KernelSet& ks = kset_of(b->dtype, b->G);
     int occ = 0;
     CK(ks.prepare(b->smem, 0, &occ));
-    CK(ks.batch(b->d_probs, (int)b->solvers.size(), b->smem, n_iters, seed, st));
+    // Fewer instances than resident block slots: give every instance several blocks (a small team
+    // with its own barrier) as long as all of them stay co-resident; capped where the per-barrier
+    // cost outweighs the rows a block still has.  SIGSDP_BATCH_BLOCKS overrides (1 = one block each).
+    int bpi = 1;
+    {
+        const int count = (int)b->solvers.size();
+        int occ_b = 0, sms = 0;
+        CK(ks.batch_occupancy(b->smem, &occ_b));
+        CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, b->device));
+        const int slots = occ_b * sms;
+        int64_t min_tiles = INT64_MAX;
+        for (const sigsdp_solver* sv : b->solvers) {
+            const int R = NT / sv->G;
+            const int64_t tiles = sv->RT > 0 ? sv->ntiles : (sv->plan->h.n + R - 1) / R;
+            min_tiles = std::min(min_tiles, tiles);
+        }
+        bpi = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)slots / std::max(1, count), (int64_t)4, min_tiles}));
+        if (const char* e = getenv("SIGSDP_BATCH_BLOCKS")) bpi = std::max(1, std::min(atoi(e), std::max(1, slots / std::max(1, count))));
+        b->last_bpi = bpi;
+    }
+    CK(ks.batch(b->d_probs, (int)b->solvers.size(), b->smem, n_iters, seed, bpi, st));
     for (sigsdp_solver* s : b->solvers) s->iters_done += n_iters;
     return SIGSDP_OK;
 }
+
+int sigsdp_batch_blocks_per_instance(const sigsdp_batch* b) { return b ? b->last_bpi : fail(SIGSDP_EINVAL, "null batch"); }
 
 int sigsdp_round_greedy(int64_t n, int Z, const int32_t* Sp, const int32_t* Si, const double* Sx, const int32_t* Qp,
                         const int32_t* Qi, const double* Qx, const double* h_max, const int32_t* rank,

@@ -6,5 +6,5 @@
 namespace sigsdp {
 using L = Launchers<SIGSDP_T, SIGSDP_G>;
 const KernelSet SIGSDP_NAME = {L::prepare, L::fused, L::dual, L::exp_, L::loss, L::term,
-                               L::copy,    L::gram,  L::record, L::batch};
+                               L::copy,    L::gram,  L::record, L::batch, L::batch_occupancy};
 }  // namespace sigsdp

@@ -26,7 +26,8 @@ struct KernelSet {
                    cudaStream_t st);
     // one thread block per independent instance
     cudaError_t (*batch)(const void* probs_dev, int count, size_t smem, int n_iters, unsigned long long seed,
-                         cudaStream_t st);
+                         int blocks_per_instance, cudaStream_t st);
+    cudaError_t (*batch_occupancy)(size_t smem, int* blocks_per_sm);
 };
 
 #ifdef SIGSDP_T
@@ -117,6 +118,26 @@ __global__ void __launch_bounds__(NT, 2) k_batch(const Prob<T>* probs, int n_ite
     CtaTeam team;
     run_iterations<T, G>(Ps, team, n_iters, dyn_smem, sh);
 }
+// batch, B > 1 blocks per instance (cooperative launch): block b works for instance b / B
+template <typename T, int G>
+__global__ void __launch_bounds__(NT, 2) k_batch_team(const Prob<T>* probs, int n_iters, unsigned long long seed, int B) {
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    __shared__ double sh[NWARP + 2];
+    __shared__ Prob<T> Ps;
+    {
+        const int* src = reinterpret_cast<const int*>(probs + blockIdx.x / B);
+        int* dst = reinterpret_cast<int*>(&Ps);
+        for (int i = threadIdx.x; i < (int)(sizeof(Prob<T>) / sizeof(int)); i += NT) dst[i] = src[i];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            Ps.omega = nullptr;
+            Ps.seed = seed + 0x9E3779B97F4A7C15ull * (Ps.seed + 1ull);
+        }
+        __syncthreads();
+    }
+    BatchTeam team(&Ps.ctrl->bar, B, (int)(blockIdx.x % B));
+    run_iterations<T, G>(Ps, team, n_iters, dyn_smem, sh);
+}
 template <typename T>
 __global__ void k_record(Prob<T> P, int it_local, int m_star, long long s, double a1, double mu, int nterms) {
     TaylorState ts;
@@ -148,6 +169,7 @@ struct Launchers {
             if ((e = cudaFuncSetAttribute(k_term<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin))) return e;
             if ((e = cudaFuncSetAttribute(k_gram<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin))) return e;
             if ((e = cudaFuncSetAttribute(k_batch<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin))) return e;
+            if ((e = cudaFuncSetAttribute(k_batch_team<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin))) return e;
             opted[dev] = true;
         }
         if (shard) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_fused_rows<T, G>, NT, smem);
@@ -174,9 +196,20 @@ struct Launchers {
     static void record(const void* p, int it_local, int m_star, long long s, double a1, double mu, int nterms, cudaStream_t st) {
         k_record<T><<<1, 1, 0, st>>>(prob(p), it_local, m_star, s, a1, mu, nterms);
     }
-    static cudaError_t batch(const void* probs, int count, size_t smem, int n_iters, unsigned long long seed, cudaStream_t st) {
-        k_batch<T, G><<<dim3((unsigned)count), dim3(NT), smem, st>>>(static_cast<const Prob<T>*>(probs), n_iters, seed);
-        return cudaGetLastError();
+    // blocks_per_instance > 1: that many co-resident blocks share an instance (the caller has checked
+    // that count * blocks_per_instance blocks fit on the device)
+    static cudaError_t batch(const void* probs, int count, size_t smem, int n_iters, unsigned long long seed,
+                             int blocks_per_instance, cudaStream_t st) {
+        const Prob<T>* pp = static_cast<const Prob<T>*>(probs);
+        if (blocks_per_instance <= 1) {
+            k_batch<T, G><<<dim3((unsigned)count), dim3(NT), smem, st>>>(pp, n_iters, seed);
+            return cudaGetLastError();
+        }
+        void* args[] = {(void*)&pp, (void*)&n_iters, (void*)&seed, (void*)&blocks_per_instance};
+        return cudaLaunchCooperativeKernel((void*)k_batch_team<T, G>, dim3((unsigned)(count * blocks_per_instance)), dim3(NT), args, smem, st);
+    }
+    static cudaError_t batch_occupancy(size_t smem, int* occ) {
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_batch_team<T, G>, NT, smem);
     }
 };
 #endif  // SIGSDP_T

@@ -109,11 +109,18 @@ def test_device_conflict_counter_matches_reference_rounding_py():
         assert n_asso == orc.conflict_counts(z, state)[2]
 
 
+@pytest.mark.parametrize("blocks", ["1", "auto"])
 @pytest.mark.parametrize("dtype,code,tol", [("float64", _lib.F64, 1e-9), ("float32", _lib.F32, 2e-3)])
-def test_batch_kernel_matches_oracle_on_exported_normals(dtype, code, tol):
-    """The one-block-per-instance kernel (cfg5) against the ORACLE: the Philox normals each
-    instance draws are exported through sigsdp_debug_normals and fed to the oracle."""
+def test_batch_kernel_matches_oracle_on_exported_normals(dtype, code, tol, blocks, monkeypatch):
+    """The batch kernel (cfg5) against the ORACLE: the Philox normals each instance draws are
+    exported through sigsdp_debug_normals and fed to the oracle.  blocks = "1": one thread block
+    per instance; "auto": a batch this small gets several co-resident blocks per instance (a team
+    with its own barrier), the way 128 instances per GPU run on an 8-GPU split."""
     _require_gpu()
+    if blocks == "1":
+        monkeypatch.setenv("SIGSDP_BATCH_BLOCKS", "1")
+    else:
+        monkeypatch.delenv("SIGSDP_BATCH_BLOCKS", raising=False)
     states = [sparse_env(cell_size=5 + (i % 3), sta_density_per_1m2=75e-4, seed=20 + i).generate_S_Q_hmax() for i in range(5)]
     states.append(sparse_env(cell_size=20, sta_density_per_1m2=6.25e-3, seed=3).generate_S_Q_hmax())   # the cfg5 instance size
     Z, rr, eta, nit, seed = 8, 2, 0.04, 12, 42
@@ -121,6 +128,8 @@ def test_batch_kernel_matches_oracle_on_exported_normals(dtype, code, tol):
     bsol = BatchSolver(states, Z, eta, rank_radio=rr, dtype=dtype)
     bsol.iterate(nit, seed=seed)
     torch.cuda.synchronize()
+    bpi = [b.blocks_per_instance() for b in bsol.batches]
+    assert all(x == 1 for x in bpi) if blocks == "1" else all(x > 1 for x in bpi)
     for i, state in enumerate(states):
         K = state[0].shape[0]
         p = orc.build_problem(Z, state)
