@@ -150,6 +150,12 @@ int sigsdp_solver_exchange_buffer(sigsdp_solver* s, void** dev_ptr, int64_t* cou
 int sigsdp_solver_create_rows(const sigsdp_plan* plan, int Z, int D, double eta, int dtype, int tiling, int rank,
                               int nranks, int max_blocks, sigsdp_solver** out);
 int sigsdp_solver_shard_info(const sigsdp_solver* s, int64_t info[12]);
+/* The row partition a row-sharded solver of `nranks` ranks would use, without a device (host-only plans work): rows
+ * cut at tile boundaries for the given tile caps (max_rows > 0, as in sigsdp_plan_tile_stats) or anywhere
+ * (max_rows = 0).  row0_out[nranks + 1] = first row of every rank (internal numbering); optional per rank: rows pushed
+ * per Taylor term (row x destination pairs), distinct foreign rows read, association edges owned. */
+int sigsdp_plan_row_partition(sigsdp_plan* plan, int nranks, int max_rows, int ucap, int nnzcap, int64_t* row0_out,
+                              int64_t* halo_send_out, int64_t* halo_recv_out, int64_t* owned_asso_out);
 int sigsdp_solver_shard_arena(sigsdp_solver* s, void** dev_ptr, int64_t* bytes);
 int sigsdp_solver_shard_ipc_handle(sigsdp_solver* s, void* handle64_host);
 int sigsdp_solver_shard_attach_ipc(sigsdp_solver* s, const void* handles64_host);

@@ -51,6 +51,7 @@ def load():
         "sigsdp_solver_device_array": [vp, C.c_int, C.POINTER(vp), i64p],
         "sigsdp_solver_create_rows": [vp, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)],
         "sigsdp_solver_shard_info": [vp, i64p],
+        "sigsdp_plan_row_partition": [vp, C.c_int, C.c_int, C.c_int, C.c_int, i64p, i64p, i64p, i64p],
         "sigsdp_solver_shard_arena": [vp, C.POINTER(vp), i64p],
         "sigsdp_solver_shard_ipc_handle": [vp, vp],
         "sigsdp_solver_shard_attach_ipc": [vp, vp],
@@ -176,6 +177,15 @@ class Plan:
         out = np.zeros(6, np.int64)
         check(load().sigsdp_plan_tile_stats(self.handle, max_rows, ucap, nnzcap, _p(out, C.c_int64)))
         return dict(zip(["tiles", "runs", "staged_rows", "umax", "nnzmax", "nnz"], out.tolist()))
+
+    def row_partition(self, nranks, max_rows=0, ucap=0, nnzcap=0):
+        """The row partition of a row-sharded solver (host only): dict of row0 (nranks + 1), and per rank the
+        rows pushed per Taylor term, foreign rows read, association edges owned."""
+        row0 = np.zeros(nranks + 1, np.int64); send = np.zeros(nranks, np.int64)
+        recv = np.zeros(nranks, np.int64); owned = np.zeros(nranks, np.int64)
+        check(load().sigsdp_plan_row_partition(self.handle, int(nranks), int(max_rows), int(ucap), int(nnzcap), _p(row0, C.c_int64),
+                                               _p(send, C.c_int64), _p(recv, C.c_int64), _p(owned, C.c_int64)))
+        return dict(row0=row0, send=send, recv=recv, owned_asso=owned)
 
     def pattern(self):
         rp = np.empty(self.n + 1, np.int32); col = np.empty(self.nnz, np.int32)

@@ -881,23 +881,8 @@ static int solver_alloc(sigsdp_solver* s) {
     tile_lock.unlock();
     {
         const int nr = s->nranks;
-        // cut points: the boundary (tile start, or row when untiled) closest to r/nranks of the non-zeros
-        s->rank_row0.assign(nr + 1, 0);
-        std::vector<int32_t> cut_tile(nr + 1, 0);
-        const int nb = htiles ? htiles->ntiles : (int)n;
-        auto brow = [&](int b) { return htiles ? htiles->trow[b] : b; };
-        for (int r = 1; r < nr; ++r) {
-            const double target = (double)h.nnz * r / nr;
-            int lo = cut_tile[r - 1], hi = nb;
-            while (lo < hi) {   // first boundary whose cumulative non-zeros reach the target
-                const int mid = (lo + hi) / 2;
-                if ((double)h.rowptr[brow(mid)] < target) lo = mid + 1; else hi = mid;
-            }
-            cut_tile[r] = std::max(lo, cut_tile[r - 1]);
-            s->rank_row0[r] = brow(cut_tile[r]);
-        }
-        cut_tile[nr] = nb;
-        s->rank_row0[nr] = (int32_t)n;
+        std::vector<int32_t> cut_tile;
+        shard_cut_points(h, htiles, nr, s->rank_row0, cut_tile);
         s->row_lo = s->rank_row0[s->rank];
         s->row_hi = s->rank_row0[s->rank + 1];
         s->tile_lo = htiles ? cut_tile[s->rank] : 0;
@@ -913,48 +898,17 @@ static int solver_alloc(sigsdp_solver* s) {
         if (const char* e = getenv("SIGSDP_SHARD_TIMEOUT_S")) P.sh.timeout_ns = (unsigned long long)(atof(e) * 1e9);
         if (nr > 1) {
             if (s->row_hi <= s->row_lo) return fail(SIGSDP_EINVAL, "more ranks than row tiles: a rank would own no rows");
-            auto owner = [&](int32_t row) {
-                return (int)(std::upper_bound(s->rank_row0.begin() + 1, s->rank_row0.end(), row) - (s->rank_row0.begin() + 1));
-            };
-            std::vector<uint8_t> pmask(n, 0), seen(n, 0);
-            std::vector<int32_t> own_e, own_p, for_e, for_p;
-            long long send = 0, recv = 0;
-            for (int32_t k = s->row_lo; k < s->row_hi; ++k) {
-                unsigned m = 0;
-                for (int32_t p = h.rowptr[k]; p < h.rowptr[k + 1]; ++p) {
-                    const int32_t c = h.col[p];
-                    const bool own_c = c >= s->row_lo && c < s->row_hi;
-                    if (!own_c) {
-                        m |= 1u << owner(c);
-                        if (!seen[c]) {
-                            seen[c] = 1;
-                            ++recv;
-                        }
-                    }
-                    if (h.eid[p] >= h.E_g) {
-                        if (k < c) {
-                            own_e.push_back(h.eid[p] - (int32_t)h.E_g);
-                            own_p.push_back(p);
-                        } else if (!own_c) {
-                            for_e.push_back(h.eid[p] - (int32_t)h.E_g);
-                            for_p.push_back(p);
-                        }
-                    }
-                }
-                pmask[k] = (uint8_t)m;
-                send += __builtin_popcount(m);
-            }
-            s->halo_send_rows = send;
-            s->halo_recv_rows = recv;
-            s->n_inc_owned = (int)own_e.size();
-            own_e.insert(own_e.end(), for_e.begin(), for_e.end());
-            own_p.insert(own_p.end(), for_p.begin(), for_p.end());
-            s->n_inc = (int)own_e.size();
+            ShardHalo halo;
+            shard_halo(h, s->rank_row0, s->rank, halo);
+            s->halo_send_rows = halo.send;
+            s->halo_recv_rows = halo.recv;
+            s->n_inc_owned = halo.n_inc_owned;
+            s->n_inc = (int)halo.inc_e.size();
             uint8_t* d_pm;
             int32_t *d_ie, *d_ip;
-            CK(s->mem.upload(&d_pm, pmask));
-            CK(s->mem.upload(&d_ie, own_e));
-            CK(s->mem.upload(&d_ip, own_p));
+            CK(s->mem.upload(&d_pm, halo.pmask));
+            CK(s->mem.upload(&d_ie, halo.inc_e));
+            CK(s->mem.upload(&d_ip, halo.inc_p));
             P.sh.pmask = d_pm;
             P.sh.inc_e = d_ie;
             P.sh.inc_pos = d_ip;
@@ -1612,6 +1566,30 @@ int sigsdp_solver_device_array(sigsdp_solver* s, int which, void** dev_ptr, int6
         case SIGSDP_ARR_Y_AVGD: *dev_ptr = d ? s->p64.Ybar : s->p32.Ybar; *count = s->C; break;
         case SIGSDP_ARR_Y: *dev_ptr = d ? s->p64.Y : s->p32.Y; *count = s->C; break;
         default: return fail(SIGSDP_EINVAL, "unknown array id");
+    }
+    return SIGSDP_OK;
+}
+
+int sigsdp_plan_row_partition(sigsdp_plan* p, int nranks, int max_rows, int ucap, int nnzcap, int64_t* row0_out,
+                              int64_t* send_out, int64_t* recv_out, int64_t* owned_asso_out) {
+    if (!p || !row0_out || nranks < 1 || nranks > MAXR) return fail(SIGSDP_EINVAL, "bad argument");
+    HostTiles t;
+    const HostTiles* ht = nullptr;
+    if (max_rows > 0) {
+        if (ucap <= 0 || nnzcap <= 0) return fail(SIGSDP_EINVAL, "bad tile caps");
+        build_tiles(p->h, max_rows, ucap, nnzcap, t);
+        if (!t.ok) return fail(SIGSDP_EINVAL, "a row exceeds the tile caps");
+        ht = &t;
+    }
+    std::vector<int32_t> row0, tile0;
+    shard_cut_points(p->h, ht, nranks, row0, tile0);
+    for (int r = 0; r <= nranks; ++r) row0_out[r] = row0[r];
+    for (int r = 0; r < nranks && (send_out || recv_out || owned_asso_out); ++r) {
+        ShardHalo halo;
+        if (nranks > 1) shard_halo(p->h, row0, r, halo); else halo.n_inc_owned = (int)p->h.E_a;
+        if (send_out) send_out[r] = halo.send;
+        if (recv_out) recv_out[r] = halo.recv;
+        if (owned_asso_out) owned_asso_out[r] = halo.n_inc_owned;
     }
     return SIGSDP_OK;
 }

@@ -148,6 +148,64 @@ void locality_order_inputs(int64_t n, const int32_t* Sp, const int32_t* Si, cons
 }  // namespace
 
 
+void shard_cut_points(const HostPlan& P, const HostTiles* ht, int nranks, std::vector<int32_t>& row0,
+                      std::vector<int32_t>& tile0) {
+    const int nb = ht ? ht->ntiles : (int)P.n;
+    auto brow = [&](int b) { return ht ? ht->trow[b] : b; };
+    row0.assign(nranks + 1, 0);
+    tile0.assign(nranks + 1, 0);
+    for (int r = 1; r < nranks; ++r) {
+        const double target = (double)P.nnz * r / nranks;
+        int lo = tile0[r - 1], hi = nb;
+        while (lo < hi) {   // first boundary whose cumulative non-zeros reach the target
+            const int mid = (lo + hi) / 2;
+            if ((double)P.rowptr[brow(mid)] < target) lo = mid + 1; else hi = mid;
+        }
+        tile0[r] = std::max(lo, tile0[r - 1]);
+        row0[r] = brow(tile0[r]);
+    }
+    tile0[nranks] = nb;
+    row0[nranks] = (int32_t)P.n;
+}
+
+void shard_halo(const HostPlan& P, const std::vector<int32_t>& row0, int rank, ShardHalo& out) {
+    const int64_t n = P.n;
+    const int32_t lo = row0[rank], hi = row0[rank + 1];
+    auto owner = [&](int32_t row) { return (int)(std::upper_bound(row0.begin() + 1, row0.end(), row) - (row0.begin() + 1)); };
+    out = ShardHalo();
+    out.pmask.assign(n, 0);
+    std::vector<uint8_t> seen(n, 0);
+    std::vector<int32_t> for_e, for_p;
+    for (int32_t k = lo; k < hi; ++k) {
+        unsigned m = 0;
+        for (int32_t p = P.rowptr[k]; p < P.rowptr[k + 1]; ++p) {
+            const int32_t c = P.col[p];
+            const bool own_c = c >= lo && c < hi;
+            if (!own_c) {
+                m |= 1u << owner(c);
+                if (!seen[c]) {
+                    seen[c] = 1;
+                    ++out.recv;
+                }
+            }
+            if (P.eid[p] >= P.E_g) {
+                if (k < c) {
+                    out.inc_e.push_back(P.eid[p] - (int32_t)P.E_g);
+                    out.inc_p.push_back(p);
+                } else if (!own_c) {
+                    for_e.push_back(P.eid[p] - (int32_t)P.E_g);
+                    for_p.push_back(p);
+                }
+            }
+        }
+        out.pmask[k] = (uint8_t)m;
+        out.send += __builtin_popcount(m);
+    }
+    out.n_inc_owned = (int)out.inc_e.size();
+    out.inc_e.insert(out.inc_e.end(), for_e.begin(), for_e.end());
+    out.inc_p.insert(out.inc_p.end(), for_p.begin(), for_p.end());
+}
+
 void parallel_for(int64_t n, const std::function<void(int64_t, int64_t)>& fn, int64_t min_parallel) {
     parallel_rows(n, fn, min_parallel);
 }

@@ -66,6 +66,23 @@ struct HostTiles {
 };
 void build_tiles(const HostPlan& P, int max_rows, int ucap, int nnzcap, HostTiles& out);
 
+// Row sharding of one graph across `nranks` GPUs (include/sigsdp_mmw.h, "row sharding"): rank r owns the rows
+// [row0[r], row0[r+1]) -- whole tiles [tile0[r], tile0[r+1]) when the solver is tiled (ht != nullptr) -- cut where
+// the cumulative non-zeros reach r / nranks of the total.
+void shard_cut_points(const HostPlan& P, const HostTiles* ht, int nranks, std::vector<int32_t>& row0,
+                      std::vector<int32_t>& tile0);
+// What rank `rank` exchanges: pmask[k] (own rows: bit p set = rank p reads row k of the sketch block / r / q), the
+// association edges with an entry in an own row (the first n_inc_owned are owned: their row < col entry is in an
+// own row) with the position of that entry, rows pushed per Taylor term (row x destination pairs) and distinct
+// foreign rows read.
+struct ShardHalo {
+    std::vector<uint8_t> pmask;
+    std::vector<int32_t> inc_e, inc_p;
+    int n_inc_owned = 0;
+    long long send = 0, recv = 0;
+};
+void shard_halo(const HostPlan& P, const std::vector<int32_t>& row0, int rank, ShardHalo& out);
+
 // Copies a list of (dst, src, bytes) segments on the host's cores (1 MB chunks dealt to the
 // builder's threads): staging the plan arrays into pinned memory takes ~1.5 ms instead of ~7.
 struct CopySeg {

@@ -118,6 +118,22 @@ def main():
             check(state, Z, rr, eta, nit, om, *out, dtype)
             print("ROWSHARD OK dist case=%s world=%d dtype=%s info=%s" % (case, world, dtype, sh.solver.shard_info()))
         sh.barrier()
+        del sh
+        # the drop-in object end to end: every rank gets the factor a single GPU computes for the same device Omega
+        from sig_sdp_mmw_b200 import mmw
+        kw = dict(nit=nit, eta=eta, rank_radio=rr, dtype="float64" if dtype == "f64" else "float32", omega="device", device=local, seed=7)
+        ok, Xh = mmw(row_shard=True, **kw).run_with_state(0, Z, state)
+        assert ok and Xh.shape == (K, min(K - 1, (Z - 1) * rr))
+        G = Xh @ Xh.T if K <= 2000 else Xh[:500] @ Xh[:500].T
+        Gs = [None] * world
+        dist.all_gather_object(Gs, G)
+        assert all(np.allclose(g, Gs[0], atol=1e-9) for g in Gs), "ranks returned different factors"
+        if rank == 0:
+            _, Xh1 = mmw(**kw).run_with_state(0, Z, state)
+            G1 = Xh1 @ Xh1.T if K <= 2000 else Xh1[:500] @ Xh1[:500].T
+            np.testing.assert_allclose(G, G1, atol=1e-8 if dtype == "f64" else 5e-3)
+            print("ROWSHARD OK mmw(row_shard=True) case=%s world=%d" % (case, world))
+        dist.barrier()
         dist.destroy_process_group()
 
 

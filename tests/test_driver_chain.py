@@ -130,6 +130,75 @@ def test_batch_split_across_ranks_gloo_world2():
     assert work == 11.0 and t == 0.5 and ids == [1.0] * 11
 
 
+# ---- row sharding of one graph: the host side (partition + halo bookkeeping) needs no device
+@pytest.mark.parametrize("nranks,tiled", [(2, True), (3, False), (8, True)])
+def test_row_partition_covers_the_graph_and_halos_match(nranks, tiled):
+    """Strips are contiguous, cover every row once, are balanced by non-zeros; every association edge has exactly one
+    owner; what the ranks push per Taylor term is what the ranks read (pairs of row x reader)."""
+    from sig_sdp_mmw_b200 import _lib
+    from sig_sdp_mmw_b200.topology import sparse_env
+    state = sparse_env(cell_size=30, sta_density_per_1m2=75e-4, seed=2).generate_S_Q_hmax()     # 2,700 nodes
+    plan = _lib.Plan(state, device=-1, order=1)
+    part = plan.row_partition(nranks, *((32, 343, 2048) if tiled else (0, 0, 0)))
+    row0 = part["row0"]
+    assert row0[0] == 0 and row0[-1] == plan.n and np.all(np.diff(row0) > 0)
+    rp, col = plan.pattern()
+    nnz_rank = np.diff(rp[row0])
+    assert nnz_rank.max() <= 1.25 * plan.nnz / nranks
+    assert part["owned_asso"].sum() == plan.E_a
+    assert part["send"].sum() == part["recv"].sum() > 0
+    # recompute the halo of rank 0 from the pattern: distinct foreign columns of its rows
+    own = slice(rp[row0[0]], rp[row0[1]])
+    foreign = np.unique(col[own][(col[own] < row0[0]) | (col[own] >= row0[1])])
+    assert part["recv"][0] == foreign.size
+    if tiled:   # cuts fall on tile boundaries: every strip is a whole number of tiles of the same caps
+        stats = plan.tile_stats(32, 343, 2048)
+        assert stats["tiles"] >= nranks
+
+
+def _gloo_rowpart_worker(rank, world, port, out):
+    import torch
+    import torch.distributed as dist
+    from sig_sdp_mmw_b200 import _lib
+    from sig_sdp_mmw_b200.topology import sparse_env
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # every rank builds the plan of the same state on its own (as the row-sharded bench does) and must arrive
+    # at the same partition; what it owns is marked and summed over the ranks
+    state = sparse_env(cell_size=12, sta_density_per_1m2=75e-4, seed=4).generate_S_Q_hmax()
+    plan = _lib.Plan(state, device=-1, order=1)
+    part = plan.row_partition(world, 32, 343, 2048)
+    rows = torch.zeros(plan.n, dtype=torch.float64)
+    rows[int(part["row0"][rank]):int(part["row0"][rank + 1])] = 1.0
+    cuts = torch.from_numpy(part["row0"].astype(np.float64))
+    lo, hi = cuts.clone(), cuts.clone()
+    dist.all_reduce(rows, op=dist.ReduceOp.SUM)
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    mine = torch.tensor([float(part["send"][rank]), float(part["recv"][rank]), float(part["owned_asso"][rank])], dtype=torch.float64)
+    dist.all_reduce(mine, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        out.put((rows.tolist(), bool(torch.equal(lo, hi)), mine.tolist(), int(plan.E_a)))
+    dist.destroy_process_group()
+
+
+def test_row_partition_agrees_across_ranks_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 30500 + (os.getpid() % 1000)
+    procs = [ctx.Process(target=_gloo_rowpart_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    rows, same_cuts, sums, E_a = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert rows == [1.0] * len(rows) and same_cuts           # every row owned exactly once, identical cut points
+    assert sums[0] == sums[1] > 0 and sums[2] == E_a          # pushed = read; every association edge owned once
+
+
 # ------------------------------------------------------------------------------ GPU
 @pytest.mark.gpu
 def test_driver_chain_matches_reference_on_gpu():
