@@ -6,7 +6,7 @@ module produces the same `state = (S_gain, Q_asso, h_max)` from the same constru
 arguments and seed using a k-d tree over the access points, so only station/AP pairs
 within radio reach are ever touched: O(n * reach) time and memory, 100k+ stations in
 seconds.  For sizes the reference can build, the output matches it (same pattern, values
-to rounding): see tests/test_topology.py against the committed reference fixtures.
+to rounding): see tests/test_host_logic.py (test_sparse_topology_reproduces_reference_state, test_sparse_evaluate_sinr_bler_matches_reference) against the committed reference fixtures.
 
 Input generator only -- not on the solver's hot path."""
 import math
