@@ -288,6 +288,13 @@ int sigsdp_round_greedy(int64_t n, int Z,
                         int32_t* z_vec_host, int64_t* remainder);
 int sigsdp_round_conflicts(const sigsdp_plan* plan, const int32_t* z_dev, double* I_dev_or_null,
                            int64_t counts_host[2], void* stream);
+/* (2') The greedy pass of (2) on the device, with the SAME result as the sequential pass (sdp_solver.py:70-101): two
+ * users interact only if they are neighbours or share a neighbour in S_gain / Q_asso, so rounds of mutually
+ * non-interacting users -- each the lowest-ranked undecided user of its neighbourhood -- decide in parallel with the
+ * host pass's arithmetic, in the same order per accumulator.  rank_dev (n): visit order, rank_dev[i] = i-th user
+ * (argsort(-norm)); pref_dev: n x Z from sigsdp_round_project; z_dev (n): slot or -1.  Synchronises the stream. */
+int sigsdp_round_greedy_device(const sigsdp_plan* plan, int Z, const int32_t* rank_dev, const int32_t* pref_dev,
+                               int32_t* z_dev, int64_t* remainder_host, int64_t* rounds_host_or_null, void* stream);
 
 /* ------------------------------------------------------------------ batch ----
  * Monte-Carlo sweeps (sim_script/journal_version/sim_all_bler.py:30-40 run `for seed in

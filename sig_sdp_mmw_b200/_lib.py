@@ -83,6 +83,7 @@ def load():
         "sigsdp_round_project": [vp, vp, C.c_int, vp, C.c_int, vp, vp, vp],
         "sigsdp_round_greedy": [C.c_int64, C.c_int, i32p, i32p, f64p, i32p, i32p, f64p, f64p, i32p, i32p, i32p, i64p],
         "sigsdp_round_conflicts": [vp, vp, vp, i64p, vp],
+        "sigsdp_round_greedy_device": [vp, C.c_int, vp, vp, vp, i64p, i64p, vp],
     }
     for name, args in sigs.items():
         fn = getattr(lib, name)

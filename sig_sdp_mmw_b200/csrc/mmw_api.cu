@@ -103,6 +103,12 @@ struct sigsdp_plan {
     hvec<int32_t> hSp, hSi;
     hvec<double> hSx, hh;
     mutable bool conflict_ready = false;
+    // the same for the device greedy pass: S and Q rows in the caller's numbering
+    hvec<int32_t> hQp, hQi;
+    hvec<double> hQx;
+    mutable int *d_Sp = nullptr, *d_Si = nullptr, *d_Qp = nullptr, *d_Qi = nullptr;
+    mutable double *d_Sx = nullptr, *d_Qx = nullptr;
+    mutable bool greedy_ready = false;
     // row tiles per (max_rows, ucap, nnzcap), built on first use (see TileDev)
     struct TileCache {
         HostTiles h;
@@ -264,6 +270,127 @@ __global__ void k_round_conflicts(int n, const int* STp, const int* STi, const d
         if (vio) atomicAdd(&counts[0], vio);
         if (asso) atomicAdd(&counts[1], asso);
     }
+}
+
+// ---------------------------------------------------------------------------
+// Greedy rounding pass on the device (sdp_solver.py:70-101), reproducing the sequential result exactly.
+// The sequential pass visits the users in rank order; what user k reads and writes is confined to its
+// neighbourhood: gain_sum[z][c] for c in {k} U out(k) (out = row k of S), written by every user j with c in
+// out(j); slot[c] for c in out(k) U Q(k); asso_sum[z][c] for c in {k} U Q(k), written by every j with c in Q(j).
+// So two users interact only if they are neighbours or share a neighbour, and the sequential result is
+// reproduced by any schedule that decides the lower-ranked of two interacting users first.  Round by round:
+//   m_out[c] = least rank among the undecided users of {c} U in(c),  m_q[c] likewise over {c} U Q(c);
+//   user k is READY when its rank is the minimum of m_out over {k} U out(k) and of m_q over {k} U Q(k):
+//   no undecided user that interacts with it ranks lower.  Ready users touch disjoint neighbourhoods, so they
+//   decide and commit in parallel with the host pass's own arithmetic (the additions into gain_sum[z][c] come
+//   from the users of in(c) in rank order either way: bit-identical sums).
+// Rounds needed = longest rank-decreasing chain of interacting users: 110 at cfg4, 206 at cfg3.
+__global__ void k_greedy_init(int n, const int* order, int* rank_of, int* undec_rank, int* slot) {
+    for (int kk = blockIdx.x * blockDim.x + threadIdx.x; kk < n; kk += gridDim.x * blockDim.x) {
+        const int k = order[kk];
+        rank_of[k] = kk;
+        undec_rank[k] = kk;
+        slot[k] = -1;
+    }
+}
+// All rounds in one persistent cooperative launch (a round is three short grid-wide steps; as separate kernels the
+// pass was launch-bound: 80 us per round against ~20 here).
+struct GreedyArgs {
+    int n, Z;
+    const int *Sp, *Si, *STp, *STi, *Qp, *Qi;
+    const double *Sx, *Qx, *h_max;
+    const int *rank_of, *pref;
+    int *undec_rank, *m_out, *m_q, *ready_list, *ready_count, *slot;
+    double *gain_sum, *asso_sum;
+    unsigned long long* counters;   // [0] decided, [1] unassigned, [2] rounds
+};
+__global__ void __launch_bounds__(256) k_greedy_all(GreedyArgs a) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ int s_ok[8];
+    const int INF = 0x7fffffff;
+    const int n = a.n, Z = a.Z;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31;
+    unsigned long long rounds = 0;
+    for (;;) {
+        // (1) least undecided rank in every neighbourhood
+        if (tid == 0) *a.ready_count = 0;
+        for (int c = tid; c < n; c += nthr) {
+            int x = a.undec_rank[c], y = x;
+            for (int p = a.STp[c]; p < a.STp[c + 1]; ++p) x = min(x, a.undec_rank[a.STi[p]]);
+            for (int p = a.Qp[c]; p < a.Qp[c + 1]; ++p) y = min(y, a.undec_rank[a.Qi[p]]);
+            a.m_out[c] = x;
+            a.m_q[c] = y;
+        }
+        grid.sync();
+        // (2) ready users: nobody undecided that interacts with them ranks lower
+        for (int k = tid; k < n; k += nthr) {
+            if (a.undec_rank[k] == INF) continue;
+            const int rk = a.rank_of[k];
+            int lim = min(a.m_out[k], a.m_q[k]);
+            for (int q = a.Sp[k]; q < a.Sp[k + 1] && lim >= rk; ++q) {
+                const int c = a.Si[q];
+                if (c != k && a.Sx[q] != 0.0) lim = min(lim, a.m_out[c]);
+            }
+            for (int q = a.Qp[k]; q < a.Qp[k + 1] && lim >= rk; ++q) lim = min(lim, a.m_q[a.Qi[q]]);
+            if (lim >= rk) a.ready_list[atomicAdd(a.ready_count, 1)] = k;   // (list order is irrelevant: ready users do not interact)
+        }
+        grid.sync();
+        // (3) decision + commit, one block per ready user: its eight warps test eight slots of the user's
+        // preference order at once (read-only), the first feasible one in that order wins, then the block commits
+        // (the host pass's arithmetic: every accumulator gets the same additions in the same order; within one
+        // user's row the order is immaterial because a row holds every column once)
+        const int nready = *reinterpret_cast<volatile int*>(a.ready_count);
+        for (int i = blockIdx.x; i < nready; i += gridDim.x) {
+            const int k = a.ready_list[i];
+            const int s0 = a.Sp[k], s1 = a.Sp[k + 1], q0 = a.Qp[k], q1 = a.Qp[k + 1];
+            const int wrp = threadIdx.x >> 5;
+            int chosen = -1;
+            for (int base = 0; base < Z && chosen < 0; base += 8) {
+                const int zz = base + wrp;
+                bool ok = false;
+                if (zz < Z) {
+                    const int z = a.pref[(size_t)k * Z + zz];
+                    const double* gs = a.gain_sum + (size_t)z * n;
+                    const double* as = a.asso_sum + (size_t)z * n;
+                    bool vio = lane == 0 && (gs[k] > a.h_max[k] || as[k] >= 1.0);
+                    for (int q = s0 + lane; q < s1; q += 32) {
+                        const int c = a.Si[q];
+                        const double x = a.Sx[q];
+                        if (c != k && x != 0.0 && a.slot[c] == z) vio = vio || (gs[c] + x > a.h_max[c]);
+                    }
+                    for (int q = q0 + lane; q < q1; q += 32) {
+                        const int c = a.Qi[q];
+                        if (a.slot[c] == z) vio = vio || (as[c] + a.Qx[q] >= 1.0);
+                    }
+                    ok = !__any_sync(0xffffffffu, vio);
+                }
+                if (lane == 0) s_ok[wrp] = ok ? 1 : 0;
+                __syncthreads();
+                for (int w = 0; w < 8 && chosen < 0; ++w)
+                    if (s_ok[w]) chosen = a.pref[(size_t)k * Z + base + w];
+                __syncthreads();
+            }
+            if (chosen >= 0) {
+                double* gs = a.gain_sum + (size_t)chosen * n;
+                double* as = a.asso_sum + (size_t)chosen * n;
+                for (int q = s0 + threadIdx.x; q < s1; q += blockDim.x)
+                    if (a.Si[q] != k) gs[a.Si[q]] += a.Sx[q];
+                for (int q = q0 + threadIdx.x; q < q1; q += blockDim.x) as[a.Qi[q]] += a.Qx[q];
+            }
+            if (threadIdx.x == 0) {
+                a.slot[k] = chosen;
+                a.undec_rank[k] = INF;
+                atomicAdd(&a.counters[0], 1ull);
+                if (chosen < 0) atomicAdd(&a.counters[1], 1ull);
+            }
+        }
+        grid.sync();
+        ++rounds;
+        if (*reinterpret_cast<volatile unsigned long long*>(&a.counters[0]) >= (unsigned long long)n) break;
+        if (rounds > (unsigned long long)n) break;   // (cannot happen: the lowest-ranked undecided user is always ready)
+    }
+    if (tid == 0) a.counters[2] = rounds;
 }
 
 // ---------------------------------------------------------------------------
@@ -636,6 +763,9 @@ int sigsdp_plan_create(int64_t n, const int32_t* Sp, const int32_t* Si, const do
         pl->hSi.resize(Sp[n]);
         pl->hSx.resize(Sp[n]);
         pl->hh.resize(n);
+        pl->hQp.resize(n + 1);
+        pl->hQi.resize(Qp[n]);
+        pl->hQx.resize(Qp[n]);
         std::vector<CopySeg> segs;
         for (const Arr& a : arrs)
             if (a.bytes) segs.push_back(CopySeg{stage + a.off, a.src, a.bytes});
@@ -643,6 +773,9 @@ int sigsdp_plan_create(int64_t n, const int32_t* Sp, const int32_t* Si, const do
         segs.push_back(CopySeg{pl->hSi.data(), Si, (size_t)Sp[n] * 4});
         segs.push_back(CopySeg{pl->hSx.data(), Sx, (size_t)Sp[n] * 8});
         segs.push_back(CopySeg{pl->hh.data(), h_max, (size_t)n * 8});
+        segs.push_back(CopySeg{pl->hQp.data(), Qp, (size_t)(n + 1) * 4});
+        segs.push_back(CopySeg{pl->hQi.data(), Qi, (size_t)Qp[n] * 4});
+        segs.push_back(CopySeg{pl->hQx.data(), Qx, (size_t)Qp[n] * 8});
         parallel_copy(segs);
         tm.lap("stage + host copies");
         if ((e = cudaMemcpyAsync(slab, stage, total, cudaMemcpyHostToDevice, (cudaStream_t)0)) != cudaSuccess) return bail(e, "plan upload");
@@ -1864,6 +1997,70 @@ int sigsdp_round_conflicts(const sigsdp_plan* plan, const int32_t* z_dev, double
     return SIGSDP_OK;
 }
 
+
+// S / Q rows (caller numbering) for the device greedy pass, uploaded when it is first used
+static int ensure_greedy_data(const sigsdp_plan* pl) {
+    int rc = ensure_conflict_data(pl);   // S^T without its diagonal / zeros, h_max
+    if (rc != SIGSDP_OK) return rc;
+    std::lock_guard<std::mutex> lock(pl->lazy_mu);
+    if (pl->greedy_ready) return SIGSDP_OK;
+    DevArena& mem = const_cast<DevArena&>(pl->mem);
+    CK(mem.upload(&pl->d_Sp, pl->hSp));
+    CK(mem.upload(&pl->d_Si, pl->hSi));
+    CK(mem.upload(&pl->d_Sx, pl->hSx));
+    CK(mem.upload(&pl->d_Qp, pl->hQp));
+    CK(mem.upload(&pl->d_Qi, pl->hQi));
+    CK(mem.upload(&pl->d_Qx, pl->hQx));
+    pl->greedy_ready = true;
+    return SIGSDP_OK;
+}
+
+int sigsdp_round_greedy_device(const sigsdp_plan* plan, int Z, const int32_t* rank_dev, const int32_t* pref_dev,
+                               int32_t* z_dev, int64_t* remainder_host, int64_t* rounds_host, void* stream) {
+    if (!plan || !rank_dev || !pref_dev || !z_dev || !remainder_host || Z < 1) return fail(SIGSDP_EINVAL, "bad argument");
+    if (plan->device < 0) return fail(SIGSDP_EINVAL, "host-only plan");
+    CK(cudaSetDevice(plan->device));
+    {
+        int rc = ensure_greedy_data(plan);
+        if (rc != SIGSDP_OK) return rc;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = (int)plan->h.n;
+    int *rank_of = nullptr, *undec = nullptr, *m_out = nullptr, *m_q = nullptr, *ready = nullptr, *nready = nullptr;
+    double *gs = nullptr, *as = nullptr;
+    unsigned long long* counters = nullptr;
+    CK(cudaMallocAsync(&rank_of, ((size_t)n * 5 + 8) * sizeof(int), st));
+    undec = rank_of + n;
+    m_out = undec + n;
+    m_q = m_out + n;
+    ready = m_q + n;
+    nready = ready + n;
+    CK(cudaMallocAsync(&gs, (size_t)2 * Z * n * sizeof(double), st));
+    as = gs + (size_t)Z * n;
+    CK(cudaMallocAsync(&counters, 4 * sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(gs, 0, (size_t)2 * Z * n * sizeof(double), st));
+    CK(cudaMemsetAsync(counters, 0, 4 * sizeof(unsigned long long), st));
+    k_greedy_init<<<plan->num_sms * 4, 256, 0, st>>>(n, rank_dev, rank_of, undec, z_dev);
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_greedy_all, 256, 0));
+    const int blocks = std::max(1, std::min(plan->num_sms * std::max(1, std::min(occ, 4)), (n + 255) / 256));
+    GreedyArgs ga{n, Z, plan->d_Sp, plan->d_Si, plan->d_STp, plan->d_STi, plan->d_Qp, plan->d_Qi, plan->d_Sx, plan->d_Qx,
+                  plan->d_hmax_caller, rank_of, pref_dev, undec, m_out, m_q, ready, nready, z_dev, gs, as, counters};
+    void* kargs[] = {(void*)&ga};
+    cudaError_t e = cudaLaunchCooperativeKernel((void*)k_greedy_all, dim3(blocks), dim3(256), kargs, 0, st);
+    unsigned long long hc[3] = {0, 0, 0};
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hc, counters, sizeof(hc), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    const int64_t rounds = (int64_t)hc[2];
+    cudaFreeAsync(counters, st);
+    cudaFreeAsync(gs, st);
+    cudaFreeAsync(rank_of, st);
+    if (e != cudaSuccess) return fail(SIGSDP_ECUDA, cudaGetErrorString(e));
+    if (hc[0] < (unsigned long long)n) return fail(SIGSDP_EINVAL, "device greedy pass made no progress (rank is not a permutation?)");
+    *remainder_host = (int64_t)hc[1];
+    if (rounds_host) *rounds_host = rounds;
+    return SIGSDP_OK;
+}
 
 // ---- batch -------------------------------------------------------------------
 int sigsdp_batch_create(sigsdp_solver* const* solvers, int count, sigsdp_batch** out) {

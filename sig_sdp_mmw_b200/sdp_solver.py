@@ -2,7 +2,8 @@
 (sim_src/alg/sdp_solver.py:9-107).  The arithmetic runs in libsigsdp_mmw.so:
 
   * sigsdp_round_project  (device): randv gX^T, per-user slot preference order, ||gX_k||
-  * sigsdp_round_greedy   (native host pass): the sequential feasibility assignment
+  * sigsdp_round_greedy_device (device): the sequential feasibility assignment, reproduced exactly by
+    rounds of mutually non-interacting users (sigsdp_round_greedy: the same pass sequentially on the host)
   * sigsdp_round_conflicts(device): same-slot interference / violation / asso-conflict counts
 
 The random draws (np.random.randn for the directions, np.random.randint for the
@@ -53,6 +54,12 @@ class sdp_solver:
     # set by subclasses / callers
     device = 0
     plan_order = 0
+    # the greedy pass of the rounding: "device" (rounds of mutually non-interacting users, sigsdp_round_greedy_device),
+    # "host" (the same pass sequentially in native code, sigsdp_round_greedy) or "auto": both give the same colours
+    # bit for bit; the device wins on large graphs (100k nodes: 6.6 ms against 30 ms), the host on small ones where
+    # the number of rounds (82-206), not the work, sets the time
+    greedy = "auto"
+    GREEDY_DEVICE_MIN_NODES = 50000
 
     def run_with_state(self, bs_iteration, Z, state):
         pass
@@ -105,16 +112,29 @@ class sdp_solver:
             _lib.check(lib.sigsdp_round_project(plan.handle, gX_d.data_ptr(), D, rv_d.data_ptr(), Z,
                                                 pref_d.data_ptr(), norm_d.data_ptr(), stream))
             # visit order argsort(-||gX_k||) (:52); stable so equal norms keep index order
-            rank = torch.argsort(-norm_d, stable=True).to(torch.int32).cpu().numpy()
-            pref = pref_d.cpu().numpy()
-        z_int = np.empty(K, np.int32)
-        rem = C.c_int64()
-        S, Q, h = plan._S, plan._Q, plan._h
-        _lib.check(lib.sigsdp_round_greedy(K, Z, _lib._p(S[0], C.c_int32), _lib._p(S[1], C.c_int32), _lib._p(S[2], C.c_double),
-                                           _lib._p(Q[0], C.c_int32), _lib._p(Q[1], C.c_int32), _lib._p(Q[2], C.c_double),
-                                           _lib._p(h, C.c_double), _lib._p(rank, C.c_int32),
-                                           _lib._p(np.ascontiguousarray(pref), C.c_int32), _lib._p(z_int, C.c_int32),
-                                           C.byref(rem)))
+            rank_d = torch.argsort(-norm_d, stable=True).to(torch.int32)
+            rem = C.c_int64()
+            on_device = self.greedy == "device" or (self.greedy == "auto" and K >= self.GREEDY_DEVICE_MIN_NODES)
+            if on_device:
+                # the sequential feasibility pass (:70-101) as rounds of mutually non-interacting users on the
+                # device: same result, no n x Z preference table over PCIe (sigsdp_round_greedy_device)
+                z_d = torch.empty(K, dtype=torch.int32, device=dev)
+                rounds = C.c_int64()
+                _lib.check(lib.sigsdp_round_greedy_device(plan.handle, Z, rank_d.data_ptr(), pref_d.data_ptr(), z_d.data_ptr(),
+                                                          C.byref(rem), C.byref(rounds), stream))
+                z_int = z_d.cpu().numpy()
+                self.last_greedy_rounds = int(rounds.value)
+            else:
+                rank = rank_d.cpu().numpy()
+                pref = pref_d.cpu().numpy()
+        if not on_device:
+            z_int = np.empty(K, np.int32)
+            S, Q, h = plan._S, plan._Q, plan._h
+            _lib.check(lib.sigsdp_round_greedy(K, Z, _lib._p(S[0], C.c_int32), _lib._p(S[1], C.c_int32), _lib._p(S[2], C.c_double),
+                                               _lib._p(Q[0], C.c_int32), _lib._p(Q[1], C.c_int32), _lib._p(Q[2], C.c_double),
+                                               _lib._p(h, C.c_double), _lib._p(rank, C.c_int32),
+                                               _lib._p(np.ascontiguousarray(pref), C.c_int32), _lib._p(z_int, C.c_int32),
+                                               C.byref(rem)))
         z_vec = z_int.astype(np.float64)
         not_assigned = z_int < 0
         z_vec[not_assigned] = 0.0

@@ -142,3 +142,26 @@ def test_batch_kernel_matches_oracle_on_exported_normals(dtype, code, tol, block
             _assert_state_close(sol, st, tol)
         else:
             _assert_fp32_close(sol, st)
+
+
+@pytest.mark.parametrize("kw,Z", [(dict(cell_size=63, sta_density_per_1m2=125e-4, seed=0), 16),     # cfg3 size, dense-ish
+                                  (dict(cell_size=30, sta_density_per_1m2=75e-4, seed=1), 6)])      # few slots: many users stay unassigned
+def test_device_greedy_pass_reproduces_the_sequential_pass(kw, Z):
+    """sigsdp_round_greedy_device against the sequential host pass (itself pinned to the reference's rounding on
+    its own seeds, tests/test_host_logic.py): bit-identical colours and remainder for the same factor and directions."""
+    _require_gpu()
+    from sig_sdp_mmw_b200 import rand_sdp_solver
+    state = sparse_env(**kw).generate_S_Q_hmax()
+    K = state[0].shape[0]
+    gX = np.random.RandomState(5).randn(K, 2 * Z)
+    out = {}
+    for mode in ("device", "host"):
+        alg = rand_sdp_solver()
+        alg.greedy = mode
+        np.random.seed(11)
+        out[mode] = alg.rounding_one_attempt(Z, gX, state)
+        if mode == "device":
+            rounds = alg.last_greedy_rounds
+    np.testing.assert_array_equal(out["device"][0], out["host"][0])
+    assert out["device"][2] == out["host"][2]
+    assert 1 <= rounds <= K
