@@ -246,13 +246,17 @@ def test_solver_object_matches_reference_outputs(name):
     if g["log_gap"]:
         gap = alg.LOGGED_NP_DATA["gap"][:, 3:]
         np.testing.assert_allclose(gap, g["gap"], rtol=1e-8, atol=1e-9)
-    # rounding from the reference's factor on the reference's seeds
-    for seed, z_ref, rem_ref in zip(g["round_seeds"], g["round_z"], g["round_rem"]):
-        np.random.seed(int(seed))
-        z, Z, rem = alg.rounding(g["Z"], g["X_half"], g["state"])
-        assert Z == g["Z"] and rem == int(rem_ref)
-        assert z.dtype == np.float64
-        np.testing.assert_array_equal(z, z_ref)
+    # rounding from the reference's factor on the reference's seeds: the sequential host pass and the device
+    # rounds (sigsdp_round_greedy_device) must both reproduce the reference's colouring exactly
+    for mode in ("host", "device"):
+        alg.greedy = mode
+        for seed, z_ref, rem_ref in zip(g["round_seeds"], g["round_z"], g["round_rem"]):
+            np.random.seed(int(seed))
+            z, Z, rem = alg.rounding(g["Z"], g["X_half"], g["state"])
+            assert Z == g["Z"] and rem == int(rem_ref)
+            assert z.dtype == np.float64
+            np.testing.assert_array_equal(z, z_ref)
+    alg.greedy = "auto"
     np.random.seed(2000)
     z, _, rem = alg.rounding_one_attempt(g["Z"], g["X_half"], g["state"])
     assert rem == int(g["round1_rem"])
