@@ -199,6 +199,13 @@ int sigsdp_solver_get_sketch(sigsdp_solver* s, double* Yh_host);
  * every entry -- e.g. the sum of the row shards' fetches, before the final factor. */
 int sigsdp_solver_set_X(sigsdp_solver* s, int averaged, const double* diag_host, const double* gain_host,
                         const double* asso_host);
+/* Warm start across the probes of the binary search (binary_search_relaxation.py:44-71 solves the same state for a
+ * sequence of Z): the constraint vector [D | F | H] has the same shape for every Z, so the accumulated constraint
+ * losses e_accu, the dual weights Y and the soft-max shift of `src` (a solver of the SAME plan, any Z / D / dtype,
+ * row shards excluded) become the initial dual state of `dst` instead of e_accu = 0, Y = 1/C (mmw.py:60-62).  `dst`
+ * must not have iterated since its creation / reset; L_accu, X and the running sums start as usual.  Device-to-device,
+ * asynchronous on `stream`.  Not something the reference does: off by default in the drop-in object. */
+int sigsdp_solver_warm_start(sigsdp_solver* dst, const sigsdp_solver* src, void* stream);
 /* Per-iteration Taylor controller history of the last `count` iterations
  * (scipy _expm_multiply.py:259-303, _fragment_3_1 :503-558): m_star, s, executed
  * terms (int32 each) and ||A - mu I||_1, mu (fp64 each).  Any pointer may be NULL. */

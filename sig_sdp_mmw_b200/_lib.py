@@ -58,6 +58,7 @@ def load():
         "sigsdp_solver_shard_attach_local": [C.POINTER(vp), C.c_int],
         "sigsdp_solver_set_X": [vp, C.c_int, f64p, f64p, f64p],
         "sigsdp_solver_reset": [vp, vp],
+        "sigsdp_solver_warm_start": [vp, vp, vp],
         "sigsdp_solver_set_mode": [vp, C.c_int],
         "sigsdp_solver_info": [vp, i64p],
         "sigsdp_solver_iterate": [vp, C.c_int, vp, C.c_uint64, vp],
@@ -240,6 +241,10 @@ class Solver:
 
     def iterate(self, n_iters, omega_dev_ptr=None, seed=0, stream=None):
         check(load().sigsdp_solver_iterate(self.handle, int(n_iters), omega_dev_ptr, int(seed), stream))
+
+    def warm_start(self, src, stream=None):
+        """Initial dual state (e_accu, Y, soft-max shift) from another solver of the same plan."""
+        check(load().sigsdp_solver_warm_start(self.handle, src.handle, stream))
 
     def split_step(self, do_iter=True, omega_dev_ptr=None, seed=0, stream=None):
         check(load().sigsdp_solver_split_step(self.handle, int(bool(do_iter)), omega_dev_ptr, int(seed), stream))

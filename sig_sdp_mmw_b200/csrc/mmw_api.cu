@@ -1629,6 +1629,28 @@ int sigsdp_solver_get_sketch(sigsdp_solver* s, double* Yh) {
     return SIGSDP_OK;
 }
 
+__global__ void k_copy_shift(Ctrl* dst, const Ctrl* src) { dst->smax_shift = src->smax_shift; }
+
+int sigsdp_solver_warm_start(sigsdp_solver* dst, const sigsdp_solver* src, void* stream) {
+    if (!dst || !src) return fail(SIGSDP_EINVAL, "null solver");
+    if (dst->plan != src->plan) return fail(SIGSDP_EINVAL, "warm start needs two solvers of the same plan");
+    if (dst->nranks > 1 || src->nranks > 1) return fail(SIGSDP_EINVAL, "warm start is not available for row shards");
+    if (dst->iters_done != 0) return fail(SIGSDP_ESTATE, "the warm-started solver has already iterated");
+    if (src->pending_finish) return fail(SIGSDP_ESTATE, "the source solver has an unfinished Gram (column shard)");
+    CK(cudaSetDevice(dst->plan->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool dd = dst->dtype == SIGSDP_F64, sd = src->dtype == SIGSDP_F64;
+    double* de = dd ? dst->p64.e_acc : dst->p32.e_acc;
+    double* dy = dd ? dst->p64.Y : dst->p32.Y;
+    const double* se = sd ? src->p64.e_acc : src->p32.e_acc;
+    const double* sy = sd ? src->p64.Y : src->p32.Y;
+    CK(cudaMemcpyAsync(de, se, (size_t)dst->C * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(dy, sy, (size_t)dst->C * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    k_copy_shift<<<1, 1, 0, st>>>(dd ? dst->p64.ctrl : dst->p32.ctrl, sd ? src->p64.ctrl : src->p32.ctrl);
+    CK(cudaGetLastError());
+    return SIGSDP_OK;
+}
+
 int sigsdp_solver_get_history(sigsdp_solver* s, int count, int32_t* m_star, int32_t* ss, int32_t* nterms,
                               double* a1norm, double* mu) {
     if (!s) return fail(SIGSDP_EINVAL, "null solver");

@@ -15,6 +15,9 @@ has no notion of (all default to the reference's behaviour):
   device  : CUDA device index
   order   : 1 (default) renumber nodes inside the kernels for locality (transparent: all
             inputs and outputs stay in the caller's numbering), 0 keep the caller's order
+  warm_start : True -- successive run_with_state calls on the SAME state (the probes of the binary
+            search, binary_search_relaxation.py:44-71) start from the previous call's dual state (e_accu, Y)
+            instead of e_accu = 0, Y = 1/C; not something the reference does, off by default
   row_shard : True -- the process is one rank of a torch.distributed job (one process per
             GPU) and the ranks solve ONE graph together, each owning a strip of rows
             (sig_sdp_mmw_b200/rowshard.py, BASELINE configs[3]); every rank passes the same
@@ -37,7 +40,8 @@ _OMEGA_CHUNK_BYTES = 1 << 30
 
 class mmw(STATS_OBJECT, sdp_solver):
     def __init__(self, nit=100, rank_radio=2, alpha=1., eta=0.1, log_gap=False,
-                 dtype="float64", omega="numpy", device=0, order=1, seed=0, row_shard=False, shard_group=None):
+                 dtype="float64", omega="numpy", device=0, order=1, seed=0, row_shard=False, shard_group=None,
+                 warm_start=False):
         sdp_solver.__init__(self, nit=nit, rank_radio=rank_radio, alpha=alpha)
         self.eta = eta
         self.LOG_GAP = log_gap
@@ -50,6 +54,7 @@ class mmw(STATS_OBJECT, sdp_solver):
         self.eig_tol = 1e-10          # relative residual of the final factor's eigenpairs
         self.row_shard = bool(row_shard)
         self.shard_group = shard_group
+        self.warm_start = bool(warm_start)
         self.last_solver = None
 
     def run_with_state(self, bs_iteration, Z, state):
@@ -164,6 +169,9 @@ class mmw(STATS_OBJECT, sdp_solver):
             solver = shard.solver
         else:
             solver = _lib.Solver(plan, Z, D, self.eta, self._dtype_code(), self.mode)
+            prev = self.last_solver
+            if self.warm_start and prev is not None and prev.plan is plan and prev.rows is None and prev.D_total == prev.D:
+                solver.warm_start(prev)
         self.last_solver = solver
         dev = torch.device("cuda", plan.device)
         self._add_np_log("mmw_state_process", 0, np.array([Z, K, self._get_tim(sp_tic)]))

@@ -407,6 +407,47 @@ def test_lanczos_on_disconnected_graph_matches_dense():
     assert float((Gd_ref(V_d, lam_d) - Gd_ref(V_l, lam_l)).abs().max()) < 1e-8
 
 
+def test_warm_start_across_probes():
+    """sigsdp_solver_warm_start: the dual state of one probe seeds the next (same plan, another Z)."""
+    g = load_case("n300_z10")
+    K = g["state"][0].shape[0]
+    plan = _lib.Plan(g["state"], device=0, order=1)
+    om = np.random.RandomState(1).randn(10, K, 2 * 9)
+    om_d = torch.from_numpy(om).cuda()
+    # from a solver that has not iterated: identical to a cold start, bit for bit
+    cold, fresh, warm0 = (_lib.Solver(plan, 9, 18, g["eta"]) for _ in range(3))
+    warm0.warm_start(fresh)
+    for s_ in (cold, warm0):
+        s_.iterate(10, om_d.data_ptr(), 0, None)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(warm0.dual()[0], cold.dual()[0])
+    # from the previous probe (Z = 10): the weights start where that probe ended
+    prev = _lib.Solver(plan, 10, 20, g["eta"])
+    prev.iterate(30, None, 3, None)
+    torch.cuda.synchronize()
+    Yp, ep, _ = prev.dual()
+    warm = _lib.Solver(plan, 9, 18, g["eta"])
+    warm.warm_start(prev)
+    Y0, e0, _ = warm.dual()
+    np.testing.assert_array_equal(e0, ep)
+    np.testing.assert_array_equal(Y0, Yp)
+    warm.iterate(10, om_d.data_ptr(), 0, None)
+    torch.cuda.synchronize()
+    Y, e_acc, Ybar = warm.dual()
+    assert np.isfinite(Y).all() and abs(Y.sum() - 1.0) < 1e-12 and np.all(Y > 0)
+    assert np.abs(e_acc - ep).max() > 0 and abs(Ybar.sum() - 10.0) < 1e-9        # Y_avgd = Y_prev(warm) + 9 more weights
+    assert np.abs(Y - cold.dual()[0]).max() > 1e-6                               # and it is a different trajectory
+    with pytest.raises(_lib.SigSdpError):
+        warm.warm_start(prev)                                                    # only before the first iteration
+    # the drop-in object: second call on the same state starts warm
+    alg = mmw(nit=20, eta=g["eta"], omega="device", warm_start=True)
+    _, X1 = alg.run_with_state(0, 10, g["state"])
+    first = alg.last_solver
+    _, X2 = alg.run_with_state(1, 9, g["state"])
+    assert np.isfinite(X2).all() and alg.last_solver is not first
+    assert np.abs(alg.last_solver.dual()[1]).max() > np.abs(first.dual()[1]).max() * 0.5
+
+
 # --------------------------------------------------- size-independent properties
 def test_properties_at_5k_nodes():
     """cfg2-sized graph (5,000 nodes): invariants that need no oracle run."""
