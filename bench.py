@@ -380,7 +380,7 @@ def run_ours(args):
     dt_code = _lib.F64 if dtype == "float64" else _lib.F32
     w = 8 if dtype == "float64" else 4
     t0 = time.perf_counter()
-    plan = _lib.Plan(state, device=local, order=args.order)
+    plan = _lib.Plan.collective(state, local, args.order) if rows else _lib.Plan(state, device=local, order=args.order)
     plan_s = time.perf_counter() - t0
     stream = torch.cuda.current_stream().cuda_stream
     shard = None

@@ -68,6 +68,18 @@ int sigsdp_plan_create(int64_t n,
                        const int32_t* Q_indptr_host, const int32_t* Q_indices_host, const double* Q_data_host,
                        const double* h_max_host, int device, int order, sigsdp_plan** out);
 void sigsdp_plan_destroy(sigsdp_plan* plan);
+/* A built plan as a flat byte image, and a plan created from such an image plus the SAME state: in a multi-GPU launch
+ * (one process per GPU on one box) ONE process builds the plan on all host cores and ships the image (a broadcast by
+ * the host language) instead of every process building the same plan side by side on a share of the cores.  The
+ * image only skips the host build; the inputs are still needed (host copies for the rounding entry points).  An
+ * image that does not describe an n-node plan is rejected (SIGSDP_EINVAL). */
+int sigsdp_plan_image_size(const sigsdp_plan* plan, int64_t* bytes);
+int sigsdp_plan_image(const sigsdp_plan* plan, void* image_host);
+int sigsdp_plan_create_from_image(int64_t n,
+                                  const int32_t* S_indptr_host, const int32_t* S_indices_host, const double* S_data_host,
+                                  const int32_t* Q_indptr_host, const int32_t* Q_indices_host, const double* Q_data_host,
+                                  const double* h_max_host, const void* image_host, int64_t image_bytes, int device,
+                                  sigsdp_plan** out);
 
 /* info[0..7] = n, E_gain, E_asso, nnzL (= n + 2 E), nnz(T), device, order, max row length */
 int sigsdp_plan_info(const sigsdp_plan* plan, int64_t info[8]);

@@ -39,6 +39,9 @@ def load():
     lib.sigsdp_device_count.restype = C.c_int
     sigs = {
         "sigsdp_plan_create": [C.c_int64, i32p, i32p, f64p, i32p, i32p, f64p, f64p, C.c_int, C.c_int, C.POINTER(vp)],
+        "sigsdp_plan_image_size": [vp, i64p],
+        "sigsdp_plan_image": [vp, vp],
+        "sigsdp_plan_create_from_image": [C.c_int64, i32p, i32p, f64p, i32p, i32p, f64p, f64p, vp, C.c_int64, C.c_int, C.POINTER(vp)],
         "sigsdp_plan_info": [vp, i64p],
         "sigsdp_plan_edges": [vp, i32p, i32p, f64p, f64p, i32p, i32p],
         "sigsdp_plan_vectors": [vp, f64p, f64p],
@@ -126,7 +129,8 @@ def csr_arrays(M, canonicalize=True):
 class Plan:
     """Graph plan (Z-independent), see sigsdp_plan_create."""
 
-    def __init__(self, state, device=0, order=0):
+    def __init__(self, state, device=0, order=0, image=None):
+        """image: a plan image (Plan.image()) of the same state built elsewhere: skips the host build."""
         lib = load()
         S, Q, h = state
         n = S.shape[0]
@@ -134,6 +138,16 @@ class Plan:
             raise ValueError("state must be (S_gain n x n, Q_asso n x n, h_max (n,))")
         self._h = np.ascontiguousarray(np.asarray(h, dtype=np.float64))
         self.handle = C.c_void_p()
+        if image is not None:
+            self._S = csr_arrays(S, True)
+            self._Q = csr_arrays(Q, True)
+            img = np.ascontiguousarray(image, dtype=np.uint8)
+            check(lib.sigsdp_plan_create_from_image(n, _p(self._S[0], C.c_int32), _p(self._S[1], C.c_int32), _p(self._S[2], C.c_double),
+                                                    _p(self._Q[0], C.c_int32), _p(self._Q[1], C.c_int32), _p(self._Q[2], C.c_double),
+                                                    _p(self._h, C.c_double), img.ctypes.data_as(C.c_void_p), img.size, device,
+                                                    C.byref(self.handle)))
+            self._read_info()
+            return
         for canonicalize in (False, True):
             self._S = csr_arrays(S, canonicalize)
             self._Q = csr_arrays(Q, canonicalize)
@@ -143,17 +157,62 @@ class Plan:
             if rc == 0 or canonicalize or b"sorted and duplicate-free" not in lib.sigsdp_last_error():
                 break      # (non-canonical input: second pass on a canonicalised copy)
         check(rc)
+        self._read_info()
+
+    def _read_info(self):
         info = (C.c_int64 * 8)()
-        check(lib.sigsdp_plan_info(self.handle, info))
+        check(load().sigsdp_plan_info(self.handle, info))
         self.n, self.E_g, self.E_a, self.nnz, self.nnzT, self.device, self.order, self.max_row = [int(x) for x in info]
 
-    def __del__(self):
-        try:
-            if getattr(self, "handle", None):
-                load().sigsdp_plan_destroy(self.handle)
-                self.handle = None
-        except Exception:
-            pass
+    def image(self):
+        """The built plan as a flat uint8 array (sigsdp_plan_image), for Plan(state, image=...) in another process."""
+        nb = C.c_int64()
+        check(load().sigsdp_plan_image_size(self.handle, C.byref(nb)))
+        buf = np.empty(int(nb.value), np.uint8)
+        check(load().sigsdp_plan_image(self.handle, buf.ctypes.data_as(C.c_void_p)))
+        return buf
+
+    @staticmethod
+    def collective(state, device, order=1, group=None, min_world=4):
+        """One plan per rank of a torch.distributed job on one box.  With few ranks every rank builds its own (the
+        cores are shared: 8 each at 2 ranks); from `min_world` ranks on, rank 0 builds it ONCE on all host cores and
+        the image travels by broadcast (NCCL: pinned host -> device -> peers -> pinned host), which the other ranks
+        import -- instead of 8 builds side by side on 2 cores each."""
+        import torch
+        import torch.distributed as dist
+        world = dist.get_world_size(group)
+        if world < min_world:
+            return Plan(state, device=device, order=order)
+        rank = dist.get_rank(group)
+        nccl = dist.get_backend(group) == "nccl"
+        dev = torch.device("cuda", device) if nccl else torch.device("cpu")
+        src = dist.get_global_rank(group, 0) if group is not None else 0
+        lib = load()
+        if rank == 0:
+            keep = os.environ.pop("LOCAL_WORLD_SIZE", None)     # the other ranks wait: rank 0 may use every core
+            try:
+                plan = Plan(state, device=device, order=order)
+            finally:
+                if keep is not None:
+                    os.environ["LOCAL_WORLD_SIZE"] = keep
+            nb = C.c_int64()
+            check(lib.sigsdp_plan_image_size(plan.handle, C.byref(nb)))
+            size = torch.tensor([int(nb.value)], dtype=torch.int64, device=dev)
+            dist.broadcast(size, src=src, group=group)
+            img = torch.empty(int(nb.value), dtype=torch.uint8, pin_memory=nccl)
+            check(lib.sigsdp_plan_image(plan.handle, C.c_void_p(img.data_ptr())))
+            dist.broadcast(img.to(dev, non_blocking=True) if nccl else img, src=src, group=group)
+            return plan
+        size = torch.zeros(1, dtype=torch.int64, device=dev)
+        dist.broadcast(size, src=src, group=group)
+        img = torch.empty(int(size.item()), dtype=torch.uint8, device=dev)
+        dist.broadcast(img, src=src, group=group)
+        if nccl:
+            host = torch.empty(img.numel(), dtype=torch.uint8, pin_memory=True)
+            host.copy_(img)
+            torch.cuda.current_stream().synchronize()
+            img = host
+        return Plan(state, device=device, order=order, image=img.numpy())
 
     def edges(self):
         gi = np.empty(self.E_g, np.int32); gj = np.empty(self.E_g, np.int32)

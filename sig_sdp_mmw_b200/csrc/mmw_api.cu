@@ -688,6 +688,9 @@ int sigsdp_device_count(void) {
     return n;
 }
 
+static int plan_finish(sigsdp_plan* pl, int64_t n, const int32_t* Sp, const int32_t* Si, const double* Sx, const int32_t* Qp,
+                       const int32_t* Qi, const double* Qx, const double* h_max, int device, sigsdp_plan** out);
+
 int sigsdp_plan_create(int64_t n, const int32_t* Sp, const int32_t* Si, const double* Sx, const int32_t* Qp,
                        const int32_t* Qi, const double* Qx, const double* h_max, int device, int order,
                        sigsdp_plan** out) {
@@ -702,6 +705,40 @@ int sigsdp_plan_create(int64_t n, const int32_t* Sp, const int32_t* Si, const do
         return fail(rc, err);
     }
     tm.lap("host plan");
+    return plan_finish(pl, n, Sp, Si, Sx, Qp, Qi, Qx, h_max, device, out);
+}
+
+int sigsdp_plan_image_size(const sigsdp_plan* plan, int64_t* bytes) {
+    if (!plan || !bytes) return fail(SIGSDP_EINVAL, "null argument");
+    *bytes = (int64_t)host_plan_image_bytes(plan->h);
+    return SIGSDP_OK;
+}
+
+int sigsdp_plan_image(const sigsdp_plan* plan, void* image_host) {
+    if (!plan || !image_host) return fail(SIGSDP_EINVAL, "null argument");
+    host_plan_to_image(plan->h, static_cast<unsigned char*>(image_host));
+    return SIGSDP_OK;
+}
+
+int sigsdp_plan_create_from_image(int64_t n, const int32_t* Sp, const int32_t* Si, const double* Sx, const int32_t* Qp,
+                                  const int32_t* Qi, const double* Qx, const double* h_max, const void* image_host,
+                                  int64_t image_bytes, int device, sigsdp_plan** out) {
+    if (!out) return fail(SIGSDP_EINVAL, "out is null");
+    *out = nullptr;
+    if (!Sp || !Si || !Sx || !Qp || !Qi || !Qx || !h_max || !image_host || image_bytes <= 0) return fail(SIGSDP_EINVAL, "null argument");
+    sigsdp_plan* pl = new sigsdp_plan();
+    std::string err;
+    if (!host_plan_from_image(static_cast<const unsigned char*>(image_host), (size_t)image_bytes, n, pl->h, err)) {
+        delete pl;
+        return fail(SIGSDP_EINVAL, err);
+    }
+    return plan_finish(pl, n, Sp, Si, Sx, Qp, Qi, Qx, h_max, device, out);
+}
+
+// the part of plan creation after the host plan exists: device upload, host copies of the inputs
+static int plan_finish(sigsdp_plan* pl, int64_t n, const int32_t* Sp, const int32_t* Si, const double* Sx, const int32_t* Qp,
+                       const int32_t* Qi, const double* Qx, const double* h_max, int device, sigsdp_plan** out) {
+    ApiTimer tm;
     pl->device = device;
     auto bail = [&](cudaError_t e, const char* what) {
         std::string m = std::string(what) + ": " + cudaGetErrorString(e);

@@ -148,6 +148,66 @@ void locality_order_inputs(int64_t n, const int32_t* Sp, const int32_t* Si, cons
 }  // namespace
 
 
+namespace {
+constexpr int64_t IMAGE_MAGIC = 0x5347504c414e3031ll;   // "SGPLAN01"
+struct ImageField {
+    void* ptr;
+    size_t bytes;
+};
+// the arrays of a plan in image order; sizes from the header fields already set in P
+template <class PlanT, class F>
+void image_fields(PlanT& P, F&& f) {
+    f(P.rowptr, (size_t)P.n + 1); f(P.col, (size_t)P.nnz); f(P.eid, (size_t)P.nnz);
+    f(P.tfwd, (size_t)P.nnz); f(P.tbwd, (size_t)P.nnz);
+    f(P.gi, (size_t)P.E_g); f(P.gj, (size_t)P.E_g); f(P.ai, (size_t)P.E_a); f(P.aj, (size_t)P.E_a);
+    f(P.tij, (size_t)P.E_g); f(P.tji, (size_t)P.E_g);
+    f(P.S_sum, (size_t)P.n); f(P.tnorm, (size_t)P.n); f(P.h_max, (size_t)P.n);
+    f(P.perm, (size_t)P.n); f(P.iperm, (size_t)P.n); f(P.dpos, (size_t)P.n); f(P.apos, (size_t)P.E_a);
+}
+inline size_t pad8(size_t b) { return (b + 7) & ~(size_t)7; }
+}  // namespace
+
+size_t host_plan_image_bytes(const HostPlan& P) {
+    size_t tot = 8 * sizeof(int64_t);
+    image_fields(P, [&](const auto& v, size_t cnt) { tot += pad8(cnt * sizeof(v[0])); });
+    return tot;
+}
+
+void host_plan_to_image(const HostPlan& P, unsigned char* buf) {
+    int64_t hdr[8] = {IMAGE_MAGIC, P.n, P.E_g, P.E_a, P.nnz, P.nnzT, P.max_row, P.order};
+    std::memcpy(buf, hdr, sizeof(hdr));
+    size_t off = sizeof(hdr);
+    std::vector<CopySeg> segs;
+    image_fields(P, [&](const auto& v, size_t cnt) {
+        segs.push_back(CopySeg{buf + off, v.data(), cnt * sizeof(v[0])});
+        off += pad8(cnt * sizeof(v[0]));
+    });
+    parallel_copy(segs);
+}
+
+bool host_plan_from_image(const unsigned char* buf, size_t bytes, int64_t n, HostPlan& P, std::string& err) {
+    int64_t hdr[8];
+    if (bytes < sizeof(hdr)) { err = "plan image too short"; return false; }
+    std::memcpy(hdr, buf, sizeof(hdr));
+    if (hdr[0] != IMAGE_MAGIC || hdr[1] != n || hdr[2] < 0 || hdr[3] < 0 || hdr[4] != n + 2 * (hdr[2] + hdr[3])) {
+        err = "plan image does not describe a plan of this state";
+        return false;
+    }
+    P = HostPlan();
+    P.n = hdr[1]; P.E_g = hdr[2]; P.E_a = hdr[3]; P.nnz = hdr[4]; P.nnzT = hdr[5]; P.max_row = (int)hdr[6]; P.order = (int)hdr[7];
+    if (host_plan_image_bytes(P) != bytes) { err = "plan image has the wrong size"; return false; }
+    size_t off = sizeof(hdr);
+    std::vector<CopySeg> segs;
+    image_fields(P, [&](auto& v, size_t cnt) {
+        v.resize(cnt);
+        segs.push_back(CopySeg{v.data(), buf + off, cnt * sizeof(v[0])});
+        off += pad8(cnt * sizeof(v[0]));
+    });
+    parallel_copy(segs);
+    if (P.rowptr[0] != 0 || P.rowptr[n] != P.nnz) { err = "plan image is inconsistent"; return false; }
+    return true;
+}
+
 void shard_cut_points(const HostPlan& P, const HostTiles* ht, int nranks, std::vector<int32_t>& row0,
                       std::vector<int32_t>& tile0) {
     const int nb = ht ? ht->ntiles : (int)P.n;

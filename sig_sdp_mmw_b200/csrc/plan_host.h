@@ -66,6 +66,13 @@ struct HostTiles {
 };
 void build_tiles(const HostPlan& P, int max_rows, int ucap, int nnzcap, HostTiles& out);
 
+// Flat image of a built plan (header + arrays), so that ONE process of a multi-GPU launch builds the plan on all
+// host cores and the others receive it instead of building the same plan side by side on a share of the cores.
+size_t host_plan_image_bytes(const HostPlan& P);
+void host_plan_to_image(const HostPlan& P, unsigned char* buf);
+// returns false (err set) when the image is malformed or does not describe an n-node plan
+bool host_plan_from_image(const unsigned char* buf, size_t bytes, int64_t n, HostPlan& P, std::string& err);
+
 // Row sharding of one graph across `nranks` GPUs (include/sigsdp_mmw.h, "row sharding"): rank r owns the rows
 // [row0[r], row0[r+1]) -- whole tiles [tile0[r], tile0[r+1]) when the solver is tiled (ht != nullptr) -- cut where
 // the cumulative non-zeros reach r / nranks of the total.

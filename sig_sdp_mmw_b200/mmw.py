@@ -159,7 +159,7 @@ class mmw(STATS_OBJECT, sdp_solver):
         sp_tic = self._get_tic()
         K = state[0].shape[0]
         D = Z * self.rank_radio                                   # mmw.py:180
-        plan = self._plan_for(state)
+        plan = self._plan_for(state, collective=self.row_shard, group=self.shard_group)
         shard = None
         if self.row_shard:
             from .rowshard import RowShardRank

@@ -65,7 +65,7 @@ class sdp_solver:
         pass
 
     # ---- plan cache: the graph plan is Z-independent and reused across the binary search
-    def _plan_for(self, state):
+    def _plan_for(self, state, collective=False, group=None):
         """The plan of `state`, rebuilt when the state's content changes.  The key is a position-
         weighted checksum of every buffer (values AND structure: an in-place permutation of the
         values, or a changed pattern with the same nnz, changes it), about 2 ms at 100k nodes
@@ -74,7 +74,10 @@ class sdp_solver:
         key = (id(S), id(Q), S.shape, self.device, self.plan_order) + _digest(S) + _digest(Q) + _digest_vec(np.asarray(h))
         cache = self.__dict__.setdefault("_plan_cache", {})
         if cache.get("key") != key:
-            cache["plan"] = _lib.Plan(state, device=self.device, order=self.plan_order)
+            if collective:      # every rank of the job calls this with the same state (row-sharded solve)
+                cache["plan"] = _lib.Plan.collective(state, self.device, self.plan_order, group)
+            else:
+                cache["plan"] = _lib.Plan(state, device=self.device, order=self.plan_order)
             cache["key"] = key
             cache["objects"] = (S, Q, h)
         return cache["plan"]

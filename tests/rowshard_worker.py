@@ -105,7 +105,7 @@ def main():
         rank, world = dist.get_rank(), dist.get_world_size()
         om = np.random.RandomState(3).randn(nit, K, D)
         om_d = torch.from_numpy(om).cuda()
-        plan = _lib.Plan(state, device=local, order=1)
+        plan = _lib.Plan.collective(state, local, 1, min_world=2)   # built by rank 0, broadcast over NCCL, imported here
         sh = RowShardRank(plan, Z, D, eta, dtype=code)
         sh.iterate(nit, om_d.data_ptr(), 0, None)
         torch.cuda.synchronize()

@@ -167,7 +167,10 @@ def _gloo_rowpart_worker(rank, world, port, out):
     # every rank builds the plan of the same state on its own (as the row-sharded bench does) and must arrive
     # at the same partition; what it owns is marked and summed over the ranks
     state = sparse_env(cell_size=12, sta_density_per_1m2=75e-4, seed=4).generate_S_Q_hmax()
-    plan = _lib.Plan(state, device=-1, order=1)
+    plan = _lib.Plan.collective(state, -1, 1, min_world=2)   # rank 0 builds, the image is broadcast, rank 1 imports it
+    if rank == 1:                                   # ... and it is the plan rank 1 would have built itself
+        mine = _lib.Plan(state, device=-1, order=1)
+        assert all(np.array_equal(x, y) for x, y in zip(plan.pattern() + (plan.perm(),), mine.pattern() + (mine.perm(),)))
     part = plan.row_partition(world, 32, 343, 2048)
     rows = torch.zeros(plan.n, dtype=torch.float64)
     rows[int(part["row0"][rank]):int(part["row0"][rank + 1])] = 1.0

@@ -240,3 +240,26 @@ def test_sparse_evaluate_sinr_bler_matches_reference(name):
     np.testing.assert_allclose(np.sort(approx), np.sort(g[name + "_sinr"]), rtol=5e-2)
     fine = e.evaluate_sinr(z, Z, exact=False, floor_ratio=1e-3)
     np.testing.assert_allclose(np.sort(fine), np.sort(g[name + "_sinr"]), rtol=2e-3)
+
+
+def test_plan_image_round_trip_and_rejection():
+    """sigsdp_plan_image / sigsdp_plan_create_from_image: a plan rebuilt from the image of another is the same plan;
+    an image of a different state or a damaged one is refused."""
+    from sig_sdp_mmw_b200.topology import sparse_env
+    state = sparse_env(cell_size=12, sta_density_per_1m2=75e-4, seed=3).generate_S_Q_hmax()
+    a = _lib.Plan(state, device=-1, order=1)
+    img = a.image()
+    b = _lib.Plan(state, device=-1, order=1, image=img)
+    assert (a.n, a.E_g, a.E_a, a.nnz, a.nnzT, a.order, a.max_row) == (b.n, b.E_g, b.E_a, b.nnz, b.nnzT, b.order, b.max_row)
+    for x, y in zip(a.pattern() + a.edges() + a.vectors() + (a.perm(),), b.pattern() + b.edges() + b.vectors() + (b.perm(),)):
+        np.testing.assert_array_equal(x, y)
+    assert a.tile_stats(32, 343, 2048) == b.tile_stats(32, 343, 2048)
+    other = sparse_env(cell_size=11, sta_density_per_1m2=75e-4, seed=3).generate_S_Q_hmax()
+    with pytest.raises(_lib.SigSdpError):
+        _lib.Plan(other, device=-1, order=1, image=img)          # image of another graph
+    with pytest.raises(_lib.SigSdpError):
+        _lib.Plan(state, device=-1, order=1, image=img[:-8])     # truncated
+    bad = img.copy()
+    bad[:8] = 0
+    with pytest.raises(_lib.SigSdpError):
+        _lib.Plan(state, device=-1, order=1, image=bad)          # no magic
