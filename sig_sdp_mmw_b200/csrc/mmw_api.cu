@@ -994,9 +994,15 @@ static int solver_alloc(sigsdp_solver* s) {
             const double grid_est = s->max_blocks > 0 ? (double)s->max_blocks : 2.0 * pl->num_sms;
             const double n_rows = (double)h.n / s->nranks;
             const double avg_nnz = (double)h.nnz / (double)h.n;
-            if (avg_nnz * max_rows <= 0.95 * nnzcap && n_rows > grid_est * max_rows) {
-                const double waves = std::ceil(1.015 * n_rows / max_rows / grid_est);
-                max_rows = std::min(max_rows, std::max(16, (int)std::ceil(1.02 * n_rows / (grid_est * waves))));
+            // A row shard with less than one wave of tiles (8 ranks at 100k nodes) gets as many tiles as blocks, so
+            // no block idles and the spare lane groups of the shorter tiles split more of the long rows.  (Not for
+            // unsharded small graphs: they are barrier-bound either way, and a solver may end up in a batch, where
+            // ONE block walks all its tiles.)
+            const double eff_rows = std::min<double>(max_rows, 0.95 * nnzcap / avg_nnz);   // rows a tile really gets
+            const double waves = std::ceil(1.015 * n_rows / eff_rows / grid_est);
+            if (waves >= 2.0 || s->nranks > 1) {
+                const int balanced = (int)std::ceil(1.02 * n_rows / (grid_est * std::max(1.0, waves)));
+                if (balanced < eff_rows) max_rows = std::min(max_rows, std::max(16, balanced));
             }
         }
         const size_t fixed = 16 + (size_t)(nnzcap + 4) * sizeof(T) + (size_t)(nnzcap + 8) * 2 + 48;
