@@ -111,9 +111,9 @@ class mmw(STATS_OBJECT, sdp_solver):
         if self.omega == "numpy":
             v0 = torch.from_numpy(np.random.standard_normal(K)).to(dev)   # svds' ARPACK start vector
         else:
-            g = torch.Generator(device="cpu").manual_seed(int(self.seed) + 1 + seed_offset)
-            v0 = torch.randn(K, dtype=torch.float64, generator=g).to(dev)
-        perm = torch.from_numpy(plan.perm().astype(np.int64)).to(dev)
+            g = torch.Generator(device=dev).manual_seed(int(self.seed) + 1 + seed_offset)
+            v0 = torch.randn(K, dtype=torch.float64, generator=g, device=dev)
+        perm = torch.from_numpy(plan.perm()).to(dev).long()
         lam, V, info = thick_restart_lanczos(self._matmat(solver, torch, dev), K, rank, "LM", v0[perm], tol=self.eig_tol,
                                             native_steps=self._native_steps(solver, torch))
         self.last_eig_info = info
@@ -121,7 +121,11 @@ class mmw(STATS_OBJECT, sdp_solver):
         X_half = torch.empty_like(X_half_int)
         X_half[perm] = X_half_int                              # internal -> caller numbering
         self.last_singular_values = lam.abs().cpu().numpy()
-        return X_half.cpu().numpy()
+        # device -> host through a pinned buffer (24 MB at cfg4: ~1 ms instead of ~4 from pageable memory)
+        host = torch.empty(X_half.shape, dtype=X_half.dtype, pin_memory=True)
+        host.copy_(X_half, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return host.numpy()      # (the array keeps the pinned block alive; it returns to torch's host cache afterwards)
 
     def run_many_with_states(self, Zs, states):
         """Monte-Carlo sweeps (the drivers' `for seed in range(REPEAT)` loops): every
