@@ -163,9 +163,15 @@ class mmw(STATS_OBJECT, sdp_solver):
         sp_tic = self._get_tic()
         K = state[0].shape[0]
         D = Z * self.rank_radio                                   # mmw.py:180
-        plan = self._plan_for(state, collective=self.row_shard, group=self.shard_group)
         shard = None
+        sharded = False
         if self.row_shard:
+            import torch.distributed as dist
+            if not (dist.is_available() and dist.is_initialized()):
+                raise _lib.SigSdpError("row_shard=True needs an initialised torch.distributed process group (one process per GPU)")
+            sharded = dist.get_world_size(self.shard_group) > 1       # a one-rank group is just the plain solver
+        plan = self._plan_for(state, collective=sharded, group=self.shard_group)
+        if sharded:
             from .rowshard import RowShardRank
             if self.LOG_GAP:
                 raise _lib.SigSdpError("LOG_GAP is not available on a row-sharded solve")
