@@ -411,6 +411,7 @@ def run_ours(args):
     barrier()
     ms = ev0.elapsed_time(ev1)
     terms = sol.total_terms()
+    same_branch = bool(sol.history(min(args.steps, 8192))["cond313"].all())
     phase = sol.phase_times(min(args.steps, 8192)).sum(axis=0)
     sync_ms = sol.sync_wait_ns() / 1e6
     bar_ns = sol.barrier_breakdown_ns()
@@ -517,6 +518,7 @@ def run_ours(args):
             "parallelism": par,
             "detail": {"E_gain": plan.E_g, "E_asso": plan.E_a, "nnzL": plan.nnz, "taylor_terms": terms,
                        "terms_per_iter": terms / args.steps, "omega": "device Philox", "node_order": args.order,
+                       "taylor_rule_is_scipys_branch": same_branch,   # ||A||_1 <= 63.36 / D on every iteration
                        "launches_per_rank": 1, "grid": sol_info["grid"], "threads": sol_info["threads"],
                        "lanes_per_row": sol_info["lanes"], "tile_rows": sol_info["tile_rows"],
                        "smem_bytes": sol_info["smem"],
