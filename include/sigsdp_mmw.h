@@ -49,6 +49,10 @@ const char* sigsdp_last_error(void);
 int sigsdp_version(void);
 /* number of CUDA devices visible, or a negative error */
 int sigsdp_device_count(void);
+/* Position-weighted 64-bit checksum of a host buffer, computed on the builder's host threads.  The host side keys its
+ * plan cache with it (the reference re-runs _process_state on every call, mmw.py:26-41; a caller of this library keeps
+ * the plan while the state's buffers are unchanged).  bytes may be 0. */
+int sigsdp_checksum(const void* data_host, int64_t bytes, uint64_t* out);
 
 /* ------------------------------------------------------------------ plan ----
  * Replaces mmw._process_state (mmw.py:26-41) and the edge-list set-up

