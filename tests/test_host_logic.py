@@ -284,7 +284,8 @@ def test_checksum_sees_values_positions_and_length_whatever_the_thread_count(mon
     assert _lib.checksum(idx) != _lib.checksum(swapped)
     assert _lib.checksum(np.zeros(0)) == _lib.checksum(np.zeros(0, np.int32))
     # and the cache key built from it tells apart two states that differ in one stored value
-    from sig_sdp_mmw_b200 import sdp_solver
+    import importlib
+    sdp_solver = importlib.import_module("sig_sdp_mmw_b200.sdp_solver")
     S = sp.random(50, 50, density=0.2, random_state=rs, format="csr")
     S2 = S.copy(); S2.data[7] *= 2.0
     assert sdp_solver._digest(S) != sdp_solver._digest(S2)
