@@ -284,6 +284,13 @@ int sigsdp_solver_get_matrix(sigsdp_solver* s, double* vals_host);
  * are device arrays of length m.  Asynchronous on `stream`. */
 int sigsdp_solver_lanczos_steps(sigsdp_solver* s, double* Q_dev, int m, int j0, int j1, double* alpha_dev,
                                 double* beta_dev, void* stream);
+/* Chebyshev filter for the steps above: with degree >= 2 the operator of sigsdp_solver_lanczos_steps becomes
+ * p(M) = T_degree((M - c) / e), c = (lo + cut) / 2, e = (cut - lo) / 2 (three-term recurrence, `degree` mat-vecs per
+ * step): eigenvalues of M inside [lo, cut] are mapped into [-1, 1], those above cut grow like cosh(degree acosh(.)),
+ * monotonically, so the top eigenvectors of M are the top eigenvectors of p(M) with a far better relative gap.  The
+ * host side (lanczos.chebyshev_filtered_lanczos) picks lo / cut from a short unfiltered run and checks the returned
+ * pairs against M itself.  degree < 2 switches the filter off.  Takes effect from the next lanczos_steps call. */
+int sigsdp_solver_lanczos_filter(sigsdp_solver* s, int degree, double lo, double cut);
 /* the symmetric union pattern in the internal numbering: rowptr (n+1), col (nnzL) */
 int sigsdp_plan_pattern(const sigsdp_plan* plan, int32_t* rowptr_host, int32_t* col_host);
 

@@ -79,6 +79,7 @@ def load():
         "sigsdp_solver_symv": [vp, vp, vp, C.c_int, vp],
         "sigsdp_solver_get_matrix": [vp, f64p],
         "sigsdp_solver_lanczos_steps": [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp],
+        "sigsdp_solver_lanczos_filter": [vp, C.c_int, C.c_double, C.c_double],
         "sigsdp_plan_pattern": [vp, i32p, i32p],
         "sigsdp_plan_tile_stats": [vp, C.c_int, C.c_int, C.c_int, i64p],
         "sigsdp_debug_normals": [C.c_uint64, C.c_int64, C.c_int, C.c_int, C.c_int, f64p],
@@ -414,6 +415,10 @@ class Solver:
 
     def lanczos_steps(self, Q_ptr, m, j0, j1, al_ptr, be_ptr, stream=None):
         check(load().sigsdp_solver_lanczos_steps(self.handle, Q_ptr, int(m), int(j0), int(j1), al_ptr, be_ptr, stream))
+
+    def lanczos_filter(self, degree, lo=0.0, cut=1.0):
+        """Chebyshev filter of the operator behind lanczos_steps (degree < 2: off), see sigsdp_solver_lanczos_filter."""
+        check(load().sigsdp_solver_lanczos_filter(self.handle, int(degree), float(lo), float(cut)))
 
     def matrix_values(self):
         v = np.empty(self.plan.nnz)

@@ -44,6 +44,17 @@ struct ApiTimer {
     }
 };
 
+static void pool_report(int device, const char* where) {   // SIGSDP_PLAN_TIMING=1: what the stream-ordered pool holds
+    if (getenv("SIGSDP_PLAN_TIMING") == nullptr) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) != cudaSuccess) return;
+    unsigned long long res = 0, used = 0, res_hi = 0;
+    cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &res);
+    cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
+    cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemHigh, &res_hi);
+    fprintf(stderr, "[pool] %-24s reserved %7.1f MB (high %7.1f)  used %7.1f MB\n", where, res / 1048576.0, res_hi / 1048576.0, used / 1048576.0);
+}
+
 // Device allocations go through the stream-ordered allocator with a pool that keeps freed
 // memory (release threshold = max): the binary search creates and destroys a solver per
 // probe, and plain cudaMalloc after cudaFree re-maps memory every time (hundreds of ms at
@@ -164,6 +175,10 @@ struct sigsdp_solver {
     // Lanczos step workspace (allocated on first use)
     double *lz_w = nullptr, *lz_part = nullptr, *lz_h = nullptr, *lz_partn = nullptr;
     int lz_rows = 0;
+    // Chebyshev filter of the Lanczos operator (sigsdp_solver_lanczos_filter): degree < 2 = none
+    int lz_deg = 0;
+    double lz_c = 0.0, lz_e = 1.0;
+    double* lz_t[2] = {nullptr, nullptr};
     // a restart cycle (same steps on the same buffers every time) is captured once into a CUDA
     // graph on an internal stream and replayed
     cudaStream_t lz_stream = nullptr;
@@ -425,6 +440,25 @@ __global__ void k_symv(PlanDev g, const double* Mval, const double* x, double* y
             for (int p = g.rowptr[k] + lane; p < g.rowptr[k + 1]; p += G) acc += Mval[p] * xv[g.col[p]];
             for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(mask, acc, o);
             if (lane == 0) yv[k] = acc;
+        }
+    }
+}
+
+// y = a (M x) + b x + c z (z may be y itself: element k is read and written by the same thread; c == 0: z unused):
+// one term of the Chebyshev recurrence of the filtered Lanczos operator
+__global__ void k_symv_axpy(PlanDev g, const double* Mval, const double* x, const double* z, double* y, double a, double b, double c) {
+    constexpr int G = 8;
+    const int lane = threadIdx.x & (G - 1);
+    const unsigned mask = 0xffu << ((threadIdx.x & 31) & ~(G - 1));
+    const int ngroups = gridDim.x * blockDim.x / G;
+    for (int k = (blockIdx.x * blockDim.x + threadIdx.x) / G; k < g.n; k += ngroups) {
+        double acc = 0.0;
+        for (int p = g.rowptr[k] + lane; p < g.rowptr[k + 1]; p += G) acc += Mval[p] * x[g.col[p]];
+        for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(mask, acc, o);
+        if (lane == 0) {
+            double r = a * acc + b * x[k];
+            if (c != 0.0) r += c * z[k];
+            y[k] = r;
         }
     }
 }
@@ -797,6 +831,7 @@ static int plan_create_on_device(sigsdp_plan* pl, int64_t n, const int32_t* Sp, 
     d.rowptr = a.rowptr; d.col = a.col; d.eid = a.eid; d.tfwd = a.tfwd; d.tbwd = a.tbwd; d.S_sum = a.S_sum; d.tnorm = a.tnorm;
     d.h_max = a.h_max; d.perm = a.perm; d.dpos = a.dpos; d.apos = a.apos;
     tm.lap("device plan");
+    pool_report(device, "after device plan");
     *out = pl;
     return SIGSDP_OK;
 }
@@ -1078,6 +1113,7 @@ static int solver_alloc(sigsdp_solver* s) {
     P.omega = nullptr;
     P.seed = 0;
     tm.lap("solver alloc");
+    pool_report(s->plan->device, "after solver alloc");
     // row tiles for the staged (shared-memory) kernels: tiles of up to `max_rows` consecutive
     // rows, capped so that a tile's distinct sketch rows, its L_accu slice and its local
     // column indices fit the per-block shared-memory budget (two blocks per SM)
@@ -2000,6 +2036,23 @@ int sigsdp_solver_symv(sigsdp_solver* s, const double* x_dev, double* y_dev, int
 }
 
 
+int sigsdp_solver_lanczos_filter(sigsdp_solver* s, int degree, double lo, double cut) {
+    if (!s) return fail(SIGSDP_EINVAL, "null solver");
+    if (degree >= 2 && !(cut > lo)) return fail(SIGSDP_EINVAL, "the damped interval [lo, cut] is empty");
+    if (degree > 64) return fail(SIGSDP_EINVAL, "filter degree above 64");
+    CK(cudaSetDevice(s->plan->device));
+    if (degree >= 2 && !s->lz_t[0]) {
+        CK(s->mem.alloc(&s->lz_t[0], (size_t)s->plan->h.n));
+        CK(s->mem.alloc(&s->lz_t[1], (size_t)s->plan->h.n));
+        CK(cudaStreamSynchronize((cudaStream_t)0));
+    }
+    s->lz_deg = degree >= 2 ? degree : 0;
+    s->lz_c = 0.5 * (lo + cut);
+    s->lz_e = degree >= 2 ? 0.5 * (cut - lo) : 1.0;
+    s->lz_key[0] = nullptr;   // a captured graph of the steps holds the old operator
+    return SIGSDP_OK;
+}
+
 int sigsdp_solver_lanczos_steps(sigsdp_solver* s, double* Q_dev, int m, int j0, int j1, double* alpha_dev,
                                 double* beta_dev, void* stream) {
     if (!s || !Q_dev || !alpha_dev || !beta_dev || m < 1 || j0 < 0 || j1 > m || j0 > j1)
@@ -2022,7 +2075,22 @@ int sigsdp_solver_lanczos_steps(sigsdp_solver* s, double* Q_dev, int m, int j0, 
     auto enqueue = [&](cudaStream_t q) {
         for (int j = j0; j < j1; ++j) {
             const int nrows = j + 1;
-            k_symv<<<s->plan->num_sms * 8, 256, 0, q>>>(s->plan->d, s->Mval, Q_dev + (size_t)j * n, s->lz_w, 1);
+            const double* qj = Q_dev + (size_t)j * n;
+            if (s->lz_deg < 2) {
+                k_symv<<<s->plan->num_sms * 8, 256, 0, q>>>(s->plan->d, s->Mval, qj, s->lz_w, 1);
+            } else {
+                // w = T_deg((M - c) / e) q_j by the three-term recurrence t_{i+1} = 2 (M - c)/e t_i - t_{i-1}; t_i lives in
+                // lz_t[(i - 1) % 2], the last one is written to w
+                const int d = s->lz_deg;
+                const double ie = 1.0 / s->lz_e, c = s->lz_c;
+                k_symv_axpy<<<s->plan->num_sms * 8, 256, 0, q>>>(s->plan->d, s->Mval, qj, nullptr, s->lz_t[0], ie, -c * ie, 0.0);
+                for (int i = 2; i <= d; ++i) {
+                    const double* x = s->lz_t[(i - 2) % 2];
+                    const double* z = i == 2 ? qj : s->lz_t[(i - 1) % 2];
+                    double* y = i == d ? s->lz_w : s->lz_t[(i - 1) % 2];
+                    k_symv_axpy<<<s->plan->num_sms * 8, 256, 0, q>>>(s->plan->d, s->Mval, x, z, y, 2.0 * ie, -2.0 * c * ie, -1.0);
+                }
+            }
             for (int pass = 0; pass < 2; ++pass) {
                 k_lz_dot<<<nb_dot, 256, 0, q>>>(Q_dev, n, nrows, s->lz_w, s->lz_part, ldp);
                 k_lz_reduce<<<(nrows + 7) / 8, 256, 0, q>>>(s->lz_part, nb_dot, ldp, nrows, s->lz_h, alpha, j, pass);

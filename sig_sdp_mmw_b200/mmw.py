@@ -27,10 +27,12 @@ has no notion of (all default to the reference's behaviour):
 There is no CPU fallback: a missing library or CUDA device raises."""
 import math
 
+import time
+
 import numpy as np
 
 from . import _lib
-from .lanczos import thick_restart_lanczos
+from .lanczos import chebyshev_filtered_lanczos, thick_restart_lanczos
 from .sdp_solver import sdp_solver
 from .stats import STATS_OBJECT
 
@@ -38,7 +40,28 @@ from .stats import STATS_OBJECT
 _OMEGA_CHUNK_BYTES = 1 << 30
 
 
+class _Laps:
+    """SIGSDP_PLAN_TIMING=1: stage times of the final factor on stderr (synchronises; diagnosis only)."""
+
+    def __init__(self, torch):
+        import os
+        self.on = os.environ.get("SIGSDP_PLAN_TIMING") is not None
+        self.torch = torch
+        self.t = time.perf_counter() if self.on else 0.0
+
+    def __call__(self, what):
+        if not self.on:
+            return
+        import sys
+        self.torch.cuda.synchronize()
+        t = time.perf_counter()
+        sys.stderr.write("[fact] %-24s %8.2f ms\n" % (what, 1e3 * (t - self.t)))
+        self.t = t
+
+
 class mmw(STATS_OBJECT, sdp_solver):
+    EIG_FILTER_MIN_NODES = 10000   # see eig_filter below
+
     def __init__(self, nit=100, rank_radio=2, alpha=1., eta=0.1, log_gap=False,
                  dtype="float64", omega="numpy", device=0, order=1, seed=0, row_shard=False, shard_group=None,
                  warm_start=False):
@@ -52,6 +75,10 @@ class mmw(STATS_OBJECT, sdp_solver):
         self.seed = seed
         self.mode = _lib.MODE_FUSED
         self.eig_tol = 1e-10          # relative residual of the final factor's eigenpairs
+        # final factor by Lanczos on a Chebyshev-filtered operator (lanczos.chebyshev_filtered_lanczos): "auto" = from
+        # EIG_FILTER_MIN_NODES nodes on, True / False = always / never; the plain solver is the fallback either way
+        self.eig_filter = "auto"
+        self.eig_filter_degree = 8
         self.row_shard = bool(row_shard)
         self.shard_group = shard_group
         self.warm_start = bool(warm_start)
@@ -105,26 +132,39 @@ class mmw(STATS_OBJECT, sdp_solver):
         """X_half = U sqrt(|Lambda|) of the top-r |lambda| eigenpairs of X_avgd / nit
         (mmw.py:202-216, where svds does it), rows in the caller's numbering."""
         plan = solver.plan
+        lap = _Laps(torch)
         K = plan.n
         rank = int(min(K - 1, (Z - 1) * self.rank_radio))
         solver.xavg_matrix(1.0 / nit, stream)
+        lap("xavg_matrix")
         if self.omega == "numpy":
             v0 = torch.from_numpy(np.random.standard_normal(K)).to(dev)   # svds' ARPACK start vector
         else:
             g = torch.Generator(device=dev).manual_seed(int(self.seed) + 1 + seed_offset)
             v0 = torch.randn(K, dtype=torch.float64, generator=g, device=dev)
         perm = torch.from_numpy(plan.perm()).to(dev).long()
-        lam, V, info = thick_restart_lanczos(self._matmat(solver, torch, dev), K, rank, "LM", v0[perm], tol=self.eig_tol,
-                                            native_steps=self._native_steps(solver, torch))
+        lap("start vector, perm")
+        out = None
+        if self.eig_filter is True or (self.eig_filter == "auto" and K >= self.EIG_FILTER_MIN_NODES):
+            out = chebyshev_filtered_lanczos(self._matmat(solver, torch, dev), K, rank, v0[perm], self._native_steps(solver, torch),
+                                             solver.lanczos_filter, tol=self.eig_tol, degree=self.eig_filter_degree)
+        if out is None:      # small graphs, or the filter declined (see chebyshev_filtered_lanczos): the plain solver
+            out = thick_restart_lanczos(self._matmat(solver, torch, dev), K, rank, "LM", v0[perm], tol=self.eig_tol,
+                                        native_steps=self._native_steps(solver, torch))
+        lam, V, info = out
+        lap("eigen-solver")
         self.last_eig_info = info
         X_half_int = V * torch.sqrt(lam.abs())[None, :]
         X_half = torch.empty_like(X_half_int)
         X_half[perm] = X_half_int                              # internal -> caller numbering
         self.last_singular_values = lam.abs().cpu().numpy()
         # device -> host through a pinned buffer (24 MB at cfg4: ~1 ms instead of ~4 from pageable memory)
+        lap("scale, unpermute")
         host = torch.empty(X_half.shape, dtype=X_half.dtype, pin_memory=True)
+        lap("pinned buffer")
         host.copy_(X_half, non_blocking=True)
         torch.cuda.current_stream().synchronize()
+        lap("factor to host")
         return host.numpy()      # (the array keeps the pinned block alive; it returns to torch's host cache afterwards)
 
     def run_many_with_states(self, Zs, states):

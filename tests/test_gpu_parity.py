@@ -346,6 +346,72 @@ def _mm_of(sol):
     return mm
 
 
+def test_native_filtered_step_applies_the_chebyshev_polynomial():
+    """sigsdp_solver_lanczos_filter: one native step on p(M) = T_d((M - c)/e) satisfies alpha_0 q_0 + beta_0 q_1 = p(M) q_0
+    with p(M) q_0 formed here from the library's plain mat-vec by the three-term recurrence."""
+    g = load_case("n500_z13")
+    _, sol, _ = _run_device(g, 20)
+    sol.xavg_matrix(1.0 / 20)
+    n = sol.plan.n
+    mm = _mm_of(sol)
+    dev = torch.device("cuda", 0)
+    steps = mmw._native_steps(sol, torch)
+    q0 = torch.randn(n, dtype=torch.float64, device=dev)
+    q0 /= torch.linalg.norm(q0)
+    for deg, lo, cut in ((2, 0.1, 0.9), (5, 0.3, 1.1), (8, 0.2, 1.0)):
+        c, e = 0.5 * (lo + cut), 0.5 * (cut - lo)
+        t0, t1 = q0[None], (mm(q0[None]) - c * q0[None]) / e
+        for _ in range(deg - 1):
+            t0, t1 = t1, 2.0 * (mm(t1) - c * t1) / e - t0
+        Q = torch.zeros((3, n), dtype=torch.float64, device=dev)
+        Q[0] = q0
+        al = torch.zeros(2, dtype=torch.float64, device=dev)
+        be = torch.zeros(2, dtype=torch.float64, device=dev)
+        sol.lanczos_filter(deg, lo, cut)
+        steps(Q, 2, 0, 1, al, be)
+        torch.cuda.synchronize()
+        got = al[0] * Q[0] + be[0] * Q[1]
+        scale = float(t1.abs().max())
+        assert float((got - t1[0]).abs().max()) <= 1e-12 * scale
+    sol.lanczos_filter(0)
+    Q = torch.zeros((3, n), dtype=torch.float64, device=dev)
+    Q[0] = q0
+    steps(Q, 2, 0, 1, al, be)
+    torch.cuda.synchronize()
+    assert float((al[0] * Q[0] + be[0] * Q[1] - mm(q0[None])[0]).abs().max()) <= 1e-13
+    with pytest.raises(_lib.SigSdpError):
+        sol.lanczos_filter(4, 1.0, 1.0)
+
+
+def test_filtered_final_factor_equals_plain_final_factor():
+    """The Chebyshev-filtered eigen-solver (default from EIG_FILTER_MIN_NODES nodes) and the plain thick-restart
+    Lanczos return the same factor: same singular values, same X_half X_half^T (applied to random vectors; the
+    factor itself is unique only up to rotations inside eigenvalue clusters)."""
+    _require_gpu()
+    from sig_sdp_mmw_b200.topology import sparse_env as _env
+    state = _env(cell_size=80, sta_density_per_1m2=75e-4, seed=1).generate_S_Q_hmax()    # 19,200 stations
+    Z, rr, nit = 8, 2, 30
+    res = {}
+    for filt in (True, False):
+        alg = mmw(nit=nit, rank_radio=rr, eta=0.04, omega="device", seed=5)
+        alg.eig_filter = filt
+        ok, X_half = alg.run_with_state(0, Z, state)
+        assert ok
+        res[filt] = (X_half, alg.last_singular_values.copy(), dict(alg.last_eig_info))
+    (Xf, sf, inf_f), (Xp, sp_, inf_p) = res[True], res[False]
+    assert "filter" in inf_f and "filter" not in inf_p and inf_f["converged"] and inf_p["converged"]
+    assert inf_f["lanczos_steps"] * 2 < inf_p["matvecs"]
+    np.testing.assert_allclose(sf, sp_, rtol=0, atol=1e-9)
+    R = np.random.RandomState(0).randn(Xf.shape[0], 4)
+    Gf, Gp = Xf @ (Xf.T @ R), Xp @ (Xp.T @ R)
+    assert np.abs(Gf - Gp).max() <= 1e-6 * np.abs(Gp).max()
+    # the default picks the filter at this size, and declines below the threshold
+    alg = mmw(nit=nit, rank_radio=rr, eta=0.04, omega="device", seed=5)
+    assert alg.eig_filter == "auto" and state[0].shape[0] >= alg.EIG_FILTER_MIN_NODES
+    alg.run_with_state(0, Z, state)
+    assert "filter" in alg.last_eig_info
+
+
 def test_lanczos_breakdown_identity_matrix():
     """nit = 1: X_avgd = X_0 = I (mmw.py:67,77), every Krylov space is invariant after one step
     (beta = 0).  The solver must return finite orthonormal eigenvectors with eigenvalue 1 instead
