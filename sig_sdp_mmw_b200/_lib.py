@@ -174,6 +174,14 @@ class Plan:
         check(load().sigsdp_plan_info(self.handle, info))
         self.n, self.E_g, self.E_a, self.nnz, self.nnzT, self.device, self.order, self.max_row = [int(x) for x in info]
 
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                load().sigsdp_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
     def image(self):
         """The built plan as a flat uint8 array (sigsdp_plan_image), for Plan(state, image=...) in another process."""
         nb = C.c_int64()

@@ -981,6 +981,7 @@ void sigsdp_plan_destroy(sigsdp_plan* plan) {
         cudaSetDevice(plan->device);
         plan->mem.release();
         plan->tile_mem.release();
+        pool_report(plan->device, "plan destroyed");
     }
     delete plan;
 }
@@ -1163,13 +1164,12 @@ static int solver_alloc(sigsdp_solver* s) {
                 if (tc.h.ok) {
                     int *trow, *ucnt, *rptr, *runs;
                     unsigned short* lcol;
-                    std::vector<uint16_t> lpad(tc.h.lcol);
-                    lpad.resize(lpad.size() + 16, 0);   // bulk copies read 16-byte supersets
+                    // (lcol carries 16 spare elements: bulk copies read 16-byte supersets)
                     CK(pl->tile_mem.upload(&trow, tc.h.trow));
                     CK(pl->tile_mem.upload(&ucnt, tc.h.ucnt));
                     CK(pl->tile_mem.upload(&rptr, tc.h.rptr));
                     CK(pl->tile_mem.upload(&runs, tc.h.runs));
-                    CK(pl->tile_mem.upload(&lcol, lpad));
+                    CK(pl->tile_mem.upload(&lcol, tc.h.lcol));
                     int* trec;
                     CK(pl->tile_mem.upload(&trec, tc.h.trec));
                     tc.d.trec = reinterpret_cast<const int4*>(trec);
@@ -1472,6 +1472,7 @@ void sigsdp_solver_destroy(sigsdp_solver* s) {
         cudaEventDestroy(s->lz_ev_out);
     }
     s->mem.release();
+    pool_report(s->plan->device, "solver destroyed");
     for (void* p : s->ipc_mapped) cudaIpcCloseMemHandle(p);
     if (s->arena) {
         cudaDeviceSynchronize();

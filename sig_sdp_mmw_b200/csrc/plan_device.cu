@@ -281,7 +281,7 @@ int build_device_plan(int64_t n64, const int32_t* Sp, const int32_t* Si, const d
                       const double* Qx, const double* h_max, int order, const DevicePlanAlloc& alloc, HostPlan& P, DevicePlanArrays& D,
                       std::string& err) {
     {
-        const int rc = validate_state(n64, Sp, Si, Sx, Qp, Qi, Qx, h_max, err);
+        const int rc = validate_pointers(n64, Sp, Si, Sx, Qp, Qi, Qx, h_max, err);
         if (rc != SIGSDP_OK) return rc;
     }
     if ((int64_t)Sp[n64] + Qp[n64] + 4 * n64 > (int64_t)0x7ffffff0) {
@@ -289,14 +289,11 @@ int build_device_plan(int64_t n64, const int32_t* Sp, const int32_t* Si, const d
         return SIGSDP_EINVAL;
     }
     DevTimer tm;
-    tm.lap("validate");
     const int n = (int)n64;
     const long long nS = Sp[n], nQ = Qp[n];
     cudaStream_t st = (cudaStream_t)0;
-    P = HostPlan();
-    P.n = n;
-    P.order = order;
-    // the locality ordering: sequential, on its own thread, next to everything below
+    // the locality ordering: sequential, on its own thread, next to everything below (it guards its own index reads:
+    // the index checks of validate_state run beside it)
     std::vector<int32_t> perm_h;
     std::thread bfs;
     if (order != 0) bfs = std::thread([&] { locality_order_of_inputs(n, Sp, Si, Qp, Qi, order > 1 ? order : 64, perm_h); });
@@ -304,6 +301,14 @@ int build_device_plan(int64_t n64, const int32_t* Sp, const int32_t* Si, const d
         std::thread& t;
         ~Joiner() { if (t.joinable()) t.join(); }
     } joiner{bfs};
+    {
+        const int rc = validate_state(n64, Sp, Si, Sx, Qp, Qi, Qx, h_max, err);
+        if (rc != SIGSDP_OK) return rc;
+    }
+    tm.lap("validate");
+    P = HostPlan();
+    P.n = n;
+    P.order = order;
 
     int device = 0;
     DK(cudaGetDevice(&device));

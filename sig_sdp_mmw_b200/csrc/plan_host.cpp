@@ -107,6 +107,7 @@ void locality_order_inputs(int64_t n, const int32_t* Sp, const int32_t* Si, cons
     std::vector<int32_t> q;
     q.reserve(cluster + 8);
     auto visit = [&](int32_t v) {
+        if ((uint32_t)v >= (uint32_t)n) return;   // (the walk starts before the index checks of validate_state finish)
         if (seen[v]) return;
         if ((int)q.size() < cluster) {
             seen[v] = 1;
@@ -317,6 +318,28 @@ void parallel_copy(const std::vector<CopySeg>& segs) {
     for (auto& x : th) x.join();
 }
 
+int validate_pointers(int64_t n, const int32_t* Sp, const int32_t* Si, const double* Sx, const int32_t* Qp, const int32_t* Qi,
+                      const double* Qx, const double* h_max, std::string& err) {
+    if (n <= 1 || n > (int64_t)1 << 30) {
+        err = "n must be in [2, 2^30]";
+        return SIGSDP_EINVAL;
+    }
+    if (!Sp || !Si || !Sx || !Qp || !Qi || !Qx || !h_max) {
+        err = "null input array";
+        return SIGSDP_EINVAL;
+    }
+    if (Sp[0] != 0 || Qp[0] != 0) {
+        err = std::string(Sp[0] != 0 ? "S_gain" : "Q_asso") + ": indptr[0] != 0";
+        return SIGSDP_EINVAL;
+    }
+    for (int64_t r = 0; r < n; ++r)
+        if (Sp[r + 1] < Sp[r] || Qp[r + 1] < Qp[r]) {
+            err = std::string(Sp[r + 1] < Sp[r] ? "S_gain" : "Q_asso") + ": indptr not monotone";
+            return SIGSDP_EINVAL;
+        }
+    return SIGSDP_OK;
+}
+
 int validate_state(int64_t n, const int32_t* Sp, const int32_t* Si, const double* Sx, const int32_t* Qp, const int32_t* Qi,
                    const double* Qx, const double* h_max, std::string& err) {
     if (n <= 1 || n > (int64_t)1 << 30) {
@@ -399,17 +422,13 @@ int build_host_plan(int64_t n, const int32_t* Sp, const int32_t* Si, const doubl
                     int order, HostPlan& P, std::string& err) {
     StageTimer tm;
     {
-        const int rc = validate_state(n, Sp, Si, Sx, Qp, Qi, Qx, h_max, err);
+        const int rc = validate_pointers(n, Sp, Si, Sx, Qp, Qi, Qx, h_max, err);
         if (rc != SIGSDP_OK) return rc;
     }
-    P = HostPlan();
-    P.n = n;
-    P.order = order;
-
-    tm.lap("validate");
-    // The locality ordering is the one sequential stage (~14 ms at 100k nodes): it only needs the
+    // The locality ordering is the one sequential stage (~11-14 ms at 100k nodes): it only needs the
     // inputs, so it runs on its own thread (the parallel stages leave it a core) while the other
-    // cores build T, the union pattern and the edge ids; it is joined in front of the renumbering.
+    // cores check the inputs and build T, the union pattern and the edge ids; it is joined in front
+    // of the renumbering.  (It guards its own index reads: the index checks run next to it.)
     std::vector<int32_t> bfs_perm;
     std::thread bfs_thread;
     if (order != 0) {
@@ -425,6 +444,14 @@ int build_host_plan(int64_t n, const int32_t* Sp, const int32_t* Si, const doubl
         std::thread& t;
         ~Joiner() { if (t.joinable()) t.join(); }
     } bfs_joiner{bfs_thread};
+    {
+        const int rc = validate_state(n, Sp, Si, Sx, Qp, Qi, Qx, h_max, err);
+        if (rc != SIGSDP_OK) return rc;
+    }
+    P = HostPlan();
+    P.n = n;
+    P.order = order;
+    tm.lap("validate");
     // ---- T = S^T with association pairs and the diagonal zeroed (mmw.py:28-33)
     std::vector<int32_t> Tp(n + 1, 0);
     hvec<int32_t> Ti;
@@ -793,7 +820,7 @@ void build_tiles(const HostPlan& P, int max_rows, int ucap, int nnzcap, HostTile
     T.max_rows = max_rows;
     T.ucap = std::min(ucap, 65535);
     T.nnzcap = nnzcap;
-    T.lcol.resize(P.nnz);
+    T.lcol.assign(P.nnz + 16, 0);   // + padding the device copy needs (bulk copies read 16-byte supersets)
     // Large graphs are cut into a FIXED number of row ranges tiled independently on the host
     // cores (fixed, not the core count: the tiling, and with it the order of the per-block
     // partial sums, is the same on every machine); a range boundary only ends a tile early.

@@ -106,6 +106,10 @@ uint64_t checksum_bytes(const void* data, size_t bytes);
 
 // structure checks of the inputs (monotone row pointers, sorted duplicate-free in-range indices, Q_asso symmetric with an
 // empty diagonal); 0 or a negative SIGSDP_E* code with the message in err
+// the part of validate_state that must hold before a row may be dereferenced at all (non-null arrays, monotone row
+// pointers): the locality ordering starts after it, next to the remaining checks
+int validate_pointers(int64_t n, const int32_t* Sp, const int32_t* Si, const double* Sx, const int32_t* Qp, const int32_t* Qi,
+                      const double* Qx, const double* h_max, std::string& err);
 int validate_state(int64_t n, const int32_t* Sp, const int32_t* Si, const double* Sx, const int32_t* Qp, const int32_t* Qi,
                    const double* Qx, const double* h_max, std::string& err);
 // the locality ordering (clustered BFS over the rows of S and Q), perm[new] = old

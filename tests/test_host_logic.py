@@ -290,3 +290,17 @@ def test_checksum_sees_values_positions_and_length_whatever_the_thread_count(mon
     S2 = S.copy(); S2.data[7] *= 2.0
     assert sdp_solver._digest(S) != sdp_solver._digest(S2)
     assert sdp_solver._digest(S) == sdp_solver._digest(S.copy())
+
+
+def test_plan_is_destroyed_with_its_python_object():
+    """A plan owns a device slab and host arrays of the graph's size: dropping the Python object must free them
+    (a Monte-Carlo sweep builds one plan per drop; a leak there also fragments the device pool and slows every
+    later set-up)."""
+    g = load_case(CASES[0])
+    plan = _lib.Plan(g["state"], device=-1, order=1)
+    assert plan.handle
+    plan.__del__()
+    assert plan.handle is None
+    plan.__del__()                                   # idempotent
+    sol_cls = _lib.Solver
+    assert "plan" in sol_cls.__init__.__code__.co_names or "plan" in sol_cls.__init__.__code__.co_varnames   # a solver keeps its plan alive
