@@ -743,26 +743,36 @@ struct TilePart {
 };
 void build_tiles_range(const HostPlan& P, int64_t ra, int64_t rb, int max_rows, int ucap, int nnzcap, int run_gap,
                        uint16_t* lcol, TilePart& out) {
-    std::vector<int32_t> stamp(P.n, -1), local(P.n, 0), cols, fresh;
+    // distinct columns of the tile under construction: one bit per node (12.5 KB at 100k nodes: cache resident);
+    // the sorted list a finished tile needs falls out of a scan over the words between its smallest and largest
+    // column instead of a sort (1.7 of the 4 ms this routine took at cfg4)
+    std::vector<uint64_t> bits(((size_t)P.n + 63) / 64, 0);
+    std::vector<int32_t> local(P.n, 0), cols, fresh;
     int64_t r0 = ra;
-    int t = 0;
     while (r0 < rb) {
         cols.clear();
+        int32_t cmin = INT32_MAX, cmax = -1;
         int64_t r1 = r0;
         while (r1 < rb && r1 - r0 < max_rows) {
             // distinct columns row r1 would add
             fresh.clear();
             for (int32_t q = P.rowptr[r1]; q < P.rowptr[r1 + 1]; ++q) {
                 const int32_t c = P.col[q];
-                if (stamp[c] != t) {
-                    stamp[c] = t;
+                uint64_t& w = bits[(size_t)c >> 6];
+                const uint64_t m = (uint64_t)1 << (c & 63);
+                if (!(w & m)) {
+                    w |= m;
                     fresh.push_back(c);
                 }
             }
             const bool fits = (int)(cols.size() + fresh.size()) <= ucap && P.rowptr[r1 + 1] - P.rowptr[r0] <= nnzcap;
             if (!fits) {
-                for (int32_t c : fresh) stamp[c] = -1;
+                for (int32_t c : fresh) bits[(size_t)c >> 6] &= ~((uint64_t)1 << (c & 63));
                 break;
+            }
+            for (int32_t c : fresh) {
+                cmin = std::min(cmin, c);
+                cmax = std::max(cmax, c);
             }
             cols.insert(cols.end(), fresh.begin(), fresh.end());
             ++r1;
@@ -771,7 +781,17 @@ void build_tiles_range(const HostPlan& P, int64_t ra, int64_t rb, int max_rows, 
             out.ok = false;
             return;
         }
-        std::sort(cols.begin(), cols.end());
+        {   // cols, ascending; the bits are cleared on the way
+            size_t k = 0;
+            for (size_t wi = (size_t)cmin >> 6; wi <= ((size_t)cmax >> 6); ++wi) {
+                uint64_t w = bits[wi];
+                bits[wi] = 0;
+                while (w) {
+                    cols[k++] = (int32_t)(wi * 64 + (size_t)__builtin_ctzll(w));
+                    w &= w - 1;
+                }
+            }
+        }
         // runs of (nearly) consecutive columns, one bulk copy each: columns separated by at most
         // `gap` unneeded rows share a run (fewer, larger copies at the price of a few extra rows);
         // the gap shrinks until the copied rows fit the cap
@@ -807,7 +827,6 @@ void build_tiles_range(const HostPlan& P, int64_t ra, int64_t rb, int max_rows, 
         out.umax = std::max<int>(out.umax, copied);
         out.nnzmax = std::max<int>(out.nnzmax, P.rowptr[r1] - P.rowptr[r0]);
         r0 = r1;
-        ++t;
     }
 }
 }  // namespace
@@ -816,16 +835,19 @@ void build_tiles(const HostPlan& P, int max_rows, int ucap, int nnzcap, HostTile
     int run_gap = 2;
     if (const char* e = getenv("SIGSDP_RUN_GAP")) run_gap = std::max(0, atoi(e));
     const int64_t n = P.n;
+    StageTimer tm;
     T = HostTiles();
     T.max_rows = max_rows;
     T.ucap = std::min(ucap, 65535);
     T.nnzcap = nnzcap;
-    T.lcol.assign(P.nnz + 16, 0);   // + padding the device copy needs (bulk copies read 16-byte supersets)
+    T.lcol.resize(P.nnz + 16);      // (not zero-filled: the range threads below touch their parts first)
+    std::fill(T.lcol.begin() + P.nnz, T.lcol.end(), (uint16_t)0);
     // Large graphs are cut into a FIXED number of row ranges tiled independently on the host
     // cores (fixed, not the core count: the tiling, and with it the order of the per-block
     // partial sums, is the same on every machine); a range boundary only ends a tile early.
     const int nchunks = n >= 32768 ? 16 : 1;
     std::vector<TilePart> parts(nchunks);
+    tm.lap("  tiles: lcol alloc");
     {
         std::atomic<int> next{0};
         auto work = [&] {
@@ -839,6 +861,7 @@ void build_tiles(const HostPlan& P, int max_rows, int ucap, int nnzcap, HostTile
         work();
         for (auto& x : th) x.join();
     }
+    tm.lap("  tiles: ranges");
     T.trow.push_back(0);
     T.rptr.push_back(0);
     for (const TilePart& pt : parts) {
@@ -866,6 +889,7 @@ void build_tiles(const HostPlan& P, int max_rows, int ucap, int nnzcap, HostTile
         r[7] = 0;
     }
     T.ok = true;
+    tm.lap("  tiles: merge");
 }
 
 int round_greedy_host(int64_t n, int Z, const int32_t* Sp, const int32_t* Si, const double* Sx,

@@ -61,7 +61,7 @@ struct HostTiles {
     std::vector<int32_t> ucnt;   // ntiles: distinct columns
     std::vector<int32_t> rptr;   // ntiles + 1: runs of consecutive distinct columns
     std::vector<int32_t> runs;   // 4 ints per run: first column, first slot, length, 0
-    std::vector<uint16_t> lcol;  // nnz
+    hvec<uint16_t> lcol;         // nnz (+ 16 zeros: the device copy is read in 16-byte supersets)
     std::vector<int32_t> trec;   // 8 ints per tile: r0, r1, p0, p1, run0, run1, distinct columns, 0
 };
 void build_tiles(const HostPlan& P, int max_rows, int ucap, int nnzcap, HostTiles& out);
