@@ -106,15 +106,19 @@ void locality_order_inputs(int64_t n, const int32_t* Sp, const int32_t* Si, cons
     size_t fhead = 0;
     std::vector<int32_t> q;
     q.reserve(cluster + 8);
+    // seen: 0 new, 1 placed in a cluster, 2 waiting in the frontier (queued once: a node's later occurrences in the
+    // FIFO would be skipped anyway, because the first one is popped first and places it)
     auto visit = [&](int32_t v) {
         if ((uint32_t)v >= (uint32_t)n) return;   // (the walk starts before the index checks of validate_state finish)
-        if (seen[v]) return;
+        const uint8_t sv = seen[v];
+        if (sv == 1) return;
         if ((int)q.size() < cluster) {
             seen[v] = 1;
             q.push_back(v);
             __builtin_prefetch(Sp + v);   // its row pointers now, its rows when it is two pops away:
             __builtin_prefetch(Qp + v);   // the walk is bound by the latency of these scattered reads
-        } else {
+        } else if (sv == 0) {
+            seen[v] = 2;
             frontier.push_back(v);
         }
     };
@@ -123,7 +127,7 @@ void locality_order_inputs(int64_t n, const int32_t* Sp, const int32_t* Si, cons
         frontier.push_back((int32_t)start);
         while (fhead < frontier.size()) {
             const int32_t seed = frontier[fhead++];
-            if (seen[seed]) continue;
+            if (seen[seed] == 1) continue;
             q.clear();
             q.push_back(seed);
             seen[seed] = 1;
