@@ -77,6 +77,10 @@ void sigsdp_plan_destroy(sigsdp_plan* plan);
  * the host language) instead of every process building the same plan side by side on a share of the cores.  The
  * image only skips the host build; the inputs are still needed (host copies for the rounding entry points).  An
  * image that does not describe an n-node plan is rejected (SIGSDP_EINVAL). */
+/* 1 when sigsdp_plan_create would build an n-node plan on the device (large graph, device >= 0, not overridden by
+ * SIGSDP_PLAN_BUILDER=host), 0 when on the host cores: the host side of a multi-GPU launch lets every rank build its
+ * own plan in the first case and broadcasts rank 0's image in the second. */
+int sigsdp_plan_builds_on_device(int64_t n, int device);
 int sigsdp_plan_image_size(const sigsdp_plan* plan, int64_t* bytes);
 int sigsdp_plan_image(const sigsdp_plan* plan, void* image_host);
 int sigsdp_plan_create_from_image(int64_t n,

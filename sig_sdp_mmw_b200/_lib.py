@@ -39,6 +39,7 @@ def load():
     lib.sigsdp_device_count.restype = C.c_int
     sigs = {
         "sigsdp_plan_create": [C.c_int64, i32p, i32p, f64p, i32p, i32p, f64p, f64p, C.c_int, C.c_int, C.POINTER(vp)],
+        "sigsdp_plan_builds_on_device": [C.c_int64, C.c_int],
         "sigsdp_plan_image_size": [vp, i64p],
         "sigsdp_plan_image": [vp, vp],
         "sigsdp_plan_create_from_image": [C.c_int64, i32p, i32p, f64p, i32p, i32p, f64p, f64p, vp, C.c_int64, C.c_int, C.POINTER(vp)],
@@ -195,11 +196,13 @@ class Plan:
         """One plan per rank of a torch.distributed job on one box.  With few ranks every rank builds its own (the
         cores are shared: 8 each at 2 ranks); from `min_world` ranks on, rank 0 builds it ONCE on all host cores and
         the image travels by broadcast (NCCL: pinned host -> device -> peers -> pinned host), which the other ranks
-        import -- instead of 8 builds side by side on 2 cores each."""
+        import -- instead of 8 builds side by side on 2 cores each.  A graph large enough for the device-side builder
+        (sigsdp_plan_builds_on_device) is always built per rank: each GPU builds its own copy, the host cores only
+        stage the inputs and run the locality ordering (one thread per rank)."""
         import torch
         import torch.distributed as dist
         world = dist.get_world_size(group)
-        if world < min_world:
+        if world < min_world or load().sigsdp_plan_builds_on_device(int(state[0].shape[0]), int(device)) == 1:
             return Plan(state, device=device, order=order)
         rank = dist.get_rank(group)
         nccl = dist.get_backend(group) == "nccl"

@@ -868,6 +868,8 @@ int sigsdp_plan_create(int64_t n, const int32_t* Sp, const int32_t* Si, const do
     return plan_finish(pl, n, Sp, Si, Sx, Qp, Qi, Qx, h_max, device, out);
 }
 
+int sigsdp_plan_builds_on_device(int64_t n, int device) { return use_device_builder(n, device) ? 1 : 0; }
+
 int sigsdp_plan_image_size(const sigsdp_plan* plan, int64_t* bytes) {
     if (!plan || !bytes) return fail(SIGSDP_EINVAL, "null argument");
     { const int rc_full = plan_host_full(plan); if (rc_full != SIGSDP_OK) return rc_full; }
