@@ -212,15 +212,15 @@ def chebyshev_filtered_lanczos(matmat, n, k, v0, native_steps, set_filter, tol=1
          returned lambda must lie above `cut` (p is monotone only there: that makes the top k of p(M) the top k of M).
 
     Returns (lam, V, info) like thick_restart_lanczos(which='LM'), or None when the filter is not applicable (probe
-    breakdown, spectrum not safely one-sided, checks failed, no convergence within max_restarts): the caller then runs
-    the unfiltered solver.  set_filter(degree, lo, cut) switches the operator behind native_steps (degree 0: off)."""
+    breakdown, 2k > probe_steps, spectrum not safely one-sided, checks failed, no progress after 4 restarts, no
+    convergence within max_restarts): the caller then runs the unfiltered solver.  set_filter(degree, lo, cut) switches the operator behind native_steps (degree 0: off)."""
     import time as _t
     dev = v0.device
     t_all = _t.perf_counter()
     m1 = int(probe_steps)
     m = int(ncv if ncv is not None else max(2 * k + 20, 48))
-    if native_steps is None or n < 4 * max(m, m1) or k >= m - 1:
-        return None
+    if native_steps is None or n < 4 * max(m, m1) or k >= m - 1 or 2 * k > m1:
+        return None      # (2k > probe steps: too few Ritz values above the wanted ones to place the cut)
     target = float(count_target if count_target is not None else 3 * k)
     set_filter(0, 0.0, 1.0)
     Q1 = torch.zeros((m1 + 1, n), dtype=torch.float64, device=dev)
@@ -235,7 +235,7 @@ def chebyshev_filtered_lanczos(matmat, n, k, v0, native_steps, set_filter, tol=1
     th, S = _small_eigh(Tm)
     lo = float(th[0] - be_h[-1])
     cum = np.cumsum((n * S[0] ** 2)[::-1])
-    i = int(min(np.searchsorted(cum, target), m1 - k))
+    i = int(min(np.searchsorted(cum, target), m1 - k))       # (never below the probe's k-th Ritz value from the bottom)
     cut = float(th[::-1][i])
     # one-sided: everything below -cut would be a large-|lambda| pair the filter cannot see
     if not (cut > lo and lo > -cut and cut - lo > 1e-8 * max(abs(cut), abs(lo))):
@@ -252,8 +252,14 @@ def chebyshev_filtered_lanczos(matmat, n, k, v0, native_steps, set_filter, tol=1
 
     found = {}
     checks = [0]
+    calls = [0]
 
     def accept(theta_want, resid, scale, ritz_rows):
+        calls[0] += 1
+        if calls[0] >= 4 and not np.all(resid <= 1e-3 * scale):
+            # a good cut converges within 2-3 restarts; this one is not getting anywhere (cut above the wanted
+            # eigenvalues, or a spectrum the filter does not separate): stop paying for it
+            raise _FilterUnusable("no progress after %d restarts" % calls[0])
         if not np.all(resid <= 10.0 * tol * scale):
             return False
         checks[0] += 1

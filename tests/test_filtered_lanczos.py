@@ -116,6 +116,11 @@ def test_filter_declines_on_probe_breakdown_and_small_problems():
     v0 = torch.from_numpy(np.random.RandomState(2).randn(n))
     nat = _EmulatedNative(M)
     assert chebyshev_filtered_lanczos(nat.matmat, n, 5, v0, nat.steps, nat.set_filter) is None
+    M3, _ = _clustered_top_matrix(3000, 6)
+    nat3 = _EmulatedNative(M3)
+    v3 = torch.from_numpy(np.random.RandomState(2).randn(3000))
+    assert chebyshev_filtered_lanczos(nat3.matmat, 3000, 40, v3, nat3.steps, nat3.set_filter, probe_steps=60) is None   # 2k > probe
+    assert nat3.spmv == 0
     M2, _ = _clustered_top_matrix(150, 4)
     nat2 = _EmulatedNative(M2)
     v2 = torch.from_numpy(np.random.RandomState(2).randn(150))
