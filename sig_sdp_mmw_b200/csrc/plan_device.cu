@@ -440,6 +440,17 @@ int build_device_plan(int64_t n64, const int32_t* Sp, const int32_t* Si, const d
     tm.lap("union fill");
     k_mirror<<<blocks, T256, 0, st>>>(n, rowptr0, col0, eid0, flags);
 
+    // the host copies of the pattern are allocated and their pages touched now, on the idle cores, while the device works
+    // and the locality ordering is still running: the copy at the end then lands in mapped memory
+    P.rowptr.resize(n + 1);
+    P.col.resize(nnz);
+    P.dpos.resize(n);
+    P.S_sum.resize(n);
+    P.tnorm.resize(n);
+    P.h_max.resize(n);
+    parallel_for((nnz + 1023) / 1024, [&](int64_t b, int64_t e) {
+        for (int64_t i = b; i < e; ++i) P.col[(size_t)i * 1024] = 0;
+    }, 64);
     tm.lap("mirror ids");
     // ---- the kernels' numbering
     P.perm.resize(n);
@@ -497,12 +508,6 @@ int build_device_plan(int64_t n64, const int32_t* Sp, const int32_t* Si, const d
             err = "internal: asymmetric union pattern";
             return SIGSDP_EINVAL;
         }
-        P.rowptr.resize(n + 1);
-        P.col.resize(nnz);
-        P.dpos.resize(n);
-        P.S_sum.resize(n);
-        P.tnorm.resize(n);
-        P.h_max.resize(n);
         parallel_copy({{P.rowptr.data(), stage + h_rowptr, (size_t)(n + 1) * 4}, {P.col.data(), stage + h_col, (size_t)nnz * 4},
                        {P.dpos.data(), stage + h_dpos, (size_t)n * 4}, {P.S_sum.data(), stage + h_ssum, (size_t)n * 8},
                        {P.tnorm.data(), stage + h_tnorm, (size_t)n * 8}, {P.h_max.data(), stage + h_hm, (size_t)n * 8}});
