@@ -49,6 +49,14 @@ const char* sigsdp_last_error(void);
 int sigsdp_version(void);
 /* number of CUDA devices visible, or a negative error */
 int sigsdp_device_count(void);
+/* The next `count` numbers of numpy's legacy normal stream (np.random.randn / RandomState.standard_normal: MT19937 ->
+ * 53-bit doubles -> polar method), bit for bit, produced on all host cores (the Mersenne Twister runs sequentially, the
+ * candidate pairs -- four output words each, accepted or not -- are evaluated in parallel and compacted in order).
+ * The reference draws np.random.randn(K, D) once per iteration (mmw.py:226); an unchanged driver sees the same numbers
+ * 3-4x sooner.  key624 / pos / has_gauss / cached_gauss: np.random.get_state() on entry, the state numpy would be left
+ * in on exit (hand it to np.random.set_state). */
+int sigsdp_numpy_standard_normal(uint32_t* key624, int32_t* pos, int32_t* has_gauss, double* cached_gauss, int64_t count,
+                                 double* out_host);
 /* Position-weighted 64-bit checksum of a host buffer, computed on the builder's host threads.  The host side keys its
  * plan cache with it (the reference re-runs _process_state on every call, mmw.py:26-41; a caller of this library keeps
  * the plan while the state's buffers are unchanged).  bytes may be 0. */

@@ -45,6 +45,8 @@ def load():
         "sigsdp_plan_create_from_image": [C.c_int64, i32p, i32p, f64p, i32p, i32p, f64p, f64p, vp, C.c_int64, C.c_int, C.POINTER(vp)],
         "sigsdp_plan_info": [vp, i64p],
         "sigsdp_checksum": [vp, C.c_int64, C.POINTER(C.c_uint64)],
+        "sigsdp_numpy_standard_normal": [C.POINTER(C.c_uint32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_double),
+                                         C.c_int64, f64p],
         "sigsdp_plan_edges": [vp, i32p, i32p, f64p, f64p, i32p, i32p],
         "sigsdp_plan_vectors": [vp, f64p, f64p],
         "sigsdp_plan_perm": [vp, i32p],
@@ -119,6 +121,24 @@ def checksum(arr):
     out = C.c_uint64()
     check(load().sigsdp_checksum(arr.ctypes.data_as(C.c_void_p), int(arr.nbytes), C.byref(out)))
     return int(out.value)
+
+
+def numpy_randn_into(out):
+    """Fills the float64 array `out` (C order) with the numbers np.random.standard_normal(out.shape) would return next
+    on numpy's GLOBAL legacy stream and leaves that stream where numpy would have left it -- bit for bit, on all host
+    cores (sigsdp_numpy_standard_normal).  Falls back to numpy itself when the global generator is not MT19937."""
+    if out.dtype != np.float64 or not out.flags.c_contiguous:
+        raise ValueError("out must be a C-contiguous float64 array")
+    st = np.random.get_state()
+    if st[0] != "MT19937" or out.size == 0:
+        out[...] = np.random.standard_normal(out.shape)
+        return out
+    key = np.ascontiguousarray(st[1], dtype=np.uint32).copy()
+    pos, hg, g = C.c_int32(int(st[2])), C.c_int32(int(st[3])), C.c_double(float(st[4]))
+    check(load().sigsdp_numpy_standard_normal(key.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(pos), C.byref(hg), C.byref(g),
+                                              int(out.size), out.ctypes.data_as(C.POINTER(C.c_double))))
+    np.random.set_state(("MT19937", key, pos.value, hg.value, g.value))
+    return out
 
 
 def csr_arrays(M, canonicalize=True):

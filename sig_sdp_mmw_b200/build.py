@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 OUT = os.path.join(HERE, "libsigsdp_mmw.so")
-DEPS = ["mmw_api.cu", "mmw_inst.cu", "plan_host.cpp", "plan_device.cu", "mmw_device.cuh", "mmw_kernels.cuh", "plan_host.h",
+DEPS = ["mmw_api.cu", "mmw_inst.cu", "plan_host.cpp", "plan_device.cu", "numpy_stream.cpp", "mmw_device.cuh", "mmw_kernels.cuh", "plan_host.h",
         "plan_device.h",
         os.path.join("..", "..", "include", "sigsdp_mmw.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
@@ -32,7 +32,7 @@ def needs_build():
 
 
 def _units():
-    units = [("mmw_api.o", ["mmw_api.cu"]), ("plan_host.o", ["plan_host.cpp"]), ("plan_device.o", ["plan_device.cu"])]
+    units = [("mmw_api.o", ["mmw_api.cu"]), ("plan_host.o", ["plan_host.cpp"]), ("plan_device.o", ["plan_device.cu"]), ("numpy_stream.o", ["numpy_stream.cpp"])]
     for t, g in INSTANCES:
         tag = "%s_g%d" % ("f64" if t == "double" else "f32", g)
         units.append(("inst_%s.o" % tag, ["-DSIGSDP_T=%s" % t, "-DSIGSDP_G=%d" % g, "-DSIGSDP_NAME=ks_%s" % tag,

@@ -728,6 +728,14 @@ int sigsdp_device_count(void) {
     return n;
 }
 
+int sigsdp_numpy_standard_normal(uint32_t* key624, int32_t* pos, int32_t* has_gauss, double* cached_gauss, int64_t count,
+                                 double* out_host) {
+    if (!key624 || !pos || !has_gauss || !cached_gauss || count < 0 || (count > 0 && !out_host)) return fail(SIGSDP_EINVAL, "bad argument");
+    if (*pos < 0 || *pos > 624) return fail(SIGSDP_EINVAL, "pos outside [0, 624]");
+    numpy_legacy_normals(key624, pos, has_gauss, cached_gauss, count, out_host);
+    return SIGSDP_OK;
+}
+
 int sigsdp_checksum(const void* data_host, int64_t bytes, uint64_t* out) {
     if (!out || bytes < 0 || (!data_host && bytes > 0)) return fail(SIGSDP_EINVAL, "bad argument");
     *out = checksum_bytes(data_host, (size_t)bytes);

@@ -298,6 +298,9 @@ void shard_halo(const HostPlan& P, const std::vector<int32_t>& row0, int rank, S
     out.inc_p.insert(out.inc_p.end(), for_p.begin(), for_p.end());
 }
 
+void side_thread_begin() { g_side_threads.fetch_add(1); }
+void side_thread_end() { g_side_threads.fetch_sub(1); }
+
 void parallel_for(int64_t n, const std::function<void(int64_t, int64_t)>& fn, int64_t min_parallel) {
     parallel_rows(n, fn, min_parallel);
 }

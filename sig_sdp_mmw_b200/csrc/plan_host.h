@@ -98,8 +98,15 @@ struct CopySeg {
     size_t bytes;
 };
 void parallel_copy(const std::vector<CopySeg>& segs);
+// a sequential helper thread starts / ends next to the parallel stages (they leave it a core)
+void side_thread_begin();
+void side_thread_end();
 // fn(begin, end) over contiguous chunks of [0, n) on the builder's threads (serial below min_parallel items)
 void parallel_for(int64_t n, const std::function<void(int64_t, int64_t)>& fn, int64_t min_parallel = 4096);
+
+// numpy's legacy normal stream continued natively (numpy_stream.cpp): `count` numbers np.random.standard_normal would return
+// next, bit for bit; key (624 words) / pos / has_gauss / gauss are RandomState.get_state() on entry, the state after the draw on exit
+void numpy_legacy_normals(uint32_t* key, int32_t* pos, int32_t* has_gauss, double* gauss, int64_t count, double* out);
 
 // checksum of a buffer on the builder's threads (the plan cache's key, sdp_solver._plan_for)
 uint64_t checksum_bytes(const void* data, size_t bytes);

@@ -37,7 +37,7 @@ from .sdp_solver import sdp_solver
 from .stats import STATS_OBJECT
 
 # host staging budget for the numpy Omega stream (bytes per kernel launch)
-_OMEGA_CHUNK_BYTES = 1 << 30
+_OMEGA_CHUNK_BYTES = 96 << 20
 
 
 class _Laps:
@@ -234,20 +234,27 @@ class mmw(STATS_OBJECT, sdp_solver):
             if self.omega == "numpy" and not self.LOG_GAP:
                 step = max(1, min(nit, _OMEGA_CHUNK_BYTES // max(1, K * D * 8)))
             done = 0
+            ring, slot = None, 0
             wall_tic = self._get_tic()
             while done < nit:
                 cnt = min(step, nit - done)
                 if self.LOG_GAP:
                     self._add_np_log("gap", done, self._gap_row(solver, torch, dev))
                 if self.omega == "numpy":
-                    # the reference's stream: one randn(K, D) per iteration (mmw.py:226)
-                    om = np.empty((cnt, K, D))
-                    for i in range(cnt):
-                        om[i] = np.random.randn(K, D)
-                    om_d = torch.from_numpy(om).to(dev)
-                    solver.iterate(cnt, om_d.data_ptr(), 0, stream)
-                    torch.cuda.current_stream().synchronize()      # om_d must outlive the kernel
-                    del om_d
+                    # the reference's stream: one randn(K, D) per iteration (mmw.py:226), continued natively on all host
+                    # cores (bit for bit numpy's numbers, numpy's global state advanced as numpy would: _lib.numpy_randn_into)
+                    # into one of two pinned buffers, so the draw of the next chunk runs while this one is copied and
+                    # iterated on
+                    if ring is None:
+                        ring = [(torch.empty((step, K, D), dtype=torch.float64, pin_memory=True),
+                                 torch.empty((step, K, D), dtype=torch.float64, device=dev), torch.cuda.Event()) for _ in range(2)]
+                    host, om_d, ev = ring[slot]
+                    slot ^= 1
+                    ev.synchronize()                               # the copy that last read this pinned buffer is done
+                    _lib.numpy_randn_into(host.numpy()[:cnt])
+                    om_d[:cnt].copy_(host[:cnt], non_blocking=True)
+                    ev.record()
+                    solver.iterate(cnt, om_d.data_ptr(), 0, stream)  # (stream order keeps om_d alive until its kernel is done)
                 elif self.omega == "device":
                     solver.iterate(cnt, None, self.seed, stream)
                 else:
@@ -255,6 +262,7 @@ class mmw(STATS_OBJECT, sdp_solver):
                 done += cnt
                 self.N_STEP = done
             torch.cuda.current_stream().synchronize()
+            ring = None
             wall_us = self._get_tim(wall_tic)
 
             # per-iteration phase logs, device-timed (mmw.py:142,170,197,200)

@@ -304,3 +304,50 @@ def test_plan_is_destroyed_with_its_python_object():
     plan.__del__()                                   # idempotent
     sol_cls = _lib.Solver
     assert "plan" in sol_cls.__init__.__code__.co_names or "plan" in sol_cls.__init__.__code__.co_varnames   # a solver keeps its plan alive
+
+
+@pytest.mark.parametrize("seed,warm,shape", [
+    (0, 0, (7,)), (1, 1, (1000, 3)), (3, 0, (1,)), (4, 5, (2,)), (5, 2, (12345, 7)),
+    (6, 0, (3200001,)),              # several chunks, odd count: the last pair's second number stays cached
+    (7, 0, (411775,)), (8, 1, (823552,)),   # counts around one chunk's worth of accepted pairs
+    (9, 3, (3, 50000, 8)),
+])
+def test_native_numpy_normal_stream_is_numpys_bit_for_bit(seed, warm, shape, monkeypatch):
+    """sigsdp_numpy_standard_normal continues np.random's GLOBAL legacy stream (MT19937 -> doubles -> polar method,
+    mmw.py:226 draws np.random.randn(K, D) per iteration): same numbers as numpy, and numpy's state afterwards is what
+    numpy's own draw would have left (next normals AND next uniforms agree), whatever the host thread count."""
+    def numpys():
+        np.random.seed(seed)
+        if warm:
+            np.random.randn(warm)        # an odd warm-up leaves a cached second normal behind
+        return np.random.standard_normal(shape), np.random.randn(5), np.random.rand(3)
+
+    def ours():
+        np.random.seed(seed)
+        if warm:
+            np.random.randn(warm)
+        out = np.empty(shape)
+        _lib.numpy_randn_into(out)
+        return out, np.random.randn(5), np.random.rand(3)
+    ref = numpys()
+    for nt in (None, "1", "3"):
+        if nt:
+            monkeypatch.setenv("SIGSDP_HOST_THREADS", nt)
+        got = ours()
+        for a, b in zip(ref, got):
+            assert np.array_equal(a, b)
+
+
+def test_native_numpy_normal_stream_rejects_bad_buffers_and_other_generators():
+    with pytest.raises(ValueError):
+        _lib.numpy_randn_into(np.empty(4, np.float32))
+    with pytest.raises(ValueError):
+        _lib.numpy_randn_into(np.empty((4, 4))[:, ::2])
+    out = np.empty(0)
+    assert _lib.numpy_randn_into(out) is out                                  # nothing drawn, state untouched
+    lib = _lib.load()
+    key = np.zeros(624, np.uint32)
+    pos, hg, g = C.c_int32(700), C.c_int32(0), C.c_double(0.0)                # pos outside the twister block
+    rc = lib.sigsdp_numpy_standard_normal(key.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(pos), C.byref(hg), C.byref(g), 4,
+                                          np.empty(4).ctypes.data_as(C.POINTER(C.c_double)))
+    assert rc != 0
