@@ -489,6 +489,24 @@ def run_ours(args):
     e2e_s = time.perf_counter() - t0
     barrier()
     clocks = sampler.stop() if rank == 0 else None
+    # the same call in the parity mode an unchanged driver gets (omega="numpy": numpy's own randn(K, D) per iteration,
+    # drawn natively and bit for bit by sigsdp_numpy_standard_normal); one GPU only, a side figure next to `e2e`
+    parity_mode = None
+    if world == 1 and not args.no_parity_mode:
+        kw_np = dict(kw, omega="numpy")
+        np.random.seed(0)
+        mmw(nit=min(args.steps, 4), **kw_np).run_with_state(0, Z, state)   # warms the pinned ring buffers (same chunk size)
+        alg_np = mmw(nit=args.steps, **kw_np)
+        np.random.seed(0)
+        t0 = time.perf_counter()
+        alg_np.run_with_state(0, Z, state)
+        torch.cuda.synchronize()
+        t_np = time.perf_counter() - t0
+        parity_mode = {"value": args.steps / t_np, "unit": UNIT, "total_ms": t_np * 1e3,
+                       "what": "mmw(nit=K).run_with_state(state) with the default omega='numpy': the reference's own Omega stream "
+                               "(np.random.randn(K, D) per iteration, mmw.py:226) reproduced bit for bit, drawn on the host cores "
+                               "and shipped over PCIe (%d MB per iteration)" % (state[0].shape[0] * D * 8 // 1000000)}
+        del alg_np
     S, Q, h = state
     h2d = (S.indptr.nbytes + S.indices.nbytes + S.data.nbytes + Q.indptr.nbytes + Q.indices.nbytes + Q.data.nbytes + h.nbytes)
     d2h = X_half.nbytes
@@ -551,6 +569,8 @@ def run_ours(args):
             line["cpu_baseline"] = cpu
         if parity is not None:
             line["parity"] = parity
+        if parity_mode is not None:
+            line["e2e_parity_mode"] = parity_mode
         if tte is not None:
             line["time_to_eps"] = tte
         print(json.dumps(line))
@@ -584,6 +604,7 @@ def main():
     ap.add_argument("--mode", default="fused", choices=["fused", "stepwise"],
                     help="stepwise = one kernel per phase / Taylor term (profiling only, not a bench value)")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs: only the device-timed region")
+    ap.add_argument("--no-parity-mode", action="store_true", help="skip the omega='numpy' end-to-end side figure")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.workload == "cfg5_batch":
