@@ -118,14 +118,13 @@ void numpy_legacy_normals(uint32_t* key, int32_t* pos, int32_t* has_gauss, doubl
     static std::mutex mu;   // the scratch below is kept between calls (one draw at a time: numpy's global stream is one)
     std::lock_guard<std::mutex> lock(mu);
     static Chunk ch[2];
-    static hvec<double> first, second;   // f * x2 (returned first), f * x1 (cached, returned second)
+    static hvec<double> packed;          // per compaction block, dense: (f * x2, f * x1) of its accepted pairs, in order
     static std::vector<uint8_t> ok;
     static std::vector<int64_t> blk_cnt;
     if (ok.empty()) {
         ch[0].words.resize((size_t)CH * 4);
         ch[1].words.resize((size_t)CH * 4);
-        first.resize((size_t)CH);
-        second.resize((size_t)CH);
+        packed.resize((size_t)CH * 2);
         ok.resize((size_t)CH);
         blk_cnt.resize((size_t)(CH / BLK) + 2);
     }
@@ -168,6 +167,7 @@ void numpy_legacy_normals(uint32_t* key, int32_t* pos, int32_t* has_gauss, doubl
             for (int64_t b = b0; b < b1; ++b) {
                 const int64_t p0 = b * BLK, p1 = std::min(cand, p0 + BLK);
                 int64_t n_acc = 0;
+                double* dst = packed.data() + 2 * p0;
                 for (int64_t p = p0; p < p1; ++p) {
                     const uint32_t* w = words + 4 * p;
                     const double x1 = 2.0 * to_double(w[0], w[1]) - 1.0;
@@ -177,8 +177,8 @@ void numpy_legacy_normals(uint32_t* key, int32_t* pos, int32_t* has_gauss, doubl
                     ok[p] = acc;
                     if (acc) {
                         const double f = std::sqrt(-2.0 * std::log(r2) / r2);   // legacy_gauss, same expression order
-                        first[p] = f * x2;
-                        second[p] = f * x1;
+                        dst[2 * n_acc] = f * x2;       // returned first
+                        dst[2 * n_acc + 1] = f * x1;   // numpy caches it and returns it next
                         ++n_acc;
                     }
                 }
@@ -196,6 +196,7 @@ void numpy_legacy_normals(uint32_t* key, int32_t* pos, int32_t* has_gauss, doubl
         blk_cnt[nblk] = run;
         const int64_t take = std::min<int64_t>(run, want);    // accepted pairs of this chunk that are used
         int64_t last_pair = cand - 1;                          // candidate index of the last used pair
+        double last_second = 0.0;                              // its second number
         if (run >= want) {
             int64_t b = 0;
             while (blk_cnt[b + 1] < want) ++b;
@@ -203,22 +204,19 @@ void numpy_legacy_normals(uint32_t* key, int32_t* pos, int32_t* has_gauss, doubl
             for (int64_t p = b * BLK;; ++p)
                 if (ok[p] && ++seen == want) {
                     last_pair = p;
+                    last_second = packed[(size_t)(2 * b * BLK + 2 * (want - blk_cnt[b] - 1) + 1)];
                     break;
                 }
         }
         const int64_t base = written + 2 * found;
-        parallel_for(nblk, [&](int64_t b0, int64_t b1) {
+        parallel_for(nblk, [&](int64_t b0, int64_t b1) {   // the blocks' dense runs, end to end
             for (int64_t b = b0; b < b1; ++b) {
-                int64_t q = blk_cnt[b];
+                const int64_t q = blk_cnt[b];
                 if (q >= take) break;
-                const int64_t p0 = b * BLK, p1 = std::min(cand, p0 + BLK);
-                for (int64_t p = p0; p < p1 && q < take; ++p)
-                    if (ok[p]) {
-                        const int64_t o = base + 2 * q;
-                        out[o] = first[p];
-                        if (o + 1 < count) out[o + 1] = second[p];
-                        ++q;
-                    }
+                const int64_t pairs = std::min(blk_cnt[b + 1], take) - q;
+                const int64_t o = base + 2 * q;
+                const int64_t doubles = std::min<int64_t>(2 * pairs, count - o);   // (an odd count drops the very last second number)
+                std::memcpy(out + o, packed.data() + 2 * b * BLK, (size_t)doubles * sizeof(double));
             }
         }, 2);
         auto t2 = now();
@@ -232,7 +230,7 @@ void numpy_legacy_normals(uint32_t* key, int32_t* pos, int32_t* has_gauss, doubl
             tw.skip((size_t)(last_pair + 1 - g * c.seg_pairs) * 4);
             if (odd) {
                 *has_gauss = 1;
-                *gauss = second[last_pair];
+                *gauss = last_second;
             }
             break;
         }
