@@ -351,3 +351,36 @@ def test_native_numpy_normal_stream_rejects_bad_buffers_and_other_generators():
     rc = lib.sigsdp_numpy_standard_normal(key.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(pos), C.byref(hg), C.byref(g), 4,
                                           np.empty(4).ctypes.data_as(C.POINTER(C.c_double)))
     assert rc != 0
+
+
+@pytest.mark.timeout(120)
+def test_worker_pool_survives_fork_and_concurrent_callers():
+    """The parallel stages run on a pool of sleeping workers: a forked child (which has none of the parent's threads)
+    must start its own instead of waiting for workers that do not exist, and host threads calling at the same time
+    must all get the right answer (one uses the pool, the others plain threads)."""
+    import threading
+    a = np.random.RandomState(0).rand(2_000_000)
+    ref = _lib.checksum(a)                                   # the pool exists now
+    pid = os.fork()
+    if pid == 0:
+        ok = _lib.checksum(a) == ref
+        b = np.empty(300000)
+        np.random.seed(1)
+        _lib.numpy_randn_into(b)
+        np.random.seed(1)
+        ok = ok and np.array_equal(b, np.random.standard_normal(300000))
+        os._exit(0 if ok else 3)
+    _, status = os.waitpid(pid, 0)
+    assert os.WIFEXITED(status) and os.WEXITSTATUS(status) == 0
+    assert _lib.checksum(a) == ref
+    res = []
+
+    def work():
+        for _ in range(40):
+            res.append(_lib.checksum(a) == ref)
+    th = [threading.Thread(target=work) for _ in range(4)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert len(res) == 160 and all(res)
