@@ -943,19 +943,9 @@ void build_tiles(const HostPlan& P, int max_rows, int ucap, int nnzcap, HostTile
     const int nchunks = n >= 32768 ? 16 : 1;
     std::vector<TilePart> parts(nchunks);
     tm.lap("  tiles: lcol alloc");
-    {
-        std::atomic<int> next{0};
-        auto work = [&] {
-            for (int c = next.fetch_add(1); c < nchunks; c = next.fetch_add(1))
-                build_tiles_range(P, n * c / nchunks, n * (c + 1) / nchunks, max_rows, T.ucap, nnzcap, run_gap,
-                                  T.lcol.data(), parts[c]);
-        };
-        const unsigned nt = std::min<unsigned>(host_threads(), (unsigned)nchunks);
-        std::vector<std::thread> th;
-        for (unsigned i = 1; i < nt; ++i) th.emplace_back(work);
-        work();
-        for (auto& x : th) x.join();
-    }
+    run_tasks(std::min<unsigned>(host_threads(), (unsigned)nchunks), nchunks, [&](int64_t c) {
+        build_tiles_range(P, n * c / nchunks, n * (c + 1) / nchunks, max_rows, T.ucap, nnzcap, run_gap, T.lcol.data(), parts[c]);
+    });
     tm.lap("  tiles: ranges");
     T.trow.push_back(0);
     T.rptr.push_back(0);
