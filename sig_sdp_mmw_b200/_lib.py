@@ -2,6 +2,7 @@
 fallback: if the library is missing or a call fails, this raises."""
 import ctypes as C
 import os
+import threading
 
 import numpy as np
 
@@ -123,21 +124,25 @@ def checksum(arr):
     return int(out.value)
 
 
+_randn_lock = threading.Lock()
+
+
 def numpy_randn_into(out):
     """Fills the float64 array `out` (C order) with the numbers np.random.standard_normal(out.shape) would return next
     on numpy's GLOBAL legacy stream and leaves that stream where numpy would have left it -- bit for bit, on all host
     cores (sigsdp_numpy_standard_normal).  Falls back to numpy itself when the global generator is not MT19937."""
     if out.dtype != np.float64 or not out.flags.c_contiguous:
         raise ValueError("out must be a C-contiguous float64 array")
-    st = np.random.get_state()
-    if st[0] != "MT19937" or out.size == 0:
-        out[...] = np.random.standard_normal(out.shape)
-        return out
-    key = np.ascontiguousarray(st[1], dtype=np.uint32).copy()
-    pos, hg, g = C.c_int32(int(st[2])), C.c_int32(int(st[3])), C.c_double(float(st[4]))
-    check(load().sigsdp_numpy_standard_normal(key.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(pos), C.byref(hg), C.byref(g),
-                                              int(out.size), out.ctypes.data_as(C.POINTER(C.c_double))))
-    np.random.set_state(("MT19937", key, pos.value, hg.value, g.value))
+    with _randn_lock:      # get_state ... set_state is one draw: two threads of this process must not interleave there
+        st = np.random.get_state()
+        if st[0] != "MT19937" or out.size == 0:
+            out[...] = np.random.standard_normal(out.shape)
+            return out
+        key = np.ascontiguousarray(st[1], dtype=np.uint32).copy()
+        pos, hg, g = C.c_int32(int(st[2])), C.c_int32(int(st[3])), C.c_double(float(st[4]))
+        check(load().sigsdp_numpy_standard_normal(key.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(pos), C.byref(hg), C.byref(g),
+                                                  int(out.size), out.ctypes.data_as(C.POINTER(C.c_double))))
+        np.random.set_state(("MT19937", key, pos.value, hg.value, g.value))
     return out
 
 
