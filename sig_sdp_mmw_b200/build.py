@@ -28,11 +28,11 @@ def needs_build():
     if not os.path.exists(OUT):
         return True
     t = os.path.getmtime(OUT)
-    return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
+    return os.path.getmtime(os.path.abspath(__file__)) > t or any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
 
 
 def _units():
-    units = [("mmw_api.o", ["mmw_api.cu"]), ("plan_host.o", ["plan_host.cpp"]), ("plan_device.o", ["plan_device.cu"]), ("numpy_stream.o", ["numpy_stream.cpp"])]
+    units = [("mmw_api.o", ["mmw_api.cu"]), ("plan_host.o", ["plan_host.cpp"]), ("plan_device.o", ["plan_device.cu"]), ("numpy_stream.o", ["-Xcompiler", "-ffp-contract=off", "numpy_stream.cpp"])]   # (no fused multiply-add: numpy rounds every product)
     for t, g in INSTANCES:
         tag = "%s_g%d" % ("f64" if t == "double" else "f32", g)
         units.append(("inst_%s.o" % tag, ["-DSIGSDP_T=%s" % t, "-DSIGSDP_G=%d" % g, "-DSIGSDP_NAME=ks_%s" % tag,

@@ -87,6 +87,41 @@ struct Twister {
 inline double to_double(uint32_t a, uint32_t b) {   // mt19937_next_double
     return ((a >> 5) * 67108864.0 + (b >> 6)) / 9007199254740992.0;
 }
+// One compaction block of candidate pairs in four passes, so that everything except the libm logarithm vectorises
+// (conversions, products, the divide and the square root are correctly rounded whether scalar or SIMD, so the numbers
+// are the ones numpy's scalar loop produces):
+//   1. x1, x2, r2 of every candidate (vector)            2. accepted candidates packed densely (branch-free scalar)
+//   3. log(r2) of the accepted ones (scalar libm)        4. f = sqrt(-2 log(r2) / r2), (f x2, f x1) written out (vector)
+__attribute__((target_clones("avx512f", "avx2", "default"))) void pairs_xy(const uint32_t* w, int64_t n, double* x1, double* x2, double* r2) {
+    for (int64_t p = 0; p < n; ++p) {
+        const double a = 2.0 * (((w[4 * p] >> 5) * 67108864.0 + (w[4 * p + 1] >> 6)) / 9007199254740992.0) - 1.0;
+        const double b = 2.0 * (((w[4 * p + 2] >> 5) * 67108864.0 + (w[4 * p + 3] >> 6)) / 9007199254740992.0) - 1.0;
+        x1[p] = a;
+        x2[p] = b;
+        r2[p] = a * a + b * b;
+    }
+}
+inline int64_t pairs_pack(int64_t n, double* x1, double* x2, double* r2, uint8_t* ok) {   // in place: j <= p always
+    int64_t j = 0;
+    for (int64_t p = 0; p < n; ++p) {
+        const double r = r2[p];
+        const bool acc = !(r >= 1.0 || r == 0.0);
+        ok[p] = acc;
+        x1[j] = x1[p];
+        x2[j] = x2[p];
+        r2[j] = r;
+        j += acc;
+    }
+    return j;
+}
+__attribute__((target_clones("avx512f", "avx2", "default"))) void pairs_out(int64_t n, const double* x1, const double* x2, const double* r2,
+                                                                            const double* lg, double* dst) {
+    for (int64_t j = 0; j < n; ++j) {
+        const double f = std::sqrt(-2.0 * lg[j] / r2[j]);   // legacy_gauss: sqrt(-2.0 * log(r2) / r2)
+        dst[2 * j] = f * x2[j];        // returned first
+        dst[2 * j + 1] = f * x1[j];    // numpy caches it and returns it next
+    }
+}
 
 }  // namespace
 
@@ -119,12 +154,14 @@ void numpy_legacy_normals(uint32_t* key, int32_t* pos, int32_t* has_gauss, doubl
     std::lock_guard<std::mutex> lock(mu);
     static Chunk ch[2];
     static hvec<double> packed;          // per compaction block, dense: (f * x2, f * x1) of its accepted pairs, in order
+    static hvec<double> scratch;         // per compaction block: x1 | x2 | r2 | log r2
     static std::vector<uint8_t> ok;
     static std::vector<int64_t> blk_cnt;
     if (ok.empty()) {
         ch[0].words.resize((size_t)CH * 4);
         ch[1].words.resize((size_t)CH * 4);
         packed.resize((size_t)CH * 2);
+        scratch.resize((size_t)CH * 4);
         ok.resize((size_t)CH);
         blk_cnt.resize((size_t)(CH / BLK) + 2);
     }
@@ -166,22 +203,15 @@ void numpy_legacy_normals(uint32_t* key, int32_t* pos, int32_t* has_gauss, doubl
         parallel_for(nblk, [&](int64_t b0, int64_t b1) {
             for (int64_t b = b0; b < b1; ++b) {
                 const int64_t p0 = b * BLK, p1 = std::min(cand, p0 + BLK);
-                int64_t n_acc = 0;
                 double* dst = packed.data() + 2 * p0;
-                for (int64_t p = p0; p < p1; ++p) {
-                    const uint32_t* w = words + 4 * p;
-                    const double x1 = 2.0 * to_double(w[0], w[1]) - 1.0;
-                    const double x2 = 2.0 * to_double(w[2], w[3]) - 1.0;
-                    const double r2 = x1 * x1 + x2 * x2;
-                    const bool acc = !(r2 >= 1.0 || r2 == 0.0);
-                    ok[p] = acc;
-                    if (acc) {
-                        const double f = std::sqrt(-2.0 * std::log(r2) / r2);   // legacy_gauss, same expression order
-                        dst[2 * n_acc] = f * x2;       // returned first
-                        dst[2 * n_acc + 1] = f * x1;   // numpy caches it and returns it next
-                        ++n_acc;
-                    }
-                }
+                double* x1 = scratch.data() + 4 * p0;   // the block's own slice: x1 | x2 | r2 | log r2
+                double* x2 = x1 + BLK;
+                double* r2 = x2 + BLK;
+                double* lg = r2 + BLK;
+                pairs_xy(words + 4 * p0, p1 - p0, x1, x2, r2);
+                const int64_t n_acc = pairs_pack(p1 - p0, x1, x2, r2, ok.data() + p0);
+                for (int64_t j = 0; j < n_acc; ++j) lg[j] = std::log(r2[j]);
+                pairs_out(n_acc, x1, x2, r2, lg, dst);
                 blk_cnt[b] = n_acc;
             }
         }, 2);
