@@ -270,12 +270,12 @@ class mmw(STATS_OBJECT, sdp_solver):
             pt = solver.phase_times(cnt) if self.mode == _lib.MODE_FUSED else np.zeros((cnt, 4))
             if not pt.any():
                 pt = np.full((cnt, 4), wall_us / max(nit, 1) / 4.0)
-            for i in range(cnt):
-                it = nit - cnt + i
-                self._add_np_log("mmw_dual", it, np.array([Z, K, pt[i, 0]]))
-                self._add_np_log("mmw_loss", it, np.array([Z, K, pt[i, 1]]))
-                self._add_np_log("mmw_expm", it, np.array([Z, K, pt[i, 2] + pt[i, 3]]))
-                self._add_np_log("mmw_per_it", it, np.array([Z, K, pt[i].sum()]))
+            its = np.arange(nit - cnt, nit)
+            zk = np.tile(np.array([float(Z), float(K)]), (cnt, 1))
+            self._add_np_log_rows("mmw_dual", its, np.column_stack((zk, pt[:, 0])))
+            self._add_np_log_rows("mmw_loss", its, np.column_stack((zk, pt[:, 1])))
+            self._add_np_log_rows("mmw_expm", its, np.column_stack((zk, pt[:, 2] + pt[:, 3])))
+            self._add_np_log_rows("mmw_per_it", its, np.column_stack((zk, pt.sum(axis=1))))
 
             # final factor (mmw.py:202-216): top-r |lambda| eigenpairs of X_avgd / nit
             tic_xavg = self._get_tic()

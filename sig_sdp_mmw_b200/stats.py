@@ -48,6 +48,22 @@ class STATS_OBJECT:
         assert row.size + LOGGED_NP_DATA_HEADER_SIZE == logs[key].shape[1]
         logs[key] = np.vstack((logs[key], np.hstack(([g_step, step, _time.time()], row))))
 
+    def _add_np_log_rows(self, key, steps, rows, g_step=0):
+        """Many rows of one key at once (same layout as _add_np_log, one timestamp for the block): the per-iteration
+        phase logs of a solve are written after it, and one vstack per row is 12 us x 4 keys x nit."""
+        logs = self._stats()["LOGGED_NP_DATA"]
+        rows = np.asarray(rows, dtype=np.float64)
+        steps = np.asarray(steps, dtype=np.float64)
+        assert rows.ndim == 2 and steps.shape == (rows.shape[0],)
+        if key not in logs:
+            logs[key] = np.zeros((0, rows.shape[1] + LOGGED_NP_DATA_HEADER_SIZE))
+        assert rows.shape[1] + LOGGED_NP_DATA_HEADER_SIZE == logs[key].shape[1]
+        head = np.empty((rows.shape[0], LOGGED_NP_DATA_HEADER_SIZE))
+        head[:, 0] = g_step
+        head[:, 1] = steps
+        head[:, 2] = _time.time()
+        logs[key] = np.vstack((logs[key], np.hstack((head, rows))))
+
     def save_np(self, path, postfix):
         os.makedirs(path, exist_ok=True)
         name = self.LOGGED_CLASS_NAME or self.__class__.__name__
